@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- batched QTTT env-steps/sec on B200 (and % of the HBM roofline) next to the
+reference's CPU path timed on the host cores.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--envs E]
+
+One bench *step* is one pass of the hot path over one batch: ``reset`` + 9 ``step`` calls
+(kernel K1) that play E games from the empty board to termination on pre-generated
+random-legal actions and forced collapse coins (config 2 of BASELINE.json scaled to fill the
+GPU: E = 2^24 envs per GPU; the literal 4096-env config is reported under ``extra``).  The
+metric counts *accepted* moves only (an env-step = one accepted make_move; finished games
+idle as illegal no-ops and are not counted).
+
+``value``  : inputs already resident in HBM when the timed region starts.
+``e2e``    : the same pass through the public API with pinned HOST buffers
+             (BatchedEnv.step_host): actions + coins copied host->device and reward / done /
+             legal mask copied device->host inside the timed region, every ply.
+``roofline``: kernel k_step, 47 algorithmic bytes per env-step,
+             duration from CUDA events around every launch in the timed region.
+``cpu_baseline``: the Python oracle port on all host cores (N=1, rank 0 only).
+
+Multi-GPU (torchrun, one rank per GPU): every rank plays its own E games (weak scaling, no
+data-path collective); the only collective is one all_reduce(SUM) of the win/draw tallies of
+the self-play sweep reported under ``extra`` (NCCL).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "batched QTTT env-steps/sec"
+UNIT = "env-steps/s"
+BYTES_PER_STEP = 47            # 16 state in + 16 out + 1 action + 1 coin + 4 reward + 1 done + 8 mask
+BYTES_PER_BOARD_QEVAL = 33     # 16 state + 1 action + 2 x 8 boards
+PLIES = 9
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.path = f"/tmp/qttt_clocks_{os.getpid()}.csv"
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [c for c in sm if c >= 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path on the host cores.  The reference is
+    pure Python and is not present on the GPU box, so this times the Python oracle port
+    (oracle/qttt_oracle.py) with the config-1 loop on every core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_baseline as B
+    cores = os.cpu_count() or 1
+    games_per_proc = args.ref_games
+    pool = B.PersistentPool(cores)
+    for w in range(args.warmup):
+        pool.step(max(50, games_per_proc // 10), 1000 + w)
+    steps_total, t_total = 0, 0.0
+    for k in range(args.steps):
+        s, wall = pool.step(games_per_proc, 2000 + k)
+        steps_total += s
+        t_total += wall
+    pool.close()
+    value = steps_total / t_total
+    sample = (f"config-1 loop (one Env per process, random.choice over legal pairs until terminated), "
+              f"{games_per_proc} games per process per step on {cores} processes")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "python-int", "data": "synthetic",
+        "config": {"workload": "random-vs-random games to termination through Env.reset/step "
+                               "(config 1), CPU, all host cores", "envs_per_process": 1,
+                   "processes": cores},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # CPU baseline first (rank 0, single-GPU runs only): forked workers, before CUDA exists.
+    cpu_baseline = None
+    cpu_c = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_baseline as B
+        from oracle import c_oracle as CO
+        cores = os.cpu_count() or 1
+        total, slowest, wall, per = B.run_pool("time", args.cpu_seconds, cores)
+        cpu_baseline = {
+            "value": total / slowest, "unit": UNIT, "cores": cores, "kind": "port",
+            "per_core": statistics.mean(per),
+            "sample": f"Python oracle port, config-1 loop (Env.reset/step, random.choice over legal "
+                      f"pairs), {cores} processes x {args.cpu_seconds:.0f} s = {total} env-steps",
+        }
+        t0 = time.perf_counter()
+        st, _ = CO.selfplay(0, 4_000_000, 1)
+        dt = time.perf_counter() - t0
+        cpu_c = {"value": float(st[3]) / dt, "unit": UNIT, "cores": CO.num_threads(), "kind": "port",
+                 "sample": "C oracle (oracle/qttt_oracle.c, OpenMP), 4,000,000 Philox self-play games"}
+
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import qtttgym_b200 as Q
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    E, K, W = args.envs, args.steps, args.warmup
+    seed = 20261018
+    launches = 0
+
+    # ---- synthetic workload: random-policy traces generated on the device (untimed)
+    env = Q.BatchedEnv(E, device=dev, seed=seed, game_base=rank * E)
+    actions = torch.empty((PLIES, E), dtype=torch.uint8, device=dev)
+    coins = torch.empty((PLIES, E), dtype=torch.uint8, device=dev)
+    accepted = []
+    for ply in range(PLIES):
+        _, _, _, _, info = env.step_random(record=True)
+        actions[ply].copy_(info["action"])
+        coins[ply].copy_(info["coin"])
+        accepted.append(int((info["status"] == 0).sum().item()))
+    steps_per_pass = sum(accepted)
+    final_winner = torch.bincount(env.observation(extras=True)["winner"].long(), minlength=3)
+
+    # ---- value: inputs resident in HBM
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2 * PLIES)] for _ in range(K)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = None
+    for it in range(W + K):
+        if it == W:
+            barrier()
+            sampler = ClockSampler(local_rank)
+            start.record()
+        env.reset()
+        for ply in range(PLIES):
+            if it >= W:
+                ev[it - W][2 * ply].record()
+            env.step(actions[ply], coins[ply])
+            if it >= W:
+                ev[it - W][2 * ply + 1].record()
+    end.record()
+    barrier()
+    clocks = sampler.stop() if sampler else {}
+    t_ms = max_over_ranks(start.elapsed_time(end))
+    launches += K * (1 + PLIES)
+    total_steps = sum_over_ranks(float(steps_per_pass)) * K
+    value = total_steps / (t_ms * 1e-3)
+    # the state after the timed passes must be the state the trace generation ended in
+    w_check = torch.bincount(env.observation(extras=True)["winner"].long(), minlength=3)
+    assert torch.equal(w_check, final_winner), "timed replay diverged from the generated trace"
+
+    kdur_ms = [ev[k][2 * p].elapsed_time(ev[k][2 * p + 1]) for k in range(K) for p in range(PLIES)]
+    avg_launch_ms = sum(kdur_ms) / len(kdur_ms)
+    per_ply_ms = [sum(ev[k][2 * p].elapsed_time(ev[k][2 * p + 1]) for k in range(K)) / K for p in range(PLIES)]
+    peak, peak_src = measured_hbm_peak()
+    achieved = BYTES_PER_STEP * (steps_per_pass / PLIES) / (avg_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_step<QTTT_ACT_INDEX,false>", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": args.traffic_bytes, "algorithmic_bytes_per_launch": BYTES_PER_STEP * steps_per_pass / PLIES,
+                "avg_launch_ms": avg_launch_ms, "launch_ms_by_ply": per_ply_ms,
+                "bytes_per_env_step": BYTES_PER_STEP}
+
+    # ---- e2e: host buffers through the public API, copies inside the timed region
+    h_act = actions.cpu().pin_memory()
+    h_coin = coins.cpu().pin_memory()
+    h_reward = torch.empty(E, dtype=torch.float32).pin_memory()
+    h_done = torch.empty(E, dtype=torch.uint8).pin_memory()
+    h_mask = torch.empty(E, dtype=torch.int64).pin_memory()
+    e2e_K = max(1, min(K, args.e2e_steps))
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for it in range(2 + e2e_K):
+        if it == 2:
+            barrier()
+            s2.record()
+        env.reset()
+        for ply in range(PLIES):
+            env.step_host(h_act[ply], h_coin[ply], h_reward, h_done, h_mask)
+    e2.record()
+    barrier()
+    e2e_ms = max_over_ranks(s2.elapsed_time(e2))
+    e2e_value = sum_over_ranks(float(steps_per_pass)) * e2e_K / (e2e_ms * 1e-3)
+    assert int((h_done != 0).sum()) == E, "e2e pass did not finish every game"
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * E * PLIES,
+           "d2h_bytes_per_step": 13 * E * PLIES, "steps": e2e_K, "ms_per_step": e2e_ms / e2e_K,
+           "api": "BatchedEnv.reset + 9 x BatchedEnv.step_host (pinned host actions/coins in, "
+                  "reward/done/mask out, chunk-pipelined over side streams)"}
+
+    # ---- extras: the other configs of BASELINE.json
+    extra = {}
+
+    def timed(fn, reps):
+        fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b)) / reps
+
+    # config 2 literal: 4096 envs (latency-bound: 10 launches of ~2 us of work each)
+    small = Q.BatchedEnv(4096, device=dev, seed=seed, game_base=rank * E)
+    sa, sc = actions[:, :4096].contiguous(), coins[:, :4096].contiguous()
+    small_steps = int(sum(int((sa[p] < 36).sum().item()) for p in range(PLIES)))
+
+    def small_pass():
+        small.reset()
+        for p in range(PLIES):
+            small.step(sa[p], sc[p])
+    ms = timed(small_pass, 50)
+    launches += 51 * (1 + PLIES)
+    extra["config2_4096_envs"] = {"env_steps_per_s": small_steps / (ms * 1e-3) * world, "ms_per_pass": ms,
+                                  "note": "launch-latency bound (10 launches per pass, 4096 threads each)"}
+
+    # config 5: fused self-play sweep (K5) + the one NCCL all_reduce of the tallies
+    G = args.sweep_games
+    stats_box = {}
+
+    def sweep_pass():
+        stats_box["s"] = Q.sharded_sweep(G * world, seed, dev)
+    ms = timed(sweep_pass, 3)
+    launches += 4
+    st = stats_box["s"].cpu().tolist()
+    extra["config5_sweep"] = {
+        "env_steps_per_s": st[3] / (ms * 1e-3), "games": st[5], "env_steps": st[3], "ms": ms,
+        "x_wins": st[0], "o_wins": st[1], "draws": st[2], "collapses": st[4],
+        "hbm_frac_at_47B": st[3] / (ms * 1e-3) * BYTES_PER_STEP / 1e9 / (peak * world),
+        "collective": "all_reduce(SUM) int64[16]" if world > 1 else "none (1 rank)"}
+
+    # config 3: qeval both outcomes over 2^20 mid-game boards
+    nb = 1 << 20
+    qa = actions[4, :nb].clone()
+    qenv = Q.BatchedEnv(nb, device=dev, seed=seed, game_base=rank * E)
+    for p in range(4):
+        qenv.step(actions[p, :nb], coins[p, :nb])
+    qa = torch.where(qa < 36, qa, torch.zeros_like(qa))
+    ms = timed(lambda: Q.qeval_both(qenv.state, qa, want_states=False, want_probs=False), 20)
+    launches += 21
+    extra["config3_qeval_1M_boards"] = {
+        "boards_per_s": nb / (ms * 1e-3) * world, "ms": ms,
+        "hbm_frac_at_33B": nb / (ms * 1e-3) * BYTES_PER_BOARD_QEVAL / 1e9 / peak}
+
+    # config 4: 1024 roots x 256 rollouts
+    roots = qenv.state[:1024].clone()
+    box = {}
+
+    def roll():
+        box["r"] = Q.rollout_eval(roots, 256, seed)
+    ms = timed(roll, 20)
+    launches += 21
+    rsteps = int(box["r"][2].item())
+    extra["config4_rollout_1024x256"] = {"playouts_per_s": 1024 * 256 / (ms * 1e-3) * world,
+                                         "env_steps_per_s": rsteps / (ms * 1e-3) * world, "ms": ms}
+    if cpu_c:
+        extra["cpu_c_oracle"] = cpu_c
+    extra["population"] = {"x_wins": int(final_winner[1]), "o_wins": int(final_winner[2]),
+                           "draws": int(final_winner[0]), "games": E}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": "step API (K1): reset + 9 step launches per pass, random legal "
+                                   "actions with forced collapse coins (config 2 scaled to fill the GPU)",
+                       "envs_per_gpu": E, "global_envs": E * world, "plies_per_pass": PLIES,
+                       "env_steps_per_pass_per_gpu": steps_per_pass,
+                       "l2": "inputs exceed L2: 16 B x E state + 2 B x E actions/coins + 13 B x E outputs per launch "
+                             f"= {31 * E / 1e6:.0f} MB vs 126 MB L2" if 31 * E > 126e6 else "inputs fit in L2 (small E)",
+                       "parallelism": f"dp{world} (independent games per rank, no data-path collective)"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks, "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=1 << 24, help="envs per GPU")
+    ap.add_argument("--sweep-games", type=int, default=125_000_000, help="config-5 games per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-seconds", type=float, default=3.0, help="CPU baseline wall seconds per core")
+    ap.add_argument("--ref-games", type=int, default=1500, help="--impl reference: games per process per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--traffic-bytes", type=float, default=None,
+                    help="dram bytes per k_step launch from the committed ncu capture (profiles/)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

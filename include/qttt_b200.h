@@ -1,0 +1,154 @@
+/* qttt_b200.h -- C ABI of libqttt_b200.so: batched quantum tic-tac-toe transitions on B200.
+ *
+ * Every entry point replaces a piece of the reference's (Oxel40/qtttgym) game-transition
+ * path; the citation after each one names the reference interface it stands in for (paths
+ * relative to the reference checkout).  The reference has no FFI of its own -- it is pure
+ * Python -- so "what its FFI would bind" is: the gym-like Env API (qtttgym/env.py:15-66),
+ * the duck-typed evaluator seam Board(qevaluator).eval (qtttgym/board.py:2,7,51), and the
+ * GameState / rollout helpers MCTS relies on (mcts.py:19-27,52-65,87-91,185-208,233-267).
+ * INTEGRATION.md shows the ctypes stub a qtttgym maintainer would add.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the name ends in _host.  The caller owns every
+ *     buffer; the library allocates nothing and keeps no mutable global state.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *     asynchronous and stream-ordered; they are re-entrant across streams and devices.
+ *   - Return value: QTTT_OK, a negative QTTT_ERR_* code, or -(1000 + cudaError_t).
+ *     Nothing throws.  qttt_strerror() never returns NULL.
+ *   - Optional outputs may be NULL.
+ *
+ * Packed game state (qttt_state, 16 bytes, opaque to callers; see csrc/qttt_core.cuh):
+ * holds what the reference keeps in Board.moves / Board.board (qtttgym/board.py:4-5);
+ * Board.qstructs (board.py:6) is derived on the fly.  Convert with qttt_pack/qttt_observe.
+ *
+ * Action encodings
+ *   QTTT_ACT_INDEX  uint8[n]     0..35, pair (i<j) in lexicographic order (mcts.py:339-349);
+ *                                any other value is an illegal action (no-op).
+ *   QTTT_ACT_PAIR   int8[n][2]   (a, b) exactly as passed to Env.step (env.py:34-40), any
+ *                                order; a == b, a classical square, or a value outside 0..8
+ *                                is an illegal action: state unchanged, turn not advanced,
+ *                                outputs recomputed (env.py:36-43).
+ */
+#ifndef QTTT_B200_H
+#define QTTT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QTTT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define QTTT_API __attribute__((visibility("default")))
+#else
+#define QTTT_API
+#endif
+
+#define QTTT_OK 0
+#define QTTT_ERR_ARG (-1)        /* NULL / negative size / bad enum */
+#define QTTT_ERR_ALIGN (-2)      /* a buffer is not aligned for its element type */
+#define QTTT_ERR_NO_DEVICE (-3)  /* no CUDA device or not an sm_100 device */
+
+#define QTTT_ACT_INDEX 0
+#define QTTT_ACT_PAIR 1
+
+/* per-game status byte written by qttt_step* */
+#define QTTT_ST_OK 0        /* move accepted */
+#define QTTT_ST_ILLEGAL 1   /* the reference would have raised; swallowed no-op (env.py:41-43) */
+#define QTTT_ST_FINISHED 2  /* random-policy step on a terminated game: nothing to do */
+
+typedef struct { uint32_t w[4]; } qttt_state;
+
+QTTT_API int qttt_abi_version(void);
+QTTT_API const char* qttt_strerror(int rc);
+
+/* Board.__init__ / Env.reset (qtttgym/board.py:2-7, qtttgym/env.py:55-57; the seed is
+ * ignored there, Q4).  Writes n empty games; mask (optional) gets the 36-bit legal mask of
+ * the empty board (all 36 actions). */
+QTTT_API int qttt_reset(qttt_state* state, uint64_t* mask, int64_t n, void* stream);
+
+/* Env.step (qtttgym/env.py:34-53) for n independent games, including Board.make_move /
+ * update_qstructs (board.py:9-69), QEvalClassic.eval (qeval.py:5-51) and check_win
+ * (board.py:71-115).
+ *   action, action_format : see above
+ *   coin   uint8[n]       : forced measurement outcome, consumed only by games whose move
+ *                           closes a cycle: 0 -> the closing move falls into its smaller
+ *                           square (index random.choice picks at qeval.py:35).  NULL = draw it
+ *                           from Philox4x32-10 keyed (seed, game_base + i, len(moves)).
+ *   reward float[n]       : env.py:49 bit-exact: -1.0f if any line exists else -0.0f
+ *   done   uint8[n]       : env.py:51 terminated
+ *   mask   uint64[n]      : 36-bit legal-action mask of the new state (mcts.py:87-91)
+ *   status uint8[n]       : QTTT_ST_* */
+QTTT_API int qttt_step(qttt_state* state, const void* action, int action_format, const uint8_t* coin,
+              uint64_t seed, uint64_t game_base, float* reward, uint8_t* done, uint64_t* mask,
+              uint8_t* status, int64_t n, void* stream);
+
+/* Env.step driven by the uniform-random policy of MCTS._simulate (mcts.py:185-198,
+ * 287-292): action ~ U(legal actions), coin ~ U{0,1}, both from Philox4x32-10 with counter
+ * (game_lo, game_hi, len(moves), 0) and key seed.  Terminated games (mcts.py:52-65) are left
+ * untouched with status QTTT_ST_FINISHED.  action_out / coin_out (optional, uint8[n]) record
+ * the trace (255 / 0 for untouched games). */
+QTTT_API int qttt_step_random(qttt_state* state, uint64_t seed, uint64_t game_base, uint8_t* action_out,
+                     uint8_t* coin_out, float* reward, uint8_t* done, uint64_t* mask,
+                     uint8_t* status, int64_t n, void* stream);
+
+/* Env._observation / Env.turn / Env._reward / check_win / update_winner / action_mask in
+ * tensor form (qtttgym/env.py:62-112, board.py:71-115, mcts.py:52-65,87-91).
+ *   classical int8[n][9]    Board.board (-1 or owning move index)
+ *   moves     int8[n][9][2] Board.moves (a, b), rows >= n_moves are (-1,-1); idx = row
+ *   n_moves   uint8[n]      len(Board.moves)  (Env.turn)
+ *   q_p1      int8[n][5][2] obs["q_states_p1"], padded with (-1,-1)
+ *   q_p2      int8[n][4][2] obs["q_states_p2"]
+ *   turn      uint8[n]      obs["turn"] = len(moves) % 2
+ *   rounds    int8[n][2]    check_win() -> (p1_round, p2_round)
+ *   reward_p1 float[n]      Env._reward()
+ *   winner    uint8[n]      0 none/draw, 1 X, 2 O (mcts.py:52-65)
+ *   mask_bool uint8[n][36]  GameState.action_mask() */
+QTTT_API int qttt_observe(const qttt_state* state, int8_t* classical, int8_t* moves, uint8_t* n_moves,
+                 int8_t* q_p1, int8_t* q_p2, uint8_t* turn, int8_t* rounds, float* reward_p1,
+                 uint8_t* winner, uint8_t* mask_bool, int64_t n, void* stream);
+
+/* Inverse of qttt_observe for (classical, moves, n_moves): builds packed states from
+ * reference-shaped positions (what MCTS.reset does with game.board / game.moves,
+ * mcts.py:139-164 -- but the entanglement is re-derived, so mid-game roots are handled
+ * correctly, unlike the reference).  Positions must be reachable ones. */
+QTTT_API int qttt_pack(qttt_state* state, const int8_t* classical, const int8_t* moves,
+              const uint8_t* n_moves, int64_t n, void* stream);
+
+/* The measurement seam: Board.update_qstructs -> QEvalClassic.eval (board.py:42-56,
+ * qeval.py:5-51) and MCTS._step's enumeration of BOTH collapse outcomes (mcts.py:233-267).
+ * For each game and action (QTTT_ACT_INDEX) computes the two successor positions.
+ *   next0/next1 qttt_state[n] : successor for coin 0 / 1 (identical when no cycle closes)
+ *   board0/board1 uint64[n]   : successor boards, 4 bits per square, value board[s]+1
+ *   sq0/sq1 int8[n][9]        : square each move index collapses into in this measurement
+ *                               (-1 = not part of it): eval()'s return value by move index
+ *   closes uint8[n]           : 1 if the action closes a cycle (two distinct outcomes)
+ *   result_prob float[n][3]   : P(X has the earlier line), P(O ...), P(neither) over the two
+ *                               equiprobable outcomes (values in {0, .5, 1}) */
+QTTT_API int qttt_qeval_both(const qttt_state* state, const uint8_t* action, qttt_state* next0,
+                    qttt_state* next1, uint64_t* board0, uint64_t* board1, int8_t* sq0,
+                    int8_t* sq1, uint8_t* closes, float* result_prob, int64_t n, void* stream);
+
+/* MCTS leaf evaluation (mcts.py:166-173 _rollout averaging, 185-208 _simulate/_reward):
+ * n_rollouts uniform-random playouts from every root; playout j of root r uses Philox
+ * game id r * n_rollouts + j, domain 1.
+ *   tallies int32[n_roots][3] : X wins, O wins, draws
+ *   value   float[n_roots]    : mean reward from the root's side to move (mcts.py:171,173)
+ *   steps_total int64[1]      : env-steps executed inside the playouts (ADDED to) */
+QTTT_API int qttt_rollout(const qttt_state* roots, int64_t n_roots, int32_t n_rollouts, uint64_t seed,
+                 int32_t* tallies, float* value, int64_t* steps_total, void* stream);
+
+/* Random self-play sweep (strat_eval.py:66-94 tally convention): plays games with global
+ * ids [game_lo, game_hi) from the empty board to termination with the random policy
+ * (domain 0), entirely in registers.  stats int64[16] is ADDED to:
+ *   [0] X wins [1] O wins [2] draws [3] env-steps [4] collapses [5] games
+ *   [6..15] games by number of env-steps (0..9)
+ * Sharding [game_lo, game_hi) over GPUs and summing stats gives the single-GPU result. */
+QTTT_API int qttt_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, int64_t* stats, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QTTT_B200_H */

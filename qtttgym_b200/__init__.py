@@ -1,0 +1,21 @@
+"""qtttgym_b200 -- B200-native batched implementation of the game-transition hot path of
+Oxel40/qtttgym (quantum tic-tac-toe): reset/step, spooky-mark placement, entanglement-cycle
+detection and collapse, the qeval measurement, and uniform-random rollout leaf evaluation.
+
+Export surface mirrors the reference package (qtttgym/__init__.py:1-4: Board, QEvalClassic,
+displayBoard, Env) for the parts on the hot path: ``Env`` (single-env adapter), ``BatchedEnv``
+(the batched form), ``QEvalB200`` (evaluator plugin), plus ``qeval_both``, ``rollout_eval`` and
+``selfplay_sweep``.  Everything computes in libqttt_b200.so (hand-written CUDA for sm_100a);
+importing this package without that library works, using it does not.
+"""
+from .actions import NUM_ACTIONS, PAIRS, ind2move, move2ind
+from .env import BatchedEnv, Env, observe_states, pack_states
+from .qeval import QEvalB200, qeval_both, square_probabilities
+from .rollout import STAT_NAMES, rollout_eval, selfplay_sweep, shard_range, sharded_sweep
+
+__all__ = [
+    "NUM_ACTIONS", "PAIRS", "ind2move", "move2ind",
+    "BatchedEnv", "Env", "observe_states", "pack_states",
+    "QEvalB200", "qeval_both", "square_probabilities",
+    "STAT_NAMES", "rollout_eval", "selfplay_sweep", "shard_range", "sharded_sweep",
+]

@@ -1,0 +1,533 @@
+// qttt_core.cuh -- packed game state and the per-game transition for batched quantum
+// tic-tac-toe on sm_100a.  One thread owns one game; everything here is register-resident
+// bitmask arithmetic (no loops over sets, no local memory).
+//
+// Reference semantics being reproduced (Oxel40/qtttgym, citations into /root/reference):
+//   Board.make_move        qtttgym/board.py:9-25     legality, append, autofill
+//   Board.update_qstructs  qtttgym/board.py:27-69    component lookup, cycle test, collapse
+//   QEvalClassic.eval      qtttgym/qeval.py:5-51     which square each move collapses into
+//   Board.check_win        qtttgym/board.py:71-115   line rounds
+//   Env.step               qtttgym/env.py:34-53      reward (-0.0 / -1.0), terminated
+//   GameState actions      mcts.py:19-27, 87-91      36-way legal mask
+//
+// How the collapse is computed here (NOT how the reference does it): before the closing move
+// the component is a tree (a cycle would have collapsed earlier).  The measurement gives the
+// closing move to one of its two squares `t` (coin), and every other move of the component
+// then has exactly one free square left: its endpoint farther from `t`.  So the collapse map
+// is "root the tree at t, every edge falls into its child endpoint".  The reference's leaf
+// peeling + cycle walk (qeval.py:23-49) yields the same map; tests pin the two against each
+// other through the oracle and fixtures recorded from the live reference.
+//
+// The same breadth-first absorption also answers "are a and b already connected?" (the
+// cycle test, board.py:42), so one pass structure serves both.
+//
+// The header is __host__ __device__ clean so that tests can run the very same transition on
+// the build container's CPU (tests/hostemu) before GPU time is spent.  The shipped library
+// only ever calls it from kernels.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define QTTT_HD __host__ __device__ __forceinline__
+#else
+#define QTTT_HD inline
+#endif
+
+namespace qttt {
+
+// ------------------------------------------------------------------------------------
+// Packed state: 16 bytes per game, one uint4 load / store.
+//
+//   x : E0[0:9]  E1[9:18]  E2[18:27]  n_moves[27:31]
+//   y : E3[0:9]  E4[9:18]  E5[18:27]  P3 squares 0..4 [27:32]
+//   z : E6[0:9]  E7[9:18]  E8[18:27]  P3 squares 5..8 [27:31]
+//   w : P0[0:9]  P1[9:18]  P2[18:27]  (5 spare bits, zero)
+//
+//   E_i : 9-bit square set of move i -- two bits for a spooky pair (a, b), one bit for the
+//         autofill entry (s, s, i) (board.py:25), zero for an empty slot.  a < b is implicit.
+//   P_k : bit-plane k of v[s] = board[s] + 1 (0 = not classical, 1..9 = owner index + 1).
+//         Plane 0 is therefore "owned by X" (even move index), and the classical set is
+//         P0|P1|P2|P3.
+// ------------------------------------------------------------------------------------
+struct State { uint32_t x, y, z, w; };
+
+constexpr uint32_t M9 = 0x1FFu;
+
+QTTT_HD int popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+QTTT_HD int ctz32(uint32_t v) {   // v != 0
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+QTTT_HD int flo32(uint32_t v) {   // index of highest set bit, v != 0
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz((int)v);
+#else
+    return 31 - __builtin_clz(v);
+#endif
+}
+QTTT_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+QTTT_HD State empty_state() { return State{0u, 0u, 0u, 0u}; }
+QTTT_HD uint32_t n_moves(const State& s) { return (s.x >> 27) & 15u; }
+QTTT_HD uint32_t plane3(const State& s) { return (s.y >> 27) | ((s.z >> 22) & 0x1E0u); }
+QTTT_HD uint32_t plane0(const State& s) { return s.w & M9; }
+QTTT_HD uint32_t plane1(const State& s) { return (s.w >> 9) & M9; }
+QTTT_HD uint32_t plane2(const State& s) { return (s.w >> 18) & M9; }
+QTTT_HD uint32_t classical(const State& s) {
+    return ((s.w | (s.w >> 9) | (s.w >> 18)) & M9) | plane3(s);
+}
+template <int I>
+QTTT_HD uint32_t edge(const State& s) {
+    const uint32_t word = I < 3 ? s.x : (I < 6 ? s.y : s.z);
+    return (word >> (9 * (I % 3))) & M9;
+}
+QTTT_HD uint32_t edge_dyn(const State& s, uint32_t i) {
+    const uint32_t q = (i * 11u) >> 5;
+    const uint32_t word = q == 0 ? s.x : (q == 1 ? s.y : s.z);
+    return (word >> (9u * (i - 3u * q))) & M9;
+}
+
+// Lookup tables: a constant image in global memory (built at compile time), staged into
+// shared memory by each block.  The step kernels only need the first kLutStepBytes.
+struct LutImage {
+    uint64_t legal[512];    // free-square set -> 36-bit legal mask            (mcts.py:19-27)
+    uint16_t pair[256];     // action index -> E mask of (i, j); 0 for index >= 36 (mcts.py:339-343)
+    uint8_t  line[512];     // square set -> 1 if it contains one of the 8 lines (board.py:84-110)
+    uint64_t spread[512];   // square set -> the same bits at a 4-bit stride
+};
+constexpr int kLutStepBytes = 512 * 8 + 256 * 2 + 512;   // legal + pair + line = 5120
+constexpr int kLutBytes = (int)sizeof(LutImage);        // 9216
+static_assert(sizeof(LutImage) == 9216, "LutImage layout");
+
+constexpr LutImage make_lut_image() {
+    LutImage t{};
+    const uint16_t lines[8] = {0x007, 0x038, 0x1C0, 0x049, 0x092, 0x124, 0x054, 0x111};
+    for (uint32_t m = 0; m < 512; ++m) {
+        uint64_t lm = 0, sp = 0;
+        int k = 0;
+        for (int i = 0; i < 9; ++i)
+            for (int j = i + 1; j < 9; ++j, ++k)
+                if ((m >> i & 1u) && (m >> j & 1u)) lm |= 1ull << k;
+        for (int s = 0; s < 9; ++s)
+            if (m >> s & 1u) sp |= 1ull << (4 * s);
+        uint8_t any = 0;
+        for (int l = 0; l < 8; ++l)
+            if ((m & lines[l]) == lines[l]) any = 1;
+        t.legal[m] = lm;
+        t.spread[m] = sp;
+        t.line[m] = any;
+    }
+    int k = 0;
+    for (int i = 0; i < 9; ++i)
+        for (int j = i + 1; j < 9; ++j, ++k) t.pair[k] = (uint16_t)((1u << i) | (1u << j));
+    return t;
+}
+
+struct Luts {
+    const uint64_t* legal;
+    const uint16_t* pair;
+    const uint8_t*  line;
+    const uint64_t* spread;
+};
+QTTT_HD Luts luts_from_image(const void* img) {
+    const LutImage* t = reinterpret_cast<const LutImage*>(img);
+    Luts l;
+    l.legal = t->legal;
+    l.pair = t->pair;
+    l.line = t->line;
+    l.spread = t->spread;
+    return l;
+}
+
+// E mask for an (a, b) byte pair as passed to Env.step (any order; env.py:37-40).  0 = cannot
+// be a move: same square (board.py:10-12) or off the board (IndexError path / negative).
+QTTT_HD uint32_t pair_to_edge(uint32_t a, uint32_t b) {
+    const bool ok = (a < 9u) & (b < 9u) & (a != b);
+    return ok ? ((1u << a) | (1u << b)) : 0u;
+}
+
+struct StepResult {
+    uint32_t illegal;     // 1: the reference would have raised -> no-op (env.py:36-43)
+    uint32_t collapsed;   // 1: a measurement happened (the coin was consumed)
+    uint32_t classical;   // classical squares after the step
+    uint32_t n;           // len(moves) after the step
+};
+
+// One breadth-first absorption of a live edge into the reached set R; T remembers the square
+// the edge brought in (its child endpoint when the tree is rooted at the start square).
+#if defined(__CUDA_ARCH__)
+// Three issue slots per edge: LOP3 with predicate output, then two predicated LOP3s
+// (T |= E & ~R  is  lop3 0xF4).  Written in PTX because the compiler otherwise turns the
+// conditional into six select-based instructions.
+#define QTTT_ABSORB(E, T)                                                     \
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 h;\n\t"                            \
+        "and.b32 h, %2, %1;\n\t"                                              \
+        "setp.ne.u32 p, h, 0;\n\t"                                            \
+        "@p lop3.b32 %0, %0, %2, %1, 0xF4;\n\t"                               \
+        "@p or.b32 %1, %1, %2;\n\t}"                                          \
+        : "+r"(T), "+r"(R) : "r"(E));
+#else
+#define QTTT_ABSORB(E, T)                         \
+    if ((E) & R) {                                \
+        (T) |= (E) & ~R;                          \
+        R |= (E);                                 \
+    }
+#endif
+
+// Board.make_move for one game.  `enew`: E mask of the requested pair (0 = malformed);
+// `coin`: 0 -> the closing move falls into its smaller square (qeval.py:35).
+//
+// kTargets: also report, per move index, the square set it collapsed into in this
+// measurement (tgt[0..8], zero when not part of it) -- eval()'s return value by move index.
+template <bool kTargets = false>
+QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, uint32_t* tgt = nullptr) {
+    const uint32_t x = s.x, y = s.y, z = s.z, w = s.w;
+    const uint32_t n = (x >> 27) & 15u;
+    const uint32_t C = classical(s);
+    const bool legal = (enew != 0u) & ((enew & C) == 0u) & (n < 9u);   // board.py:10-15
+    enew = legal ? enew : 0u;
+
+    // t = square the closing move would take; o = its other square.
+    const uint32_t lo = enew & (0u - enew);
+    const uint32_t t = coin ? (enew ^ lo) : lo;
+    const uint32_t o = enew ^ t;
+
+    // Live edges are exactly the moves whose squares are not classical; collapsed moves have
+    // both squares classical and can never touch R (which starts on a free square), so the
+    // raw E fields can be used unfiltered.
+    const uint32_t E0 = x & M9, E1 = (x >> 9) & M9, E2 = (x >> 18) & M9;
+    const uint32_t E3 = y & M9, E4 = (y >> 9) & M9, E5 = (y >> 18) & M9;
+    const uint32_t E6 = z & M9, E7 = (z >> 9) & M9;
+    uint32_t T0 = 0, T1 = 0, T2 = 0, T3 = 0, T4 = 0, T5 = 0, T6 = 0, T7 = 0;
+    uint32_t R = t, before;
+    do {
+        before = R;
+        QTTT_ABSORB(E0, T0) QTTT_ABSORB(E1, T1) QTTT_ABSORB(E2, T2) QTTT_ABSORB(E3, T3)
+        QTTT_ABSORB(E4, T4) QTTT_ABSORB(E5, T5) QTTT_ABSORB(E6, T6) QTTT_ABSORB(E7, T7)
+    } while (R != before);
+
+    const bool col = (R & o) != 0u;            // a, b already connected -> cycle (board.py:42)
+    const uint32_t cm = col ? 0xFFFFFFFFu : 0u;
+
+    // board[square] = move index for every move of the component (board.py:53-54), written
+    // into the bit-planes of v = index + 1.  Old moves have static indices; the closing
+    // move has index n.
+    const uint32_t v = n + 1u;
+    uint32_t A0 = T0 | T2 | T4 | T6 | ((v & 1u) ? t : 0u);
+    uint32_t A1 = T1 | T2 | T5 | T6 | ((v & 2u) ? t : 0u);
+    uint32_t A2 = T3 | T4 | T5 | T6 | ((v & 4u) ? t : 0u);
+    uint32_t A3 = (T7 | ((v & 8u) ? t : 0u)) & cm;
+    uint32_t wn = w | ((A0 | (A1 << 9) | (A2 << 18)) & cm);
+    uint32_t Cn = C | (R & cm);
+
+    // moves.append((a, b, n))  (board.py:19)
+    const uint32_t q = (n * 11u) >> 5, r = n - 3u * q;
+    const uint32_t val = enew << (9u * r);
+    uint32_t xn = x | (q == 0u ? val : 0u);
+    uint32_t yn = y | (q == 1u ? val : 0u);
+    uint32_t zn = z | (q == 2u ? val : 0u);
+    uint32_t inc = legal ? 1u : 0u;
+
+    // Autofill (board.py:21-25): one free square left.  Only reachable right after the
+    // collapse triggered by move 7, so the entry is always (s, s, 8): v = 9 -> planes 0, 3.
+    const uint32_t fr = ~Cn & M9;
+    const bool fill = col & (popc32(fr) == 1);
+    const uint32_t fs = fill ? fr : 0u;
+    zn |= fs << 18;
+    wn |= fs;
+    A3 |= fs;
+    Cn |= fs;
+    inc += fill ? 1u : 0u;
+
+    yn |= (A3 & 0x1Fu) << 27;
+    zn |= (A3 >> 5) << 27;
+    xn += inc << 27;
+
+    if (kTargets) {
+        tgt[0] = T0 & cm; tgt[1] = T1 & cm; tgt[2] = T2 & cm; tgt[3] = T3 & cm;
+        tgt[4] = T4 & cm; tgt[5] = T5 & cm; tgt[6] = T6 & cm; tgt[7] = T7 & cm;
+        tgt[8] = 0u;
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            if ((uint32_t)i == n) tgt[i] = t & cm;
+    }
+
+    s.x = xn; s.y = yn; s.z = zn; s.w = wn;
+    StepResult out;
+    out.illegal = legal ? 0u : 1u;
+    out.collapsed = col ? 1u : 0u;
+    out.classical = Cn;
+    out.n = n + inc;
+    return out;
+}
+
+// Env.step's scalar outputs from the post-step state (env.py:48-51).
+//   reward bits: -(1**p) * float(win)  ->  0xBF800000 (-1.0) if any line exists else
+//   0x80000000 (-0.0) -- quirk Q1;  terminated: win or len(moves) > 8.
+QTTT_HD uint32_t any_line(const State& s, uint32_t C, const Luts& L) {
+    const uint32_t X = s.w & M9;        // plane 0: owned by an even move index (X)
+    const uint32_t O = C & ~X;
+    return (uint32_t)L.line[X] | (uint32_t)L.line[O];
+}
+QTTT_HD uint32_t reward_bits(uint32_t win) { return win ? 0xBF800000u : 0x80000000u; }
+
+// board.py:71-115 in plane form.  Returns (pX, pO) as in check_win: -1 or the round.
+QTTT_HD void win_rounds(const State& s, const Luts& L, int& px, int& po) {
+    const uint32_t P0 = plane0(s), P1 = plane1(s), P2 = plane2(s), P3 = plane3(s);
+    const uint32_t C = P0 | P1 | P2 | P3;
+    const uint32_t x8 = P0;                       // X squares: v in {1,3,5,7,9}
+    const uint32_t x6 = P0 & ~P3;                 // v <= 7
+    const uint32_t x4 = x6 & ~(P1 & P2);          // v <= 5
+    const uint32_t o7 = C & ~P0;                  // O squares: v in {2,4,6,8}
+    const uint32_t o5 = o7 & ~P3;                 // v <= 6
+    px = L.line[x4] ? 4 : (L.line[x6] ? 6 : (L.line[x8] ? 8 : -1));
+    po = L.line[o5] ? 5 : (L.line[o7] ? 7 : -1);
+}
+// mcts.py:52-65 / strat_eval.py:21-32: 1 = X, 2 = O, 0 = none (draw or unfinished).
+QTTT_HD uint32_t winner_of(int px, int po) {
+    if (px > 0 && po > 0) return px < po ? 1u : 2u;
+    if (px > 0) return 1u;
+    if (po > 0) return 2u;
+    return 0u;
+}
+
+// ------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), counter (game_lo, game_hi, ply, domain), key = seed.
+// x0 picks the action, bit 0 of x1 is the collapse coin.
+// ------------------------------------------------------------------------------------
+QTTT_HD void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3,
+                           uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0;
+        c2 = h0 ^ c3 ^ k1;
+        c1 = l1;
+        c3 = l0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+
+// k-th (0-based) set bit of a 36-bit mask, k < popcount.  Branch-free binary search.
+QTTT_HD uint32_t nth_set_bit36(uint64_t m, uint32_t k) {
+    uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+    uint32_t c = (uint32_t)popc32(lo);
+    bool up = k >= c;
+    uint32_t wd = up ? hi : lo;
+    k -= up ? c : 0u;
+    uint32_t base = up ? 32u : 0u;
+#pragma unroll
+    for (int width = 16; width >= 1; width >>= 1) {
+        const uint32_t part = wd & ((1u << width) - 1u);
+        c = (uint32_t)popc32(part);
+        up = k >= c;
+        wd = up ? (wd >> width) : part;
+        k -= up ? c : 0u;
+        base += up ? (uint32_t)width : 0u;
+    }
+    return base;
+}
+
+// uniform-random legal action + coin for (seed, game, ply, domain)
+QTTT_HD void policy_draw(uint64_t seed, uint64_t game, uint32_t ply, uint32_t domain,
+                         uint64_t legal_mask, uint32_t& action, uint32_t& coin) {
+    uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = ply, c3 = domain;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t m = (uint32_t)popc32((uint32_t)legal_mask) + (uint32_t)popc32((uint32_t)(legal_mask >> 32));
+    action = m ? nth_set_bit36(legal_mask, mulhi32(c0, m)) : 255u;
+    coin = c1 & 1u;
+}
+
+
+// ====================================================================================
+// Per-game bodies of the kernels (shared with the host emulation used by CPU tests).
+// All pointer arguments are the full output arrays; `i` is the game's row.
+// ====================================================================================
+
+QTTT_HD float bits_to_float(uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(b);
+#else
+    union { uint32_t u; float f; } c; c.u = b; return c.f;
+#endif
+}
+
+// Scalar outputs of Env.step for the post-step state (env.py:46-53).
+QTTT_HD void emit_step_outputs(const State& s, const StepResult& r, uint32_t status, const Luts& L,
+                               float* reward, uint8_t* done, uint64_t* mask, uint8_t* status_out,
+                               int64_t i) {
+    const uint32_t win = any_line(s, r.classical, L);
+    if (reward) reward[i] = bits_to_float(reward_bits(win));                 // env.py:49
+    if (done) done[i] = (uint8_t)((win != 0u) | (r.n > 8u));                  // env.py:51
+    if (mask) mask[i] = L.legal[~r.classical & M9];                           // mcts.py:87-91
+    if (status_out) status_out[i] = (uint8_t)status;
+}
+
+// mcts.py:52-65 terminal test on a state (winner exists or 9 entries in moves).
+QTTT_HD uint32_t finished_winner(const State& s, const Luts& L, bool& terminal) {
+    int px, po;
+    win_rounds(s, L, px, po);
+    const uint32_t w = winner_of(px, po);
+    terminal = (w != 0u) | (n_moves(s) >= 9u);
+    return w;
+}
+
+// One ply of MCTS._simulate (mcts.py:188-196): action ~ U(legal), coin ~ U{0,1}.
+QTTT_HD StepResult playout_ply(State& s, uint32_t C, uint64_t seed, uint64_t game, uint32_t domain,
+                               const Luts& L, uint32_t* act_out = nullptr, uint32_t* coin_out = nullptr) {
+    uint32_t act, c;
+    policy_draw(seed, game, n_moves(s), domain, L.legal[~C & M9], act, c);
+    if (act_out) *act_out = act;
+    if (coin_out) *coin_out = c;
+    return step_core(s, (uint32_t)L.pair[act & 255u], c);
+}
+
+QTTT_HD int board_value(uint32_t P0, uint32_t P1, uint32_t P2, uint32_t P3, int sq) {
+    return (int)((P0 >> sq & 1u) | ((P1 >> sq & 1u) << 1) | ((P2 >> sq & 1u) << 2) |
+                 ((P3 >> sq & 1u) << 3)) - 1;
+}
+
+// Env._observation and friends in tensor form (env.py:62-112, board.py:71-115, mcts.py:52-65,87-91).
+QTTT_HD void observe_game(const State& s, const Luts& L, int8_t* classical_out, int8_t* moves,
+                          uint8_t* nmoves, int8_t* q1, int8_t* q2, uint8_t* turn, int8_t* rounds,
+                          float* reward_p1, uint8_t* winner, uint8_t* mask_bool, int64_t i) {
+    const uint32_t P0 = plane0(s), P1 = plane1(s), P2 = plane2(s), P3 = plane3(s);
+    const uint32_t C = P0 | P1 | P2 | P3;
+    const uint32_t nm = n_moves(s);
+    if (classical_out)
+        for (int sq = 0; sq < 9; ++sq) classical_out[9 * i + sq] = (int8_t)board_value(P0, P1, P2, P3, sq);
+    if (nmoves) nmoves[i] = (uint8_t)nm;
+    if (turn) turn[i] = (uint8_t)(nm & 1u);                                   // env.py:83
+    int c1 = 0, c2 = 0;
+    if (q1) for (int k = 0; k < 10; ++k) q1[10 * i + k] = -1;
+    if (q2) for (int k = 0; k < 8; ++k) q2[8 * i + k] = -1;
+    for (uint32_t m = 0; m < 9; ++m) {
+        const uint32_t E = edge_dyn(s, m);
+        const bool present = (m < nm) & (E != 0u);
+        const int a = present ? ctz32(E) : -1, b = present ? flo32(E) : -1;
+        if (moves) { moves[18 * i + 2 * m] = (int8_t)a; moves[18 * i + 2 * m + 1] = (int8_t)b; }
+        if (present && (E & C) == 0u) {                                       // env.py:73-78
+            if (m & 1u) { if (q2 && c2 < 4) { q2[8 * i + 2 * c2] = (int8_t)a; q2[8 * i + 2 * c2 + 1] = (int8_t)b; } ++c2; }
+            else        { if (q1 && c1 < 5) { q1[10 * i + 2 * c1] = (int8_t)a; q1[10 * i + 2 * c1 + 1] = (int8_t)b; } ++c1; }
+        }
+    }
+    int px, po;
+    win_rounds(s, L, px, po);
+    if (rounds) { rounds[2 * i] = (int8_t)px; rounds[2 * i + 1] = (int8_t)po; }
+    if (reward_p1) {                                                          // env.py:87-112
+        const int a = px < 0 ? 10 : px, b = po < 0 ? 10 : po;
+        reward_p1[i] = a < b ? 1.0f : (b < a ? -1.0f : 0.0f);
+    }
+    if (winner) winner[i] = (uint8_t)winner_of(px, po);                       // mcts.py:52-65
+    if (mask_bool) {
+        const uint64_t lm = L.legal[~C & M9];
+        for (int k = 0; k < 36; ++k) mask_bool[36 * i + k] = (uint8_t)(lm >> k & 1ull);
+    }
+}
+
+// (classical, moves, n_moves) -> packed state.
+QTTT_HD State pack_game(const int8_t* classical_in, const int8_t* moves, const uint8_t* nmoves, int64_t i) {
+    State s = empty_state();
+    uint32_t nm = nmoves[i];
+    nm = nm > 9u ? 9u : nm;
+    uint32_t P3 = 0u;
+    for (int sq = 0; sq < 9; ++sq) {
+        const uint32_t v = (uint32_t)(classical_in[9 * i + sq] + 1) & 15u;
+        s.w |= ((v & 1u) << sq) | (((v >> 1) & 1u) << (9 + sq)) | (((v >> 2) & 1u) << (18 + sq));
+        P3 |= ((v >> 3) & 1u) << sq;
+    }
+    uint32_t wx = 0u, wy = 0u, wz = 0u;
+    for (uint32_t m = 0; m < nm; ++m) {
+        const uint32_t a = (uint32_t)moves[18 * i + 2 * m] & 15u, b = (uint32_t)moves[18 * i + 2 * m + 1] & 15u;
+        const uint32_t E = (((1u << a) | (1u << b)) & M9) << (9u * (m % 3u));
+        if (m < 3u) wx |= E; else if (m < 6u) wy |= E; else wz |= E;
+    }
+    s.x = wx | (nm << 27);
+    s.y = wy | ((P3 & 0x1Fu) << 27);
+    s.z = wz | ((P3 >> 5) << 27);
+    return s;
+}
+
+QTTT_HD uint64_t board_nibbles(const State& s, const Luts& L) {
+    return L.spread[plane0(s)] | (L.spread[plane1(s)] << 1) | (L.spread[plane2(s)] << 2) |
+           (L.spread[plane3(s)] << 3);
+}
+
+// Both measurement outcomes of one (position, action): board.py:42-56 + qeval.py:5-51 twice,
+// i.e. what MCTS._step enumerates by rejection sampling (mcts.py:233-267).
+QTTT_HD void qeval_game(const State& s, uint32_t action, const Luts& L, State* next0, State* next1,
+                        uint64_t* board0, uint64_t* board1, int8_t* sq0, int8_t* sq1,
+                        uint8_t* closes, float* result_prob, int64_t i) {
+    const uint32_t enew = L.pair[action & 255u];
+    float px_prob = 0.f, po_prob = 0.f;
+    uint32_t col = 0u;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        State t = s;
+        uint32_t tgt[9];
+        const StepResult r = step_core<true>(t, enew, (uint32_t)c, tgt);
+        col = r.collapsed;
+        State* nx = c ? next1 : next0;
+        uint64_t* bd = c ? board1 : board0;
+        int8_t* sq = c ? sq1 : sq0;
+        if (nx) nx[i] = t;
+        if (bd) bd[i] = board_nibbles(t, L);
+        if (sq) {
+#pragma unroll
+            for (int m = 0; m < 9; ++m) sq[9 * i + m] = (int8_t)(tgt[m] ? ctz32(tgt[m]) : -1);
+        }
+        if (result_prob) {
+            int px, po;
+            win_rounds(t, L, px, po);
+            const uint32_t wnr = winner_of(px, po);
+            px_prob += wnr == 1u ? 0.5f : 0.f;
+            po_prob += wnr == 2u ? 0.5f : 0.f;
+        }
+    }
+    if (closes) closes[i] = (uint8_t)col;
+    if (result_prob) {
+        result_prob[3 * i] = px_prob;
+        result_prob[3 * i + 1] = po_prob;
+        result_prob[3 * i + 2] = 1.0f - px_prob - po_prob;
+    }
+}
+
+// Number of plies behind a position: the autofill entry (s, s, 8) is not a ply (mcts.py:243).
+QTTT_HD uint32_t plies_of(const State& s) {
+    const uint32_t nm = n_moves(s);
+    const uint32_t e8 = (s.z >> 18) & M9;
+    return nm - (uint32_t)((nm == 9u) & (popc32(e8) == 1));
+}
+
+// One uniform-random playout to a terminal state (mcts.py:185-208).  Returns the winner.
+QTTT_HD uint32_t playout_game(State s, uint64_t seed, uint64_t game, uint32_t domain, const Luts& L,
+                              uint32_t& steps, uint32_t& collapses) {
+    bool terminal;
+    uint32_t w = finished_winner(s, L, terminal);
+    while (!terminal) {
+        const StepResult r = playout_ply(s, classical(s), seed, game, domain, L);
+        ++steps;
+        collapses += r.collapsed;
+        w = finished_winner(s, L, terminal);
+    }
+    return w;
+}
+
+}  // namespace qttt

@@ -1,0 +1,346 @@
+// qttt_kernels.cu -- sm_100a kernels and the C ABI (include/qttt_b200.h) of libqttt_b200.so.
+//
+// All kernels are one-thread-per-game integer programs over the packed 16-byte state of
+// qttt_core.cuh: one coalesced 128-bit load and store per game, lookup tables staged in
+// shared memory, no tensor cores (nothing here is a contraction).  No torch headers: the
+// Python side passes raw device pointers and a stream.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/qttt_b200.h"
+#include "qttt_core.cuh"
+
+namespace qttt {
+
+__device__ const LutImage g_lut = make_lut_image();
+
+constexpr int kThreads = 256;
+constexpr int kBlocksPerSM = 8;   // 2048 resident threads per SM
+
+// Stage the first `bytes` of the table image into shared memory (16-byte vectors).
+__device__ __forceinline__ void stage_luts(uint8_t* smem, int bytes) {
+    const uint4* src = reinterpret_cast<const uint4*>(&g_lut);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+}
+
+__device__ __forceinline__ State load_state(const qttt_state* p, int64_t i) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p + i);
+    return State{v.x, v.y, v.z, v.w};
+}
+__device__ __forceinline__ void store_state(qttt_state* p, int64_t i, const State& s) {
+    *reinterpret_cast<uint4*>(p + i) = make_uint4(s.x, s.y, s.z, s.w);
+}
+
+// ------------------------------------------------------------------------------ K2 reset
+__global__ void __launch_bounds__(kThreads) k_reset(qttt_state* state, uint64_t* mask, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+        *reinterpret_cast<uint4*>(state + i) = make_uint4(0u, 0u, 0u, 0u);
+        if (mask) mask[i] = 0xFFFFFFFFFull;   // all 36 pairs legal on the empty board
+    }
+}
+
+// ------------------------------------------------------------------------------ K1 step
+// kFmt: QTTT_ACT_INDEX / QTTT_ACT_PAIR; kRandom: Philox policy instead of given actions.
+template <int kFmt, bool kRandom>
+__global__ void __launch_bounds__(kThreads)
+k_step(qttt_state* __restrict__ state, const uint8_t* __restrict__ action,
+       const uint8_t* __restrict__ coin, uint64_t seed, uint64_t game_base,
+       float* __restrict__ reward, uint8_t* __restrict__ done, uint64_t* __restrict__ mask,
+       uint8_t* __restrict__ status, uint8_t* __restrict__ action_out,
+       uint8_t* __restrict__ coin_out, int64_t n) {
+    __shared__ __align__(16) uint8_t smem[kLutStepBytes];
+    stage_luts(smem, kLutStepBytes);
+    const Luts L = luts_from_image(smem);
+
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+        State s = load_state(state, i);
+        uint32_t enew, c, st_extra = 0u;
+        if (kRandom) {
+            const uint32_t C = classical(s);
+            const uint32_t nm = n_moves(s);
+            const bool finished = (any_line(s, C, L) != 0u) | (nm >= 9u);   // mcts.py:52-65
+            uint32_t act;
+            policy_draw(seed, game_base + (uint64_t)i, nm, 0u, L.legal[~C & M9], act, c);
+            if (finished) { act = 255u; c = 0u; st_extra = QTTT_ST_FINISHED; }
+            enew = L.pair[act];
+            if (action_out) action_out[i] = (uint8_t)act;
+            if (coin_out) coin_out[i] = (uint8_t)c;
+        } else {
+            if (kFmt == QTTT_ACT_INDEX) {
+                enew = L.pair[action[i]];
+            } else {
+                const uchar2 ab = reinterpret_cast<const uchar2*>(action)[i];
+                enew = pair_to_edge(ab.x, ab.y);
+            }
+            if (coin) {
+                c = coin[i] & 1u;
+            } else {
+                const uint64_t game = game_base + (uint64_t)i;
+                uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = n_moves(s), c3 = 0u;
+                philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+                c = c1 & 1u;
+            }
+        }
+        const StepResult r = step_core(s, enew, c);
+        store_state(state, i, s);
+        emit_step_outputs(s, r, st_extra ? st_extra : r.illegal, L, reward, done, mask, status, i);
+    }
+}
+
+// ------------------------------------------------------------------------------ observe / pack
+__global__ void __launch_bounds__(kThreads)
+k_observe(const qttt_state* __restrict__ state, int8_t* __restrict__ classical_out,
+          int8_t* __restrict__ moves, uint8_t* __restrict__ nmoves, int8_t* __restrict__ q1,
+          int8_t* __restrict__ q2, uint8_t* __restrict__ turn, int8_t* __restrict__ rounds,
+          float* __restrict__ reward_p1, uint8_t* __restrict__ winner,
+          uint8_t* __restrict__ mask_bool, int64_t n) {
+    __shared__ __align__(16) uint8_t smem[kLutStepBytes];
+    stage_luts(smem, kLutStepBytes);
+    const Luts L = luts_from_image(smem);
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
+        observe_game(load_state(state, i), L, classical_out, moves, nmoves, q1, q2, turn, rounds,
+                     reward_p1, winner, mask_bool, i);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_pack(qttt_state* __restrict__ state, const int8_t* __restrict__ classical_in,
+       const int8_t* __restrict__ moves, const uint8_t* __restrict__ nmoves, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
+        store_state(state, i, pack_game(classical_in, moves, nmoves, i));
+}
+
+// ------------------------------------------------------------------------------ K3 qeval
+__global__ void __launch_bounds__(kThreads)
+k_qeval_both(const qttt_state* __restrict__ state, const uint8_t* __restrict__ action,
+             qttt_state* __restrict__ next0, qttt_state* __restrict__ next1,
+             uint64_t* __restrict__ board0, uint64_t* __restrict__ board1,
+             int8_t* __restrict__ sq0, int8_t* __restrict__ sq1, uint8_t* __restrict__ closes,
+             float* __restrict__ result_prob, int64_t n) {
+    __shared__ __align__(16) uint8_t smem[kLutBytes];
+    stage_luts(smem, kLutBytes);
+    const Luts L = luts_from_image(smem);
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
+        qeval_game(load_state(state, i), action[i], L, reinterpret_cast<State*>(next0),
+                   reinterpret_cast<State*>(next1), board0, board1, sq0, sq1, closes, result_prob, i);
+}
+
+// ------------------------------------------------------------------------------ playouts
+// K4: block per root, rollouts strided over the block's threads.
+__global__ void __launch_bounds__(kThreads)
+k_rollout(const qttt_state* __restrict__ roots, int32_t n_rollouts, uint64_t seed,
+          int32_t* __restrict__ tallies, float* __restrict__ value,
+          unsigned long long* __restrict__ steps_total) {
+    __shared__ __align__(16) uint8_t smem[kLutStepBytes];
+    __shared__ int sh_tally[3];
+    __shared__ unsigned long long sh_steps;
+    stage_luts(smem, kLutStepBytes);
+    const Luts L = luts_from_image(smem);
+    if (threadIdx.x < 3) sh_tally[threadIdx.x] = 0;
+    if (threadIdx.x == 0) sh_steps = 0ull;
+    __syncthreads();
+
+    const int64_t root = blockIdx.x;
+    const State s0 = load_state(roots, root);
+    int xw = 0, ow = 0, dr = 0;
+    uint32_t steps = 0, cols = 0;
+    for (int32_t j = threadIdx.x; j < n_rollouts; j += kThreads) {
+        const uint64_t game = (uint64_t)root * (uint64_t)n_rollouts + (uint64_t)j;
+        const uint32_t w = playout_game(s0, seed, game, 1u, L, steps, cols);
+        xw += w == 1u; ow += w == 2u; dr += w == 0u;
+    }
+    xw = __reduce_add_sync(0xFFFFFFFFu, xw);
+    ow = __reduce_add_sync(0xFFFFFFFFu, ow);
+    dr = __reduce_add_sync(0xFFFFFFFFu, dr);
+    steps = __reduce_add_sync(0xFFFFFFFFu, steps);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sh_tally[0], xw); atomicAdd(&sh_tally[1], ow); atomicAdd(&sh_tally[2], dr);
+        atomicAdd(&sh_steps, (unsigned long long)steps);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (tallies) { tallies[3 * root] = sh_tally[0]; tallies[3 * root + 1] = sh_tally[1]; tallies[3 * root + 2] = sh_tally[2]; }
+        if (value) {
+            // mcts.py:171,173: sum(r if leaf.turn else -r) / num_simulations
+            const float r = (float)(sh_tally[0] - sh_tally[1]) / (float)n_rollouts;
+            value[root] = (plies_of(s0) & 1u) ? -r : r;
+        }
+        if (steps_total) atomicAdd(steps_total, sh_steps);
+    }
+}
+
+// K5: self-play sweep from the empty board.  Lanes refill: a thread that finishes a game
+// immediately starts its next one, so every lane executes a real ply on every iteration.
+__global__ void __launch_bounds__(kThreads)
+k_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, unsigned long long* __restrict__ stats) {
+    __shared__ __align__(16) uint8_t smem[kLutStepBytes];
+    __shared__ unsigned long long sh[16];
+    stage_luts(smem, kLutStepBytes);
+    const Luts L = luts_from_image(smem);
+    if (threadIdx.x < 16) sh[threadIdx.x] = 0ull;
+    __syncthreads();
+
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    int64_t g = game_lo + (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    State s = empty_state();
+    uint32_t C = 0u, steps = 0u;
+    uint32_t xw = 0, ow = 0, dr = 0, st = 0, co = 0, games = 0;
+    while (g < game_hi) {
+        const StepResult r = playout_ply(s, C, seed, (uint64_t)g, 0u, L);
+        C = r.classical;
+        ++steps;
+        co += r.collapsed;
+        bool terminal = r.n >= 9u;
+        uint32_t w = 0u;
+        if (r.collapsed) w = finished_winner(s, L, terminal);   // lines only appear through a collapse
+        if (terminal) {
+            xw += w == 1u; ow += w == 2u; dr += w == 0u;
+            st += steps; ++games;
+            atomicAdd(&sh[6 + steps], 1ull);
+            g += stride;
+            s = empty_state(); C = 0u; steps = 0u;
+        }
+    }
+    xw = __reduce_add_sync(0xFFFFFFFFu, xw);
+    ow = __reduce_add_sync(0xFFFFFFFFu, ow);
+    dr = __reduce_add_sync(0xFFFFFFFFu, dr);
+    co = __reduce_add_sync(0xFFFFFFFFu, co);
+    games = __reduce_add_sync(0xFFFFFFFFu, games);
+    st = __reduce_add_sync(0xFFFFFFFFu, st);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&sh[0], (unsigned long long)xw); atomicAdd(&sh[1], (unsigned long long)ow);
+        atomicAdd(&sh[2], (unsigned long long)dr); atomicAdd(&sh[3], (unsigned long long)st);
+        atomicAdd(&sh[4], (unsigned long long)co); atomicAdd(&sh[5], (unsigned long long)games);
+    }
+    __syncthreads();
+    if (threadIdx.x < 16 && sh[threadIdx.x]) atomicAdd(&stats[threadIdx.x], sh[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------ launch helpers
+static int grid_for(int64_t n) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = (n + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)sms * kBlocksPerSM;
+    return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+static int check_launch() {
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? QTTT_OK : -(1000 + (int)e);
+}
+static bool misaligned(const void* p, uintptr_t a) { return p && (reinterpret_cast<uintptr_t>(p) & (a - 1)); }
+
+}  // namespace qttt
+
+using namespace qttt;
+
+extern "C" {
+
+int qttt_abi_version(void) { return QTTT_ABI_VERSION; }
+
+const char* qttt_strerror(int rc) {
+    switch (rc) {
+        case QTTT_OK: return "ok";
+        case QTTT_ERR_ARG: return "qttt: invalid argument (NULL buffer, negative size or bad enum)";
+        case QTTT_ERR_ALIGN: return "qttt: buffer not aligned for its element type";
+        case QTTT_ERR_NO_DEVICE: return "qttt: no usable CUDA device";
+        default: break;
+    }
+    if (rc <= -1000) return cudaGetErrorString((cudaError_t)(-rc - 1000));
+    return "qttt: unknown error code";
+}
+
+int qttt_reset(qttt_state* state, uint64_t* mask, int64_t n, void* stream) {
+    if (!state || n < 0) return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(mask, 8)) return QTTT_ERR_ALIGN;
+    if (n == 0) return QTTT_OK;
+    k_reset<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state, mask, n);
+    return check_launch();
+}
+
+int qttt_step(qttt_state* state, const void* action, int action_format, const uint8_t* coin,
+              uint64_t seed, uint64_t game_base, float* reward, uint8_t* done, uint64_t* mask,
+              uint8_t* status, int64_t n, void* stream) {
+    if (!state || !action || n < 0) return QTTT_ERR_ARG;
+    if (action_format != QTTT_ACT_INDEX && action_format != QTTT_ACT_PAIR) return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(mask, 8) || misaligned(reward, 4)) return QTTT_ERR_ALIGN;
+    if (action_format == QTTT_ACT_PAIR && misaligned(action, 2)) return QTTT_ERR_ALIGN;
+    if (n == 0) return QTTT_OK;
+    const uint8_t* act = static_cast<const uint8_t*>(action);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (action_format == QTTT_ACT_INDEX)
+        k_step<QTTT_ACT_INDEX, false><<<grid_for(n), kThreads, 0, st>>>(state, act, coin, seed, game_base, reward, done, mask, status, nullptr, nullptr, n);
+    else
+        k_step<QTTT_ACT_PAIR, false><<<grid_for(n), kThreads, 0, st>>>(state, act, coin, seed, game_base, reward, done, mask, status, nullptr, nullptr, n);
+    return check_launch();
+}
+
+int qttt_step_random(qttt_state* state, uint64_t seed, uint64_t game_base, uint8_t* action_out,
+                     uint8_t* coin_out, float* reward, uint8_t* done, uint64_t* mask,
+                     uint8_t* status, int64_t n, void* stream) {
+    if (!state || n < 0) return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(mask, 8) || misaligned(reward, 4)) return QTTT_ERR_ALIGN;
+    if (n == 0) return QTTT_OK;
+    k_step<QTTT_ACT_INDEX, true><<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(
+        state, nullptr, nullptr, seed, game_base, reward, done, mask, status, action_out, coin_out, n);
+    return check_launch();
+}
+
+int qttt_observe(const qttt_state* state, int8_t* classical, int8_t* moves, uint8_t* n_moves,
+                 int8_t* q_p1, int8_t* q_p2, uint8_t* turn, int8_t* rounds, float* reward_p1,
+                 uint8_t* winner, uint8_t* mask_bool, int64_t n, void* stream) {
+    if (!state || n < 0) return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(reward_p1, 4)) return QTTT_ERR_ALIGN;
+    if (n == 0) return QTTT_OK;
+    k_observe<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state, classical, moves, n_moves, q_p1, q_p2, turn, rounds, reward_p1, winner, mask_bool, n);
+    return check_launch();
+}
+
+int qttt_pack(qttt_state* state, const int8_t* classical, const int8_t* moves,
+              const uint8_t* n_moves, int64_t n, void* stream) {
+    if (!state || !classical || !moves || !n_moves || n < 0) return QTTT_ERR_ARG;
+    if (misaligned(state, 16)) return QTTT_ERR_ALIGN;
+    if (n == 0) return QTTT_OK;
+    k_pack<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state, classical, moves, n_moves, n);
+    return check_launch();
+}
+
+int qttt_qeval_both(const qttt_state* state, const uint8_t* action, qttt_state* next0,
+                    qttt_state* next1, uint64_t* board0, uint64_t* board1, int8_t* sq0,
+                    int8_t* sq1, uint8_t* closes, float* result_prob, int64_t n, void* stream) {
+    if (!state || !action || n < 0) return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(next0, 16) || misaligned(next1, 16) ||
+        misaligned(board0, 8) || misaligned(board1, 8) || misaligned(result_prob, 4))
+        return QTTT_ERR_ALIGN;
+    if (n == 0) return QTTT_OK;
+    k_qeval_both<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state, action, next0, next1, board0, board1, sq0, sq1, closes, result_prob, n);
+    return check_launch();
+}
+
+int qttt_rollout(const qttt_state* roots, int64_t n_roots, int32_t n_rollouts, uint64_t seed,
+                 int32_t* tallies, float* value, int64_t* steps_total, void* stream) {
+    if (!roots || n_roots < 0 || n_rollouts <= 0 || n_roots > 0x7FFFFFFF) return QTTT_ERR_ARG;
+    if (misaligned(roots, 16) || misaligned(tallies, 4) || misaligned(value, 4) || misaligned(steps_total, 8))
+        return QTTT_ERR_ALIGN;
+    if (n_roots == 0) return QTTT_OK;
+    k_rollout<<<(int)n_roots, kThreads, 0, (cudaStream_t)stream>>>(
+        roots, n_rollouts, seed, tallies, value, reinterpret_cast<unsigned long long*>(steps_total));
+    return check_launch();
+}
+
+int qttt_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, int64_t* stats, void* stream) {
+    if (!stats || game_hi < game_lo) return QTTT_ERR_ARG;
+    if (misaligned(stats, 8)) return QTTT_ERR_ALIGN;
+    if (game_hi == game_lo) return QTTT_OK;
+    k_sweep<<<grid_for(game_hi - game_lo), kThreads, 0, (cudaStream_t)stream>>>(
+        game_lo, game_hi, seed, reinterpret_cast<unsigned long long*>(stats));
+    return check_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,321 @@
+"""Batched, GPU-resident stand-in for ``qtttgym.Env`` (reference: qtttgym/env.py:15-112).
+
+``BatchedEnv`` holds N independent games as packed 16-byte states in HBM and advances all of
+them with one kernel launch per ``step``.  The call shapes follow the reference's gym-like
+API -- ``reset() -> (obs, info)``, ``step(action) -> (obs, reward, terminated, truncated,
+info)`` -- with tensors in place of Python scalars.  ``Env`` is the ``num_envs == 1`` adapter
+that reproduces the reference's exact return types so it drops into ``qtttgym.Env`` call
+sites.  All arithmetic happens in libqttt_b200.so (CUDA, sm_100a); there is no CPU path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .actions import PAIRS
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class BatchedEnv:
+    """N quantum tic-tac-toe games on one GPU.
+
+    Parameters
+    ----------
+    num_envs : number of games.
+    device   : CUDA device.
+    seed     : Philox key for collapse coins (when ``choices`` is not forced) and for
+               ``step_random``; draws are keyed ``(seed, game_base + env index, len(moves))``
+               so results do not depend on how games are sharded over GPUs.
+    game_base: global id of env 0 (rank offset in multi-GPU runs).
+    obs_mode : ``"packed"`` (default) -> ``obs = {"packed": int32[N,4]}``, the live state tensor
+               (like the reference, whose obs aliases the live board -- quirk Q5);
+               ``"full"`` -> snapshot tensors per ``observation()``.
+    """
+
+    def __init__(self, num_envs: int, device="cuda", seed: int = 0, game_base: int = 0,
+                 obs_mode: str = "packed"):
+        if obs_mode not in ("packed", "full"):
+            raise ValueError("obs_mode must be 'packed' or 'full'")
+        self.lib = _lib.lib()                       # raises if the CUDA library is missing
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("qtttgym_b200 runs on CUDA devices only (no CPU fallback)")
+        self.num_envs = int(num_envs)
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.game_base = int(game_base)
+        self.obs_mode = obs_mode
+        n, dev = self.num_envs, self.device
+        self.state = torch.zeros((n, 4), dtype=torch.int32, device=dev)
+        self.reward = torch.empty(n, dtype=torch.float32, device=dev)
+        self.done = torch.empty(n, dtype=torch.uint8, device=dev)
+        self.mask = torch.empty(n, dtype=torch.int64, device=dev)     # 36-bit legal mask
+        self.status = torch.empty(n, dtype=torch.uint8, device=dev)
+        self._host_streams = None            # lazily created by step_host
+        self._d_act = self._d_coin = None
+        self.reset()
+
+    # ------------------------------------------------------------------ gym-like API
+    def reset(self, *, seed=None, options=None):
+        """env.py:55-57.  ``seed`` / ``options`` are accepted and ignored, as in the reference (Q4)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.qttt_reset(self.state.data_ptr(), self.mask.data_ptr(),
+                                           self.num_envs, _stream_ptr(self.device)))
+        return self._obs(), {"action_mask": self.mask}
+
+    def step(self, actions, choices=None):
+        """env.py:34-53 for every env.
+
+        actions : uint8[N] action indices 0..35 (mcts.py:339-349) **or** int8[N,2] ``(a, b)``
+                  pairs as passed to the reference's ``Env.step`` (any order).  Illegal actions
+                  are swallowed no-ops exactly as env.py:36-43 (``info["invalid"]``).
+        choices : uint8[N] forced collapse coins (0 -> the closing move falls into its smaller
+                  square, qeval.py:35), consumed only by envs whose move closes a cycle;
+                  ``None`` -> Philox coins.
+        Returns ``(obs, reward f32[N], terminated bool[N], truncated bool[N], info)``; reward is
+        the reference's -1.0 / -0.0 (quirk Q1).  The returned tensors are views of buffers that
+        the next ``step`` overwrites.
+        """
+        act, fmt = self._check_actions(actions)
+        coin = None
+        if choices is not None:
+            coin = choices if choices.dtype == torch.uint8 else choices.to(torch.uint8)
+            coin = coin.contiguous()
+            if coin.device != self.device or coin.numel() != self.num_envs:
+                raise ValueError("choices must be a uint8[N] tensor on the env's device")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.qttt_step(
+                self.state.data_ptr(), act.data_ptr(), fmt, _lib.ptr(coin), self.seed,
+                self.game_base, self.reward.data_ptr(), self.done.data_ptr(),
+                self.mask.data_ptr(), self.status.data_ptr(), self.num_envs,
+                _stream_ptr(self.device)))
+        return self._result()
+
+    def step_random(self, record: bool = False):
+        """One ply of the uniform-random policy of ``MCTS._simulate`` (mcts.py:185-198) for
+        every env that is not terminated; terminated envs are left untouched
+        (``info["status"] == 2``)."""
+        a_out = c_out = None
+        if record:
+            a_out = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
+            c_out = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.qttt_step_random(
+                self.state.data_ptr(), self.seed, self.game_base, _lib.ptr(a_out), _lib.ptr(c_out),
+                self.reward.data_ptr(), self.done.data_ptr(), self.mask.data_ptr(),
+                self.status.data_ptr(), self.num_envs, _stream_ptr(self.device)))
+        out = self._result()
+        if record:
+            out[4]["action"], out[4]["coin"] = a_out, c_out
+        return out
+
+    def step_host(self, actions_host, choices_host, reward_host, done_host, mask_host,
+                  chunks: int = 8, n_streams: int = 4):
+        """``step`` for callers whose buffers live in (pinned) HOST memory -- the end-to-end path.
+
+        actions_host uint8[N] action indices and choices_host uint8[N] coins are copied to the
+        device, the step kernel runs, and reward f32[N] / done uint8[N] / mask int64[N] are
+        copied back into the given host tensors.  The batch is cut into ``chunks`` slices that
+        are pipelined over ``n_streams`` side streams so that host->device copies, kernels and
+        device->host copies of different slices overlap (PCIe is full duplex).  Returns after
+        enqueueing; the current stream waits for all slices, so synchronise it before reading
+        the host outputs.
+        """
+        n, dev = self.num_envs, self.device
+        for t, dt in ((actions_host, torch.uint8), (choices_host, torch.uint8),
+                      (reward_host, torch.float32), (done_host, torch.uint8), (mask_host, torch.int64)):
+            if t.dtype != dt or t.numel() != n or t.device.type != "cpu" or not t.is_contiguous():
+                raise ValueError("step_host expects contiguous CPU tensors of N elements "
+                                 "(uint8 actions, uint8 coins, f32 reward, uint8 done, int64 mask)")
+        if self._host_streams is None or len(self._host_streams) != n_streams:
+            self._host_streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
+            self._d_act = torch.empty(n, dtype=torch.uint8, device=dev)
+            self._d_coin = torch.empty(n, dtype=torch.uint8, device=dev)
+        cur = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        chunks = max(1, min(chunks, (n + 255) // 256))
+        per = -(-n // chunks)
+        per = -(-per // 256) * 256
+        with torch.cuda.device(dev):
+            for c in range(chunks):
+                lo, hi = c * per, min(n, (c + 1) * per)
+                if lo >= hi:
+                    break
+                st = self._host_streams[c % n_streams]
+                st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    self._d_act[lo:hi].copy_(actions_host[lo:hi], non_blocking=True)
+                    self._d_coin[lo:hi].copy_(choices_host[lo:hi], non_blocking=True)
+                    _lib.check(self.lib.qttt_step(
+                        self.state.data_ptr() + 16 * lo, self._d_act.data_ptr() + lo, _lib.ACT_INDEX,
+                        self._d_coin.data_ptr() + lo, self.seed, self.game_base + lo,
+                        self.reward.data_ptr() + 4 * lo, self.done.data_ptr() + lo,
+                        self.mask.data_ptr() + 8 * lo, self.status.data_ptr() + lo, hi - lo,
+                        st.cuda_stream))
+                    reward_host[lo:hi].copy_(self.reward[lo:hi], non_blocking=True)
+                    done_host[lo:hi].copy_(self.done[lo:hi], non_blocking=True)
+                    mask_host[lo:hi].copy_(self.mask[lo:hi], non_blocking=True)
+            for st in self._host_streams:
+                fin = torch.cuda.Event()
+                fin.record(st)
+                cur.wait_event(fin)
+        return reward_host, done_host, mask_host
+
+    def turn(self):
+        """env.py:65-66: len(moves) per env (uint8[N])."""
+        return ((self.state[:, 0] >> 27) & 15).to(torch.uint8)
+
+    def observ(self):
+        return self.observation()
+
+    def observation(self, extras: bool = False):
+        """env.py:68-85 as tensors: ``classical`` int8[N,9], ``q_states_p1`` int8[N,5,2],
+        ``q_states_p2`` int8[N,4,2] (padded with -1), ``turn`` uint8[N]; with ``extras`` also
+        ``moves`` int8[N,9,2], ``n_moves``, ``rounds`` (check_win), ``reward_p1`` (Env._reward),
+        ``winner`` (0 none, 1 X, 2 O) and ``action_mask`` bool[N,36]."""
+        return observe_states(self.state, extras=extras)
+
+    def action_mask(self):
+        """mcts.py:87-91 for every env: bool[N,36]."""
+        bits = torch.arange(36, device=self.device, dtype=torch.int64)
+        return ((self.mask.unsqueeze(1) >> bits) & 1).bool()
+
+    # ------------------------------------------------------------------ helpers
+    def load_positions(self, classical, moves, n_moves):
+        """Sets every env to a reference-shaped position (Board.board, Board.moves)."""
+        self.state.copy_(pack_states(classical, moves, n_moves, self.device))
+        return self
+
+    def _check_actions(self, actions):
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(actions, device=self.device)
+        if actions.device != self.device:
+            raise ValueError("actions must live on the env's device")
+        if actions.dim() == 1:
+            if actions.dtype != torch.uint8:
+                actions = actions.to(torch.uint8)
+            fmt = _lib.ACT_INDEX
+        elif actions.dim() == 2 and actions.shape[1] == 2:
+            if actions.dtype != torch.int8:
+                # values outside int8 would wrap; anything outside 0..8 is illegal anyway
+                actions = actions.clamp(-1, 127).to(torch.int8)
+            fmt = _lib.ACT_PAIR
+        else:
+            raise ValueError("actions must be uint8[N] indices or int8[N,2] pairs")
+        if actions.shape[0] != self.num_envs:
+            raise ValueError(f"expected {self.num_envs} actions, got {actions.shape[0]}")
+        return actions.contiguous(), fmt
+
+    def _obs(self):
+        if self.obs_mode == "packed":
+            return {"packed": self.state}
+        return self.observation()
+
+    def _result(self):
+        info = {"action_mask": self.mask, "status": self.status, "invalid": self.status == 1}
+        terminated = self.done.bool()
+        return self._obs(), self.reward, terminated, torch.zeros_like(terminated), info
+
+
+def observe_states(state, extras: bool = False):
+    lib = _lib.lib()
+    n, dev = state.shape[0], state.device
+    e8 = lambda *shape: torch.empty(shape, dtype=torch.int8, device=dev)   # noqa: E731
+    out = {"classical": e8(n, 9), "q_states_p1": e8(n, 5, 2), "q_states_p2": e8(n, 4, 2),
+           "turn": torch.empty(n, dtype=torch.uint8, device=dev)}
+    ex = {}
+    if extras:
+        ex = {"moves": e8(n, 9, 2), "n_moves": torch.empty(n, dtype=torch.uint8, device=dev),
+              "rounds": e8(n, 2), "reward_p1": torch.empty(n, dtype=torch.float32, device=dev),
+              "winner": torch.empty(n, dtype=torch.uint8, device=dev),
+              "action_mask": torch.empty((n, 36), dtype=torch.uint8, device=dev)}
+    with torch.cuda.device(dev):
+        _lib.check(lib.qttt_observe(
+            state.data_ptr(), out["classical"].data_ptr(), _lib.ptr(ex.get("moves")),
+            _lib.ptr(ex.get("n_moves")), out["q_states_p1"].data_ptr(),
+            out["q_states_p2"].data_ptr(), out["turn"].data_ptr(), _lib.ptr(ex.get("rounds")),
+            _lib.ptr(ex.get("reward_p1")), _lib.ptr(ex.get("winner")),
+            _lib.ptr(ex.get("action_mask")), n, _stream_ptr(dev)))
+    if extras:
+        ex["action_mask"] = ex["action_mask"].bool()
+        out.update(ex)
+    return out
+
+
+def pack_states(classical, moves, n_moves, device="cuda"):
+    """Reference-shaped positions -> packed states int32[N,4] (see qttt_pack)."""
+    lib = _lib.lib()
+    dev = torch.device(device)
+    classical = torch.as_tensor(classical, dtype=torch.int8).to(dev).contiguous()
+    moves = torch.as_tensor(moves, dtype=torch.int8).to(dev).contiguous()
+    n_moves = torch.as_tensor(n_moves, dtype=torch.uint8).to(dev).contiguous()
+    n = classical.shape[0]
+    assert classical.shape == (n, 9) and moves.shape == (n, 9, 2) and n_moves.shape == (n,)
+    state = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.qttt_pack(state.data_ptr(), classical.data_ptr(), moves.data_ptr(),
+                                 n_moves.data_ptr(), n, _stream_ptr(dev)))
+    return state
+
+
+class Env:
+    """Single-env adapter with the reference's exact return types (qtttgym/env.py:15-66):
+    Python lists / tuples in ``obs``, a Python float reward (``-0.0`` / ``-1.0``), bools.
+
+    Deviations, all documented in DESIGN.md: ``obs["classical"]`` is a snapshot list, not an
+    alias of live state (Q5); the collapse coin comes from Philox ``(seed, 0, len(moves))``
+    unless ``coin`` is passed to ``step``; gymnasium spaces are not constructed (the reference's
+    ``observation_space`` is wrong anyway, Q6)."""
+
+    def __init__(self, device="cuda", seed: int = 0):
+        self._batched = BatchedEnv(1, device=device, seed=seed)
+        self._device = self._batched.device
+
+    def reset(self, *, seed=None, options=None):
+        self._batched.reset()
+        return self._observation(), {}
+
+    def step(self, action, verbose=False, coin=None):
+        try:
+            a, b = int(action[0]), int(action[1])
+        except Exception as e:              # env.py:41: anything raised becomes a no-op
+            if verbose:
+                print("noop (i.e. invalid) move...", e)
+            a = b = -1
+        a = a if -1 <= a <= 127 else -1
+        b = b if -1 <= b <= 127 else -1
+        act = torch.tensor([[a, b]], dtype=torch.int8, device=self._device)
+        ch = None if coin is None else torch.tensor([int(coin) & 1], dtype=torch.uint8,
+                                                    device=self._device)
+        _, reward, term, _, info = self._batched.step(act, ch)
+        if verbose and bool(info["invalid"][0]):
+            print("noop (i.e. invalid) move...")
+        return self._observation(), float(reward[0].item()), bool(term[0].item()), False, {}
+
+    def observ(self):
+        return self._observation()
+
+    def turn(self):
+        return int(self._batched.turn()[0].item())
+
+    def action_mask(self):
+        return self._batched.action_mask()[0].cpu().numpy()
+
+    def render(self):
+        print(self._observation())
+
+    def _observation(self):
+        o = self._batched.observation()
+        unpad = lambda t: [tuple(p) for p in t[0].tolist() if p[0] >= 0]   # noqa: E731
+        return {"q_states_p1": unpad(o["q_states_p1"]), "q_states_p2": unpad(o["q_states_p2"]),
+                "classical": o["classical"][0].tolist(), "turn": int(o["turn"][0].item())}
+
+    def _reward(self):
+        """env.py:87-112."""
+        return float(self._batched.observation(extras=True)["reward_p1"][0].item())
+
+
+__all__ = ["BatchedEnv", "Env", "observe_states", "pack_states", "PAIRS"]

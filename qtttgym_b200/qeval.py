@@ -1,0 +1,101 @@
+"""The measurement seam on the GPU (reference: qtttgym/qeval.py:5-51, called from
+qtttgym/board.py:51; MCTS._step's both-outcomes enumeration mcts.py:233-267).
+
+``qeval_both`` is the batched form.  ``QEvalB200`` is the duck-typed plugin: an object with
+``eval(entangled_moves) -> list[int]`` that can be handed to the reference's own
+``qtttgym.Board(qevaluator)`` (board.py:2,7) in place of ``QEvalClassic``.
+"""
+from __future__ import annotations
+
+import random as _random
+
+import torch
+
+from . import _lib
+from .actions import move2ind
+from .env import _stream_ptr, pack_states
+
+
+def qeval_both(state, actions, *, want_states=True, want_boards=True, want_squares=False,
+               want_probs=True):
+    """Both collapse outcomes of ``actions`` (uint8[N], 0..35) applied to packed ``state``
+    (int32[N,4]).  Returns a dict with
+
+    next0/next1  int32[N,4] successor states for coin 0 / 1 (equal when no cycle closes)
+    board0/board1 int64[N]  successor boards, 4 bits per square, value ``board[s] + 1``
+    sq0/sq1      int8[N,9]  square each move index collapses into (-1: not in the measurement)
+    closes       uint8[N]   1 when the action closes a cycle
+    result_prob  f32[N,3]   P(X wins), P(O wins), P(neither) over the two equiprobable outcomes
+    """
+    lib = _lib.lib()
+    dev, n = state.device, state.shape[0]
+    actions = actions.to(torch.uint8).contiguous()
+    assert actions.device == dev and actions.shape == (n,)
+    out = {"closes": torch.empty(n, dtype=torch.uint8, device=dev)}
+    if want_states:
+        out["next0"] = torch.empty_like(state)
+        out["next1"] = torch.empty_like(state)
+    if want_boards:
+        out["board0"] = torch.empty(n, dtype=torch.int64, device=dev)
+        out["board1"] = torch.empty(n, dtype=torch.int64, device=dev)
+    if want_squares:
+        out["sq0"] = torch.empty((n, 9), dtype=torch.int8, device=dev)
+        out["sq1"] = torch.empty((n, 9), dtype=torch.int8, device=dev)
+    if want_probs:
+        out["result_prob"] = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    g = lambda k: _lib.ptr(out.get(k))   # noqa: E731
+    with torch.cuda.device(dev):
+        _lib.check(lib.qttt_qeval_both(state.data_ptr(), actions.data_ptr(), g("next0"), g("next1"),
+                                       g("board0"), g("board1"), g("sq0"), g("sq1"),
+                                       out["closes"].data_ptr(), g("result_prob"), n,
+                                       _stream_ptr(dev)))
+    return out
+
+
+def square_probabilities(sq0, sq1):
+    """P[n, k, s] = probability that move k of the measured component collapses into square s
+    (values in {0, 1/2, 1}; SURVEY section 8(a) 'derived quantity for config 3')."""
+    n = sq0.shape[0]
+    p = torch.zeros((n, 9, 9), dtype=torch.float32, device=sq0.device)
+    for sq in (sq0, sq1):
+        valid = sq >= 0
+        idx = sq.clamp(min=0).long().unsqueeze(-1)
+        p.scatter_add_(2, idx, valid.unsqueeze(-1).float() * 0.5)
+    return p
+
+
+class QEvalB200:
+    """Drop-in for ``qtttgym.QEvalClassic`` at the plugin seam (board.py:51).
+
+    ``eval(entangled_moves)`` takes the component's ``(a, b, idx)`` moves in idx order, the last
+    one having closed the cycle, and returns the square each collapses into.  The coin is one
+    call to ``rng.choice((0, 1))`` -- the stdlib ``random`` module by default, which is what
+    the reference consumes (qeval.py:35) -- or a forced bit via ``force``.
+    """
+
+    def __init__(self, device="cuda", rng=None):
+        self.device = torch.device(device)
+        self.rng = rng if rng is not None else _random
+        self.forced: list[int] = []
+
+    def force(self, *bits):
+        self.forced.extend(int(b) & 1 for b in bits)
+
+    def eval(self, entangled_moves):
+        k = len(entangled_moves)
+        if not 2 <= k <= 9:
+            raise ValueError("a measured component has 2..9 moves")
+        classical = torch.full((1, 9), -1, dtype=torch.int8)
+        moves = torch.full((1, 9, 2), -1, dtype=torch.int8)
+        for r, m in enumerate(entangled_moves[:-1]):
+            moves[0, r, 0], moves[0, r, 1] = int(m[0]), int(m[1])
+        state = pack_states(classical, moves, torch.tensor([k - 1], dtype=torch.uint8), self.device)
+        last = entangled_moves[-1]
+        act = torch.tensor([move2ind(int(last[0]), int(last[1]))], dtype=torch.uint8,
+                           device=self.device)
+        res = qeval_both(state, act, want_states=False, want_boards=False, want_squares=True,
+                         want_probs=False)
+        if int(res["closes"][0].item()) != 1:
+            raise ValueError("the last move does not close a cycle in this component")
+        coin = self.forced.pop(0) if self.forced else self.rng.choice((0, 1))
+        return res["sq1" if coin else "sq0"][0, :k].tolist()

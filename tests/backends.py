@@ -1,0 +1,225 @@
+"""Two ways to run the packed-state transition, behind one numpy-facing interface:
+
+* ``CudaBackend``  -- the product: qtttgym_b200 (ctypes -> libqttt_b200.so -> CUDA kernels).
+* ``EmuBackend``   -- TEST ONLY: tests/hostemu/hostemu.cpp compiles the very same per-game
+  functions (qttt_core.cuh) for the CPU so the logic can be checked without a GPU.
+
+Both expose what oracle.c_oracle.Games exposes, so parity_suite.py can diff any of them
+against the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+# ------------------------------------------------------------------------------ host emulation
+class EmuBackend:
+    name = "hostemu"
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            src = os.path.join(HERE, "hostemu", "hostemu.cpp")
+            core = os.path.join(ROOT, "qtttgym_b200", "csrc", "qttt_core.cuh")
+            out_dir = os.path.join(HERE, "hostemu", "_build")
+            os.makedirs(out_dir, exist_ok=True)
+            out = os.path.join(out_dir, "libqttt_hostemu.so")
+            if (not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src),
+                                                                        os.path.getmtime(core))):
+                subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++",
+                                "-o", out, src], check=True)
+            cls._lib = C.CDLL(out)
+        return cls._lib
+
+    def games(self, n):
+        return EmuGames(n)
+
+    def sweep(self, lo, hi, seed):
+        stats = np.zeros(16, np.int64)
+        self.lib().emu_sweep(C.c_int64(lo), C.c_int64(hi), C.c_uint64(seed), _p(stats))
+        return stats
+
+
+class EmuGames:
+    def __init__(self, n):
+        self.n = int(n)
+        self.state = np.zeros((self.n, 4), np.uint32)
+        self.lib = EmuBackend.lib()
+        self.lib.emu_reset(_p(self.state), None, C.c_int64(self.n))
+
+    def _outs(self):
+        n = self.n
+        return dict(reward=np.empty(n, np.float32), done=np.empty(n, np.uint8),
+                    mask=np.empty(n, np.uint64), status=np.empty(n, np.uint8))
+
+    def step(self, pairs, coins=None):
+        ap = np.ascontiguousarray(pairs, dtype=np.int8).reshape(self.n, 2)
+        co = None if coins is None else np.ascontiguousarray(coins, dtype=np.uint8)
+        o = self._outs()
+        self.lib.emu_step(_p(self.state), _p(ap), 1, _p(co), C.c_uint64(0), C.c_uint64(0),
+                          _p(o["reward"]), _p(o["done"]), _p(o["mask"]), _p(o["status"]),
+                          C.c_int64(self.n))
+        return o
+
+    def step_index(self, actions, coins=None, seed=0, game_base=0):
+        ac = np.ascontiguousarray(actions, dtype=np.uint8)
+        co = None if coins is None else np.ascontiguousarray(coins, dtype=np.uint8)
+        o = self._outs()
+        self.lib.emu_step(_p(self.state), _p(ac), 0, _p(co), C.c_uint64(seed), C.c_uint64(game_base),
+                          _p(o["reward"]), _p(o["done"]), _p(o["mask"]), _p(o["status"]),
+                          C.c_int64(self.n))
+        return o
+
+    def step_random(self, seed, game_base=0):
+        o = self._outs()
+        o["action"] = np.empty(self.n, np.uint8)
+        o["coin"] = np.empty(self.n, np.uint8)
+        self.lib.emu_step_random(_p(self.state), C.c_uint64(seed), C.c_uint64(game_base),
+                                 _p(o["action"]), _p(o["coin"]), _p(o["reward"]), _p(o["done"]),
+                                 _p(o["mask"]), _p(o["status"]), C.c_int64(self.n))
+        return o
+
+    def observe(self):
+        n = self.n
+        o = dict(classical=np.empty((n, 9), np.int8), moves=np.empty((n, 9, 2), np.int8),
+                 n_moves=np.empty(n, np.uint8), q_p1=np.empty((n, 5, 2), np.int8),
+                 q_p2=np.empty((n, 4, 2), np.int8), turn=np.empty(n, np.uint8),
+                 rounds=np.empty((n, 2), np.int8), reward_p1=np.empty(n, np.float32),
+                 winner=np.empty(n, np.uint8), mask_bool=np.empty((n, 36), np.uint8))
+        self.lib.emu_observe(_p(self.state), _p(o["classical"]), _p(o["moves"]), _p(o["n_moves"]),
+                             _p(o["q_p1"]), _p(o["q_p2"]), _p(o["turn"]), _p(o["rounds"]),
+                             _p(o["reward_p1"]), _p(o["winner"]), _p(o["mask_bool"]), C.c_int64(n))
+        return o
+
+    def load(self, classical, moves, n_moves):
+        cl = np.ascontiguousarray(classical, np.int8)
+        mv = np.ascontiguousarray(moves, np.int8)
+        nm = np.ascontiguousarray(n_moves, np.uint8)
+        self.lib.emu_pack(_p(self.state), _p(cl), _p(mv), _p(nm), C.c_int64(self.n))
+        return self
+
+    def qeval_both(self, actions):
+        n = self.n
+        ac = np.ascontiguousarray(actions, np.uint8)
+        o = dict(next0=np.empty((n, 4), np.uint32), next1=np.empty((n, 4), np.uint32),
+                 board0=np.empty(n, np.uint64), board1=np.empty(n, np.uint64),
+                 sq0=np.empty((n, 9), np.int8), sq1=np.empty((n, 9), np.int8),
+                 closes=np.empty(n, np.uint8), result_prob=np.empty((n, 3), np.float32))
+        self.lib.emu_qeval_both(_p(self.state), _p(ac), _p(o["next0"]), _p(o["next1"]),
+                                _p(o["board0"]), _p(o["board1"]), _p(o["sq0"]), _p(o["sq1"]),
+                                _p(o["closes"]), _p(o["result_prob"]), C.c_int64(n))
+        return o
+
+    def rollout(self, n_rollouts, seed):
+        tallies = np.empty((self.n, 3), np.int32)
+        value = np.empty(self.n, np.float32)
+        steps = np.zeros(1, np.int64)
+        self.lib.emu_rollout(_p(self.state), C.c_int64(self.n), C.c_int32(n_rollouts),
+                             C.c_uint64(seed), _p(tallies), _p(value), _p(steps))
+        return tallies, value, int(steps[0])
+
+    def with_state(self, state):
+        g = EmuGames.__new__(EmuGames)
+        g.lib = self.lib
+        g.state = np.ascontiguousarray(state, np.uint32).reshape(-1, 4).copy()
+        g.n = g.state.shape[0]
+        return g
+
+
+# ------------------------------------------------------------------------------ CUDA (product)
+class CudaBackend:
+    name = "cuda"
+
+    def games(self, n):
+        return CudaGames(n)
+
+    def sweep(self, lo, hi, seed):
+        import qtttgym_b200 as Q
+        return Q.selfplay_sweep(lo, hi, seed).cpu().numpy()
+
+
+class CudaGames:
+    def __init__(self, n, seed=0, game_base=0):
+        import torch
+        import qtttgym_b200 as Q
+        self.torch, self.Q = torch, Q
+        self.n = int(n)
+        self.env = Q.BatchedEnv(self.n, seed=seed, game_base=game_base)
+
+    def _outs(self, res):
+        _, reward, term, _, info = res
+        t = self.torch
+        t.cuda.synchronize()
+        return dict(reward=reward.cpu().numpy().copy(), done=term.to(t.uint8).cpu().numpy(),
+                    mask=info["action_mask"].cpu().numpy().astype(np.uint64),
+                    status=info["status"].cpu().numpy().copy())
+
+    def step(self, pairs, coins=None):
+        t = self.torch
+        ap = t.from_numpy(np.ascontiguousarray(pairs, dtype=np.int8).reshape(self.n, 2)).cuda()
+        co = None if coins is None else t.from_numpy(np.ascontiguousarray(coins, np.uint8)).cuda()
+        return self._outs(self.env.step(ap, co))
+
+    def step_index(self, actions, coins=None, seed=0, game_base=0):
+        t = self.torch
+        self.env.seed, self.env.game_base = seed, game_base
+        ac = t.from_numpy(np.ascontiguousarray(actions, np.uint8)).cuda()
+        co = None if coins is None else t.from_numpy(np.ascontiguousarray(coins, np.uint8)).cuda()
+        return self._outs(self.env.step(ac, co))
+
+    def step_random(self, seed, game_base=0):
+        self.env.seed, self.env.game_base = seed, game_base
+        res = self.env.step_random(record=True)
+        o = self._outs(res)
+        o["action"] = res[4]["action"].cpu().numpy()
+        o["coin"] = res[4]["coin"].cpu().numpy()
+        return o
+
+    def observe(self):
+        o = self.env.observation(extras=True)
+        out = {k: v.cpu().numpy() for k, v in o.items()}
+        out["q_p1"], out["q_p2"] = out.pop("q_states_p1"), out.pop("q_states_p2")
+        out["mask_bool"] = out.pop("action_mask").astype(np.uint8)
+        return out
+
+    def load(self, classical, moves, n_moves):
+        self.env.load_positions(np.asarray(classical, np.int8), np.asarray(moves, np.int8),
+                                np.asarray(n_moves, np.uint8))
+        return self
+
+    @property
+    def state(self):
+        return self.env.state.cpu().numpy().view(np.uint32)
+
+    def qeval_both(self, actions):
+        t = self.torch
+        ac = t.from_numpy(np.ascontiguousarray(actions, np.uint8)).cuda()
+        res = self.Q.qeval_both(self.env.state, ac, want_squares=True)
+        out = {k: v.cpu().numpy() for k, v in res.items()}
+        for k in ("next0", "next1"):
+            out[k] = out[k].view(np.uint32)
+        for k in ("board0", "board1"):
+            out[k] = out[k].astype(np.uint64)
+        return out
+
+    def rollout(self, n_rollouts, seed):
+        tallies, value, steps = self.Q.rollout_eval(self.env.state, n_rollouts, seed)
+        return tallies.cpu().numpy(), value.cpu().numpy(), int(steps.item())
+
+    def with_state(self, state):
+        t = self.torch
+        g = CudaGames(np.asarray(state).reshape(-1, 4).shape[0])
+        g.env.state.copy_(t.from_numpy(np.ascontiguousarray(state).view(np.int32).reshape(-1, 4)).cuda())
+        return g

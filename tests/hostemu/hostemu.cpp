@@ -1,0 +1,124 @@
+// TEST INFRASTRUCTURE ONLY -- runs the per-game functions of qtttgym_b200/csrc/qttt_core.cuh
+// on the CPU with the same signatures as the C ABI (include/qttt_b200.h) minus streams, so
+// that the transition logic can be checked against the oracle in the build container (which
+// has no GPU) before GPU time is spent.  Never shipped, never loaded by qtttgym_b200: the
+// product path has no CPU fallback.
+#include <stdint.h>
+#include <string.h>
+
+#include "../../qtttgym_b200/csrc/qttt_core.cuh"
+
+using namespace qttt;
+
+static const LutImage g_img = make_lut_image();
+static Luts luts() { return luts_from_image(&g_img); }
+
+extern "C" {
+
+int emu_reset(State* state, uint64_t* mask, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) { state[i] = empty_state(); if (mask) mask[i] = 0xFFFFFFFFFull; }
+    return 0;
+}
+
+int emu_step(State* state, const void* action, int fmt, const uint8_t* coin, uint64_t seed,
+             uint64_t game_base, float* reward, uint8_t* done, uint64_t* mask, uint8_t* status,
+             int64_t n) {
+    const Luts L = luts();
+    const uint8_t* act = static_cast<const uint8_t*>(action);
+    for (int64_t i = 0; i < n; ++i) {
+        State s = state[i];
+        uint32_t enew, c;
+        if (fmt == 0) enew = L.pair[act[i]];
+        else enew = pair_to_edge(act[2 * i], act[2 * i + 1]);
+        if (coin) c = coin[i] & 1u;
+        else {
+            const uint64_t game = game_base + (uint64_t)i;
+            uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = n_moves(s), c3 = 0u;
+            philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+            c = c1 & 1u;
+        }
+        const StepResult r = step_core(s, enew, c);
+        state[i] = s;
+        emit_step_outputs(s, r, r.illegal, L, reward, done, mask, status, i);
+    }
+    return 0;
+}
+
+int emu_step_random(State* state, uint64_t seed, uint64_t game_base, uint8_t* action_out,
+                    uint8_t* coin_out, float* reward, uint8_t* done, uint64_t* mask,
+                    uint8_t* status, int64_t n) {
+    const Luts L = luts();
+    for (int64_t i = 0; i < n; ++i) {
+        State s = state[i];
+        const uint32_t C = classical(s), nm = n_moves(s);
+        const bool finished = (any_line(s, C, L) != 0u) | (nm >= 9u);
+        uint32_t act, c;
+        policy_draw(seed, game_base + (uint64_t)i, nm, 0u, L.legal[~C & M9], act, c);
+        if (finished) { act = 255u; c = 0u; }
+        if (action_out) action_out[i] = (uint8_t)act;
+        if (coin_out) coin_out[i] = (uint8_t)c;
+        const StepResult r = step_core(s, (uint32_t)L.pair[act], c);
+        state[i] = s;
+        emit_step_outputs(s, r, finished ? 2u : r.illegal, L, reward, done, mask, status, i);
+    }
+    return 0;
+}
+
+int emu_observe(const State* state, int8_t* classical_out, int8_t* moves, uint8_t* nmoves,
+                int8_t* q1, int8_t* q2, uint8_t* turn, int8_t* rounds, float* reward_p1,
+                uint8_t* winner, uint8_t* mask_bool, int64_t n) {
+    const Luts L = luts();
+    for (int64_t i = 0; i < n; ++i)
+        observe_game(state[i], L, classical_out, moves, nmoves, q1, q2, turn, rounds, reward_p1,
+                     winner, mask_bool, i);
+    return 0;
+}
+
+int emu_pack(State* state, const int8_t* classical_in, const int8_t* moves, const uint8_t* nmoves,
+             int64_t n) {
+    for (int64_t i = 0; i < n; ++i) state[i] = pack_game(classical_in, moves, nmoves, i);
+    return 0;
+}
+
+int emu_qeval_both(const State* state, const uint8_t* action, State* next0, State* next1,
+                   uint64_t* board0, uint64_t* board1, int8_t* sq0, int8_t* sq1, uint8_t* closes,
+                   float* result_prob, int64_t n) {
+    const Luts L = luts();
+    for (int64_t i = 0; i < n; ++i)
+        qeval_game(state[i], action[i], L, next0, next1, board0, board1, sq0, sq1, closes,
+                   result_prob, i);
+    return 0;
+}
+
+int emu_rollout(const State* roots, int64_t n_roots, int32_t n_rollouts, uint64_t seed,
+                int32_t* tallies, float* value, int64_t* steps_total) {
+    const Luts L = luts();
+    for (int64_t r = 0; r < n_roots; ++r) {
+        int t[3] = {0, 0, 0};
+        uint32_t steps = 0, cols = 0;
+        for (int32_t j = 0; j < n_rollouts; ++j) {
+            const uint32_t w = playout_game(roots[r], seed, (uint64_t)r * (uint64_t)n_rollouts + (uint64_t)j, 1u, L, steps, cols);
+            t[w == 1u ? 0 : (w == 2u ? 1 : 2)]++;
+        }
+        if (tallies) { tallies[3 * r] = t[0]; tallies[3 * r + 1] = t[1]; tallies[3 * r + 2] = t[2]; }
+        if (value) {
+            const float v = (float)(t[0] - t[1]) / (float)n_rollouts;
+            value[r] = (plies_of(roots[r]) & 1u) ? -v : v;
+        }
+        if (steps_total) *steps_total += steps;
+    }
+    return 0;
+}
+
+int emu_sweep(int64_t lo, int64_t hi, uint64_t seed, int64_t* stats) {
+    const Luts L = luts();
+    for (int64_t g = lo; g < hi; ++g) {
+        uint32_t steps = 0, cols = 0;
+        const uint32_t w = playout_game(empty_state(), seed, (uint64_t)g, 0u, L, steps, cols);
+        stats[w == 1u ? 0 : (w == 2u ? 1 : 2)]++;
+        stats[3] += steps; stats[4] += cols; stats[5]++; stats[6 + steps]++;
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,349 @@
+"""Backend-agnostic parity checks: every function takes a backend from tests/backends.py and
+diffs it against the oracle (oracle/c_oracle.py, pinned to the live reference) or against the
+fixtures recorded from the reference (tests/golden).  The GPU tests run them on the CUDA
+path; the CPU tests run the same checks on the host emulation of the same source."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import c_oracle as CO
+from oracle import qttt_oracle as O
+
+from helpers import load_golden, run_traces_and_check
+
+PAIRS = np.array(O.PAIRS, dtype=np.int8)
+OBS_KEYS = ("classical", "moves", "n_moves", "q_p1", "q_p2", "turn", "rounds", "reward_p1", "winner")
+
+
+def expand_mask(mask_u64):
+    bits = np.arange(36, dtype=np.uint64)
+    return ((mask_u64[:, None] >> bits) & np.uint64(1)).astype(bool)
+
+
+def assert_same_step(out, ref, where):
+    assert np.array_equal(out["reward"].view(np.uint32), ref["reward"].view(np.uint32)), f"{where}: reward bits"
+    assert np.array_equal(out["done"], ref["done"]), f"{where}: done"
+    assert np.array_equal(out["mask"], ref["mask"]), f"{where}: legal mask"
+    assert np.array_equal(out["status"], ref["status"]), f"{where}: status"
+
+
+def assert_same_obs(obs, ref, where):
+    for k in OBS_KEYS:
+        assert np.array_equal(obs[k], ref[k]), f"{where}: {k}"
+    if "mask_bool" in obs:
+        assert np.array_equal(obs["mask_bool"].astype(bool), expand_mask(_mask_from_obs(ref))), f"{where}: mask_bool"
+
+
+def _mask_from_obs(ref):
+    free = ref["classical"] < 0
+    m = np.zeros(free.shape[0], np.uint64)
+    for k, (i, j) in enumerate(O.PAIRS):
+        m |= (free[:, i] & free[:, j]).astype(np.uint64) << np.uint64(k)
+    return m
+
+
+# ------------------------------------------------------------------ golden fixtures
+def check_golden_traces(backend):
+    for fixture in ("kat_appendix_a.json.gz", "traces_v1.json.gz"):
+        data = load_golden(fixture)
+        games = list(data.values()) if isinstance(data, dict) else data
+        run_traces_and_check(backend.games, [g["trace"] for g in games],
+                             [g["records"] for g in games], where=f"{backend.name}:{fixture}")
+
+
+def check_golden_qeval(backend):
+    cases = load_golden("qeval_v1.json.gz")
+    n = len(cases)
+    classical = np.full((n, 9), -1, np.int8)
+    moves = np.full((n, 9, 2), -1, np.int8)
+    n_moves = np.zeros(n, np.uint8)
+    acts = np.zeros(n, np.uint8)
+    for i, case in enumerate(cases):
+        ent = case["entangled"]
+        for r, (a, b, _) in enumerate(ent[:-1]):
+            moves[i, r] = (a, b)
+        n_moves[i] = len(ent) - 1
+        acts[i] = O.move2ind(ent[-1][0], ent[-1][1])
+    res = backend.games(n).load(classical, moves, n_moves).qeval_both(acts)
+    for i, case in enumerate(cases):
+        k = len(case["entangled"])
+        assert res["closes"][i] == 1
+        assert res["sq0"][i][:k].tolist() == case["out0"], i
+        assert res["sq1"][i][:k].tolist() == case["out1"], i
+        assert (res["sq0"][i][k:] == -1).all() and (res["sq1"][i][k:] == -1).all()
+
+
+def check_golden_mcts_step(backend):
+    """mcts.py:233-267 children (both collapse outcomes), action lists, winner / terminal."""
+    recs = load_golden("mcts_step_v1.json.gz")
+    n = len(recs)
+    classical = np.array([r["board"] for r in recs], np.int8)
+    moves = np.full((n, 9, 2), -1, np.int8)
+    n_moves = np.zeros(n, np.uint8)
+    for i, r in enumerate(recs):
+        for m in r["moves"]:
+            moves[i, m[2]] = m[:2]
+        n_moves[i] = len(r["moves"])
+    games = backend.games(n).load(classical, moves, n_moves)
+    obs = games.observe()
+    for i, r in enumerate(recs):
+        assert obs["mask_bool"][i].astype(bool).tolist() == r["mask"]
+    acts = np.array([r["action"] for r in recs], np.uint8)
+    res = games.qeval_both(acts)
+    kids = [games.with_state(res["next0"]).observe(), games.with_state(res["next1"]).observe()]
+    for i, r in enumerate(recs):
+        assert int(res["closes"][i]) == (len(r["children"]) == 2), i
+        for c, ch in enumerate(r["children"]):
+            o = kids[c]
+            assert o["classical"][i].tolist() == ch["board"], (i, c)
+            nm = int(o["n_moves"][i])
+            assert [m + [j] for j, m in enumerate(o["moves"][i][:nm].tolist())] == ch["moves"], (i, c)
+            assert {0: None, 1: True, 2: False}[int(o["winner"][i])] == ch["winner"]
+            assert (int(o["winner"][i]) != 0 or nm == 9) == ch["terminal"]
+            assert np.nonzero(o["mask_bool"][i])[0].tolist() == ch["actions"]
+
+
+# ------------------------------------------------------------------ differential vs C oracle
+def random_actions(rng, mask_u64, illegal_rate):
+    """uniform legal (a, b) per env (random order), with injected illegal pairs."""
+    n = mask_u64.shape[0]
+    legal = expand_mask(mask_u64)
+    score = rng.random((n, 36)) * legal
+    k = score.argmax(1)
+    pairs = PAIRS[k].copy()
+    none = ~legal.any(1)
+    pairs[none] = (-1, -1)
+    flip = rng.random(n) < 0.5
+    pairs[flip] = pairs[flip][:, ::-1]
+    if illegal_rate > 0:
+        bad = rng.random(n) < illegal_rate
+        kind = rng.integers(0, 4, n)
+        r1 = rng.integers(0, 9, n).astype(np.int8)
+        r2 = rng.integers(0, 9, n).astype(np.int8)
+        big = rng.integers(9, 128, n).astype(np.int8)
+        neg = rng.integers(-128, 0, n).astype(np.int8)
+        cand = np.stack([
+            np.stack([r1, r1], 1),                 # same square
+            np.stack([big, r2], 1),                # off the board
+            np.stack([r1, neg], 1),                # negative index (outside the action domain)
+            np.stack([r1, r2], 1),                 # arbitrary pair: often hits a classical square
+        ], 0)
+        pairs[bad] = cand[kind[bad], np.nonzero(bad)[0]]
+    return pairs
+
+
+def check_random_play(backend, n_games, seed, illegal_rate=0.0, overrun=False, fmt="pair",
+                      full_obs_every=1):
+    """config 2: n_games envs stepped ply by ply on identical (action, coin) traces; every
+    output compared bit for bit after every call."""
+    rng = np.random.default_rng(seed)
+    ref = CO.Games(n_games)
+    dut = backend.games(n_games)
+    mask = np.full(n_games, (1 << 36) - 1, np.uint64)
+    done = np.zeros(n_games, bool)
+    total_steps = 0
+    for ply in range(14 if (illegal_rate > 0 or overrun) else 9):
+        pairs = random_actions(rng, mask, illegal_rate)
+        if not overrun:
+            pairs[done] = (-1, -1)             # finished envs idle (illegal no-op)
+        coins = rng.integers(0, 2, n_games).astype(np.uint8)
+        r = ref.step(pairs, coins)
+        if fmt == "pair":
+            o = dut.step(pairs, coins)
+        else:
+            a, b = pairs[:, 0].astype(np.int16), pairs[:, 1].astype(np.int16)
+            ok = (a >= 0) & (a < 9) & (b >= 0) & (b < 9) & (a != b)
+            lo, hi = np.minimum(a, b), np.maximum(a, b)
+            idx = np.where(ok, (15 * lo - lo * lo + 2 * hi - 2) // 2, rng.integers(36, 256, n_games))
+            o = dut.step_index(idx.astype(np.uint8), coins)
+        where = f"{backend.name} seed {seed} ply {ply}"
+        assert_same_step(o, r, where)
+        if ply % full_obs_every == 0 or ply >= 8:
+            assert_same_obs(dut.observe(), ref.observe(), where)
+        total_steps += int((r["status"] == 0).sum())
+        mask, done = r["mask"], r["done"].astype(bool)
+    assert_same_obs(dut.observe(), ref.observe(), f"{backend.name} seed {seed} final")
+    return total_steps
+
+
+def check_pack_observe_roundtrip(backend, n_games=2000, seed=5):
+    rng = np.random.default_rng(seed)
+    ref = CO.Games(n_games)
+    dut = backend.games(n_games)
+    mask = np.full(n_games, (1 << 36) - 1, np.uint64)
+    for ply in range(9):
+        stop = rng.random(n_games) < 0.15      # freeze some games at every depth
+        pairs = random_actions(rng, mask, 0.0)
+        pairs[stop] = (-1, -1)
+        coins = rng.integers(0, 2, n_games).astype(np.uint8)
+        mask = ref.step(pairs, coins)["mask"]
+        dut.step(pairs, coins)
+    obs = ref.observe()
+    packed = backend.games(n_games).load(obs["classical"], obs["moves"], obs["n_moves"])
+    assert np.array_equal(np.asarray(packed.state), np.asarray(dut.state)), "pack(observe(s)) != s"
+    assert_same_obs(packed.observe(), obs, "roundtrip")
+
+
+def harvest_positions(n_target, seed, want="closing"):
+    """Positions from random self-play on the oracle.
+    want='closing': (position, action) pairs at the moment a cycle-closing action is chosen;
+    want='any': positions at a uniformly random ply with a random legal action."""
+    rng = np.random.default_rng(seed)
+    out_cl, out_mv, out_nm, out_act = [], [], [], []
+    got = 0
+    while got < n_target:
+        n = 4096
+        ref = CO.Games(n)
+        mask = np.full(n, (1 << 36) - 1, np.uint64)
+        alive = np.ones(n, bool)
+        for ply in range(9):
+            legal = expand_mask(mask)
+            k = (rng.random((n, 36)) * legal).argmax(1).astype(np.uint8)
+            coins = rng.integers(0, 2, n).astype(np.uint8)
+            before = ref.observe()
+            both = ref.qeval_both(k)
+            if want == "closing":
+                take = alive & legal.any(1) & (both["closes"] == 1)
+            else:
+                take = alive & legal.any(1) & (rng.random(n) < 0.15)
+            if take.any():
+                out_cl.append(before["classical"][take]); out_mv.append(before["moves"][take])
+                out_nm.append(before["n_moves"][take]); out_act.append(k[take])
+                got += int(take.sum())
+            pairs = PAIRS[k].copy()
+            pairs[~alive | ~legal.any(1)] = (-1, -1)
+            r = ref.step(pairs, coins)
+            mask = r["mask"]
+            alive &= ~r["done"].astype(bool)
+    cat = lambda xs: np.concatenate(xs)[:n_target]   # noqa: E731
+    return cat(out_cl), cat(out_mv), cat(out_nm), cat(out_act)
+
+
+def check_qeval_both(backend, n_boards, seed):
+    """config 3: both outcomes bit-exact vs two forced-coin oracle calls; probabilities within
+    1e-6 (they are exactly 0, 1/2 or 1)."""
+    for want in ("closing", "any"):
+        cl, mv, nm, act = harvest_positions(n_boards, seed, want)
+        ref = CO.Games.from_arrays(cl, mv, nm)
+        want_res = ref.qeval_both(act)
+        dut = backend.games(len(act)).load(cl, mv, nm)
+        res = dut.qeval_both(act)
+        for k in ("closes", "sq0", "sq1"):
+            assert np.array_equal(res[k], want_res[k]), f"{backend.name} qeval {want}: {k}"
+        assert np.array_equal(res["board0"], want_res["out0"]) and np.array_equal(res["board1"], want_res["out1"])
+        probs = np.zeros((len(act), 3), np.float64)
+        for c in (0, 1):
+            branch = ref.copy()
+            branch.step(PAIRS[act], np.full(len(act), c, np.uint8))
+            bo = branch.observe()
+            assert_same_obs(dut.with_state(res[f"next{c}"]).observe(), bo, f"{backend.name} qeval next{c}")
+            probs[:, 0] += 0.5 * (bo["winner"] == 1)
+            probs[:, 1] += 0.5 * (bo["winner"] == 2)
+        probs[:, 2] = 1.0 - probs[:, 0] - probs[:, 1]
+        assert np.abs(res["result_prob"].astype(np.float64) - probs).max() <= 1e-6
+        if want == "closing":
+            assert (res["closes"] == 1).all()
+            assert (res["board0"] != res["board1"]).all()      # the two outcomes always differ
+
+
+def check_rollout(backend, n_roots, n_rollouts, seed):
+    """config 4: per-root tallies identical to the oracle playing the same Philox stream from
+    the same roots; value per mcts.py:171-173."""
+    cl, mv, nm, _ = harvest_positions(n_roots, seed, "any")
+    # add the empty root, a terminal root and an autofilled root when available
+    ref = CO.Games.from_arrays(cl, mv, nm)
+    want_t, want_steps = ref.rollout(n_rollouts, seed)
+    dut = backend.games(len(nm)).load(cl, mv, nm)
+    tallies, value, steps = dut.rollout(n_rollouts, seed)
+    assert np.array_equal(tallies, want_t), f"{backend.name} rollout tallies"
+    assert steps == want_steps
+    assert (tallies.sum(1) == n_rollouts).all()
+    autofill = (nm == 9) & (mv[:, 8, 0] == mv[:, 8, 1])
+    plies = nm.astype(np.int64) - autofill
+    r = (tallies[:, 0] - tallies[:, 1]).astype(np.float32) / np.float32(n_rollouts)
+    want_v = np.where(plies % 2 == 0, r, -r).astype(np.float32)
+    assert np.abs(value - want_v).max() <= 1e-6
+
+
+def check_rollout_terminal_roots(backend):
+    """terminal and autofilled roots: zero-length playouts, value sign from plies (mcts.py:243)."""
+    kat = load_golden("kat_appendix_a.json.gz")
+    recs = [kat["kat8"]["records"][-1], kat["kat7"]["records"][-1], kat["kat10"]["records"][-1]]
+    n = len(recs)
+    classical = np.array([r["board"] for r in recs], np.int8)
+    moves = np.full((n, 9, 2), -1, np.int8)
+    nmv = np.array([len(r["moves"]) for r in recs], np.uint8)
+    for i, r in enumerate(recs):
+        for m in r["moves"]:
+            moves[i, m[2]] = m[:2]
+    tallies, value, steps = backend.games(n).load(classical, moves, nmv).rollout(8, 3)
+    assert steps == 0
+    assert tallies.tolist() == [[0, 8, 0], [8, 0, 0], [0, 8, 0]]
+    # kat8: 9 entries, 8 plies -> turn True -> value = r = -1; kat7: 5 plies -> -(+1); kat10: 7 plies -> -(-1)
+    assert value.tolist() == [-1.0, -1.0, 1.0]
+
+
+def check_sweep(backend, n_games, seed):
+    """config 5: tallies identical to the oracle's self-play on the same Philox stream, and
+    additive over shards of the game-id range (the multi-GPU invariant)."""
+    want, hist = CO.selfplay(0, n_games, seed)
+    got = backend.sweep(0, n_games, seed)
+    assert got[:6].tolist() == want.tolist(), (got[:6], want)
+    assert got[6:].tolist() == hist.tolist()
+    cuts = [0, n_games // 3, n_games // 2 + 7, n_games]
+    parts = sum(backend.sweep(a, b, seed) for a, b in zip(cuts[:-1], cuts[1:]))
+    assert parts.tolist() == got.tolist()
+    off = backend.sweep(10_000_000_000, 10_000_000_000 + 257, seed)     # 64-bit game ids
+    want_off, _ = CO.selfplay(10_000_000_000, 10_000_000_000 + 257, seed)
+    assert off[:6].tolist() == want_off.tolist()
+
+
+def check_step_random(backend, n_games, seed, game_base=0):
+    """step_random traces == the oracle's Philox playouts; replaying the emitted (action, coin)
+    trace through the oracle ends in the same state."""
+    dut = backend.games(n_games)
+    ref = CO.Games(n_games)
+    acts, coins = [], []
+    for ply in range(9):
+        o = dut.step_random(seed, game_base)
+        acts.append(o["action"]); coins.append(o["coin"])
+        pairs = np.full((n_games, 2), -1, np.int8)
+        live = o["action"] < 36
+        pairs[live] = PAIRS[o["action"][live]]
+        r = ref.step(pairs, o["coin"])
+        assert np.array_equal(o["status"] == 2, ~live)
+        assert np.array_equal(o["status"][live], r["status"][live]) and (r["status"][live] == 0).all()
+        assert np.array_equal(o["reward"].view(np.uint32), r["reward"].view(np.uint32))
+        assert np.array_equal(o["done"], r["done"]) and np.array_equal(o["mask"], r["mask"])
+    assert_same_obs(dut.observe(), ref.observe(), "step_random final")
+    fin = dut.observe()
+    assert ((fin["winner"] != 0) | (fin["n_moves"] == 9)).all()        # all games terminated
+    acts, coins = np.stack(acts, 1), np.stack(coins, 1)
+    for g in range(min(n_games, 300)):
+        w, a, c, _ = CO.playout_trace(CO.Games(1), 0, seed, game_base + g, 0)
+        k = len(a)
+        assert acts[g, :k].tolist() == a.tolist() and coins[g, :k].tolist() == c.tolist()
+        assert (acts[g, k:] == 255).all()
+        assert int(fin["winner"][g]) == w
+
+
+def check_philox_coin(backend, n_games=3000, seed=99, game_base=1234):
+    """step(..., choices=None): the coin is bit 0 of x1 of Philox(seed; game, len(moves), 0)."""
+    rng = np.random.default_rng(seed)
+    ref = CO.Games(n_games)
+    dut = backend.games(n_games)
+    mask = np.full(n_games, (1 << 36) - 1, np.uint64)
+    for ply in range(9):
+        legal = expand_mask(mask)
+        k = (rng.random((n_games, 36)) * legal).argmax(1).astype(np.uint8)
+        k[~legal.any(1)] = 255
+        nm = ref.observe()["n_moves"]
+        coins = np.array([O.policy_draw(seed, game_base + g, int(nm[g]), 0)[1] & 1
+                          for g in range(n_games)], np.uint8)
+        pairs = np.full((n_games, 2), -1, np.int8)
+        pairs[k < 36] = PAIRS[k[k < 36]]
+        r = ref.step(pairs, coins)
+        o = dut.step_index(k, None, seed=seed, game_base=game_base)
+        assert_same_step(o, r, f"philox coin ply {ply}")
+        mask = r["mask"]
+    assert_same_obs(dut.observe(), ref.observe(), "philox coin final")

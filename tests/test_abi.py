@@ -1,0 +1,85 @@
+"""CPU: the C-ABI library loads and exports every symbol include/*.h declares (no compute)."""
+import ctypes as C
+import glob
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = set()
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        text = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
+        names |= set(re.findall(r"QTTT_API[^;(]*?\b(qttt_\w+)\s*\(", text))
+    return names
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from qtttgym_b200 import build
+    return build.build()
+
+
+def test_header_declares_the_expected_surface():
+    assert _declared_symbols() == {
+        "qttt_abi_version", "qttt_strerror", "qttt_reset", "qttt_step", "qttt_step_random",
+        "qttt_observe", "qttt_pack", "qttt_qeval_both", "qttt_rollout", "qttt_sweep"}
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    out = subprocess.run(["nm", "-D", "--defined-only", built_lib], capture_output=True, text=True, check=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert _declared_symbols() <= exported
+    assert not any(s.startswith("orc_") or s.startswith("emu_") for s in exported)   # no oracle / emulation inside
+
+
+def test_ctypes_binding_matches_header(built_lib):
+    from qtttgym_b200 import _lib
+    assert set(_lib.EXPORTED_SYMBOLS) == _declared_symbols()
+    lib = _lib.lib()
+    assert lib.qttt_abi_version() == 1
+    assert lib.qttt_strerror(0) == b"ok"
+    assert b"invalid argument" in lib.qttt_strerror(-1)
+    # argument validation happens before any CUDA call, so it is testable without a GPU
+    assert lib.qttt_reset(None, None, 4, None) == -1
+    assert lib.qttt_sweep(3, 2, 0, None, None) == -1
+
+
+def test_sass_is_sm100_only(built_lib):
+    out = subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_cpu_fallback_in_package():
+    """The product never imports the oracle or the host emulation."""
+    pkg = os.path.join(ROOT, "qtttgym_b200")
+    for path in glob.glob(os.path.join(pkg, "**", "*.py"), recursive=True):
+        text = open(path).read()
+        assert "oracle" not in text.replace("# oracle", ""), path
+        assert "hostemu" not in text, path
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from qtttgym_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.QtttLibraryError):
+        _lib.lib()
+
+
+def test_action_table():
+    import qtttgym_b200 as Q
+    assert len(Q.PAIRS) == 36 and Q.PAIRS[0] == (0, 1) and Q.PAIRS[7] == (0, 8) and Q.PAIRS[35] == (7, 8)
+    for k, (i, j) in enumerate(Q.PAIRS):
+        assert Q.ind2move(k) == (i, j) and Q.move2ind(i, j) == k == Q.move2ind(j, i)
+
+
+def test_cpu_device_is_refused():
+    import qtttgym_b200 as Q
+    with pytest.raises(RuntimeError):
+        Q.BatchedEnv(4, device="cpu")

@@ -1,0 +1,203 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes ->
+libqttt_b200.so), against the oracle and the fixtures recorded from the live reference."""
+import os
+
+import numpy as np
+import pytest
+
+import parity_suite as S
+from backends import CudaBackend
+from helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    import torch
+    assert torch.cuda.is_available()
+    import qtttgym_b200._lib as L
+    L.lib()                       # fails loudly when the CUDA library is missing
+    return CudaBackend()
+
+
+def test_native_library_is_the_in_tree_one(cuda):
+    import qtttgym_b200._lib as L
+    with open("/proc/self/maps") as f:
+        loaded = [l.split()[-1] for l in f if "libqttt_b200.so" in l]
+    assert loaded and os.path.samefile(loaded[0], L.LIB)
+    assert not any("libqttt_oracle" in p and "qtttgym_b200" in p for p in loaded)
+
+
+def test_golden_traces(cuda):
+    S.check_golden_traces(cuda)
+
+
+def test_golden_qeval(cuda):
+    S.check_golden_qeval(cuda)
+
+
+def test_golden_mcts_step(cuda):
+    S.check_golden_mcts_step(cuda)
+
+
+@pytest.mark.parametrize("seed,illegal,overrun,fmt", [
+    (20261018, 0.0, False, "index"),      # config 2: 4096 envs, random legal actions, forced coins
+    (20261019, 0.1, True, "pair"),        # config 2b: 10 % illegal actions + post-terminal moves
+    (20261020, 0.1, True, "index")])
+def test_config2_4096_envs(cuda, seed, illegal, overrun, fmt):
+    S.check_random_play(cuda, 4096, seed, illegal, overrun, fmt)
+
+
+def test_equivalence_suite_one_million_games(cuda):
+    """North-star: bit-exact on 1e6 random games (4 x 262,144 envs, every output after every ply)."""
+    total = 0
+    for b in range(4):
+        total += S.check_random_play(cuda, 262144, 1000 + b, illegal_rate=0.02 * (b % 2), fmt=("pair", "index")[b // 2])
+    assert total > 8.0e6
+
+
+@pytest.mark.parametrize("n", [1, 31, 257, 4097])
+def test_ragged_batch_sizes(cuda, n):
+    S.check_random_play(cuda, n, 77 + n, illegal_rate=0.05, overrun=True)
+
+
+def test_empty_batch(cuda):
+    import torch
+    import qtttgym_b200 as Q
+    env = Q.BatchedEnv(0)
+    obs, r, term, trunc, info = env.step(torch.zeros(0, dtype=torch.uint8, device="cuda"))
+    assert r.numel() == 0 and term.numel() == 0
+    assert Q.selfplay_sweep(5, 5, 1).sum().item() == 0
+
+
+def test_pack_observe_roundtrip(cuda):
+    S.check_pack_observe_roundtrip(cuda, 20000)
+
+
+def test_config3_qeval_one_million_boards(cuda):
+    S.check_qeval_both(cuda, 1 << 20, 7)
+
+
+def test_config4_rollout_1024_roots_x_256(cuda):
+    S.check_rollout(cuda, 1024, 256, 11)
+    S.check_rollout_terminal_roots(cuda)
+
+
+def test_rollout_non_multiple_of_block(cuda):
+    S.check_rollout(cuda, 33, 300, 12)
+    S.check_rollout(cuda, 5, 1, 13)
+
+
+def test_config5_sweep_matches_oracle_and_shards(cuda):
+    S.check_sweep(cuda, 2_000_000, 13)
+
+
+def test_step_random_traces(cuda):
+    S.check_step_random(cuda, 50000, 17, game_base=123456789012)
+
+
+def test_philox_coin(cuda):
+    S.check_philox_coin(cuda, 3000)
+
+
+def test_step_api_and_sweep_agree_at_full_size(cuda):
+    """Size-independent property at 2^24 envs: playing the random policy through the step API
+    (9 launches of K1) gives exactly the tallies of the fused sweep (K5) on the same game ids."""
+    import torch
+    import qtttgym_b200 as Q
+    n, seed, base = 1 << 24, 424242, 7_000_000_000
+    env = Q.BatchedEnv(n, seed=seed, game_base=base)
+    steps = 0
+    for _ in range(9):
+        _, _, _, _, info = env.step_random()
+        steps += int((info["status"] == 0).sum().item())
+    obs = env.observation(extras=True)
+    w = torch.bincount(obs["winner"].long(), minlength=3)
+    stats = Q.selfplay_sweep(base, base + n, seed)
+    assert [int(w[1]), int(w[2]), int(w[0])] == stats[:3].tolist()
+    assert steps == int(stats[3]) and int(stats[5]) == n
+    assert bool(((obs["winner"] != 0) | (obs["n_moves"] == 9)).all())
+
+
+def test_population_statistics(cuda):
+    """T2: tallies of 2M Philox games vs the reference's own MT19937 tallies (20k games)."""
+    ref = load_golden("population_v1.json")
+    stats = cuda.sweep(0, 2_000_000, 5)
+    n, m = stats[5], ref["games"]
+    for k, key in enumerate(("x", "o", "draw")):
+        p, q = stats[k] / n, ref[key] / m
+        assert abs(p - q) < 5 * (q * (1 - q) * (1 / n + 1 / m)) ** 0.5
+    hist = stats[6:] / n
+    ref_hist = np.array(ref["steps_hist"]) / m
+    assert np.abs(hist - ref_hist).max() < 0.02
+
+
+def test_single_env_adapter_reference_types(cuda):
+    """Env (num_envs=1) returns the reference's Python types and values on the Appendix-A games."""
+    import qtttgym_b200 as Q
+    kat = load_golden("kat_appendix_a.json.gz")
+    for name, g in kat.items():
+        env = Q.Env()
+        obs, info = env.reset(seed=123)
+        assert info == {} and obs == {"q_states_p1": [], "q_states_p2": [], "classical": [-1] * 9, "turn": 0}
+        for (a, b, coin), rec in zip(g["trace"], g["records"]):
+            obs, r, term, trunc, info = env.step((a, b), coin=coin)
+            assert isinstance(r, float) and isinstance(term, bool) and trunc is False and info == {}
+            assert np.float32(r).view(np.uint32) == rec["reward_bits"], name
+            assert term == rec["terminated"]
+            assert obs["classical"] == rec["board"] and obs["turn"] == rec["turn"]
+            assert [list(p) for p in obs["q_states_p1"]] == rec["q1"]
+            assert [list(p) for p in obs["q_states_p2"]] == rec["q2"]
+            assert env.turn() == len(rec["moves"]) and env._reward() == rec["reward_p1"]
+
+
+def test_qeval_plugin_seam(cuda):
+    """QEvalB200.eval is a drop-in for QEvalClassic.eval (board.py:51 -> qeval.py:5)."""
+    import qtttgym_b200 as Q
+    ev = Q.QEvalB200()
+    for case in load_golden("qeval_v1.json.gz")[:60]:
+        ent = [tuple(m) for m in case["entangled"]]
+        ev.force(0)
+        assert ev.eval(ent) == case["out0"]
+        ev.force(1)
+        assert ev.eval(ent) == case["out1"]
+    # unforced: the coin comes from the stdlib random module, like the reference
+    import random
+    random.seed(3)
+    got = {tuple(ev.eval([(0, 1, 0), (0, 1, 1)])) for _ in range(40)}
+    assert got == {(0, 1), (1, 0)}
+
+
+def test_square_probabilities(cuda):
+    import torch
+    import qtttgym_b200 as Q
+    cl, mv, nm, act = S.harvest_positions(5000, 3, "closing")
+    st = Q.pack_states(cl, mv, nm)
+    res = Q.qeval_both(st, torch.from_numpy(act).cuda(), want_squares=True)
+    p = Q.square_probabilities(res["sq0"], res["sq1"]).cpu().numpy()
+    assert set(np.unique(p).tolist()) <= {0.0, 0.5, 1.0}
+    rows = p.sum(2)                                # each measured move: total probability 1
+    measured = (res["sq0"] >= 0).cpu().numpy()
+    assert np.abs(rows[measured] - 1.0).max() <= 1e-6 and np.abs(rows[~measured]).max() == 0
+    cols = p.sum(1)                                # each square of the component gets exactly one move
+    assert set(np.unique(cols).tolist()) <= {0.0, 1.0}
+
+
+def test_error_codes(cuda):
+    import ctypes as C
+    import torch
+    import qtttgym_b200._lib as L
+    lib = L.lib()
+    st = torch.zeros((8, 4), dtype=torch.int32, device="cuda")
+    act = torch.zeros(8, dtype=torch.uint8, device="cuda")
+    assert lib.qttt_reset(None, None, 8, None) == -1
+    assert lib.qttt_reset(st.data_ptr(), None, -1, None) == -1
+    assert lib.qttt_step(st.data_ptr(), act.data_ptr(), 7, None, 0, 0, None, None, None, None, 8, None) == -1
+    assert lib.qttt_reset(st.data_ptr() + 4, None, 4, None) == -2
+    assert lib.qttt_rollout(st.data_ptr(), 8, 0, 0, None, None, None, None) == -1
+    assert lib.qttt_sweep(5, 4, 0, st.data_ptr(), None) == -1
+    assert b"invalid argument" in lib.qttt_strerror(-1) and b"aligned" in lib.qttt_strerror(-2)
+    with pytest.raises(RuntimeError):
+        L.check(-1)
+    torch.cuda.synchronize()

@@ -1,0 +1,58 @@
+"""CPU (no GPU): the CUDA source's per-game functions, compiled for the host
+(tests/hostemu), against the oracle and the reference fixtures.  This is a pre-flight of the
+kernel LOGIC; the real parity tests are tests/test_gpu_parity.py, which run the same suite
+through the C ABI on the device."""
+import pytest
+
+import parity_suite as S
+from backends import EmuBackend
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return EmuBackend()
+
+
+def test_golden_traces(emu):
+    S.check_golden_traces(emu)
+
+
+def test_golden_qeval(emu):
+    S.check_golden_qeval(emu)
+
+
+def test_golden_mcts_step(emu):
+    S.check_golden_mcts_step(emu)
+
+
+@pytest.mark.parametrize("seed,illegal,overrun,fmt", [
+    (1, 0.0, False, "pair"), (2, 0.1, False, "pair"), (3, 0.1, True, "pair"),
+    (4, 0.0, False, "index"), (5, 0.1, True, "index")])
+def test_random_play(emu, seed, illegal, overrun, fmt):
+    steps = S.check_random_play(emu, 20000, seed, illegal, overrun, fmt)
+    assert steps > 100000
+
+
+def test_pack_observe_roundtrip(emu):
+    S.check_pack_observe_roundtrip(emu)
+
+
+def test_qeval_both(emu):
+    S.check_qeval_both(emu, 20000, 7)
+
+
+def test_rollout(emu):
+    S.check_rollout(emu, 64, 32, 11)
+    S.check_rollout_terminal_roots(emu)
+
+
+def test_sweep(emu):
+    S.check_sweep(emu, 30000, 13)
+
+
+def test_step_random(emu):
+    S.check_step_random(emu, 2000, 17, game_base=5)
+
+
+def test_philox_coin(emu):
+    S.check_philox_coin(emu, 1500)
