@@ -55,54 +55,63 @@ def measured_hbm_peak():
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and clock-event (throttle) reasons through NVML from a background
+    thread every ~2 ms DURING the timed region (the timed region of a short run is only tens
+    of milliseconds, too short for an `nvidia-smi -lms` subprocess to see)."""
 
-    def __init__(self, gpu_index: int):
-        self.proc = None
-        self.path = f"/tmp/qttt_clocks_{os.getpid()}.csv"
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap"}
+
+    def __init__(self, torch_device):
+        import threading
+        self.samples, self.masks = [], []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.err = None
         try:
-            self.fh = open(self.path, "w")
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
-                stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            handle = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(torch_device).uuid)
+                uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+                handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(torch_device.index or 0)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+                        self.masks.append(int(get_reasons(handle)))
+                    except Exception as e:   # pragma: no cover
+                        self.err = repr(e)
+                        return
+                    time.sleep(0.002)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception as e:
+            self.err = repr(e)
+            self.thread = None
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.fh.close()
-        sm, mx, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for line in open(self.path):
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 8:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        try:
-            os.remove(self.path)
-        except OSError:
-            pass
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = [c for c in sm if c >= 0.5 * max(sm)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "samples": len(sm),
-                "reasons": sorted(reasons)}
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [f"no samples ({self.err})"]}
+        seen = 0
+        for m in self.masks:
+            seen |= m
+        reasons = sorted(name for bit, name in self.REASONS.items() if seen & bit)
+        return {"sm_mhz": statistics.median(self.samples), "sm_min_mhz": min(self.samples),
+                "sm_max_mhz": self.max_mhz, "samples": len(self.samples), "reasons": reasons,
+                "how": "NVML SM clock + clock-event reasons sampled every ~2 ms inside the timed region"}
 
 
 # ----------------------------------------------------------------------------- reference arm
@@ -221,7 +230,7 @@ def run_b200(args):
     for it in range(W + K):
         if it == W:
             barrier()
-            sampler = ClockSampler(local_rank)
+            sampler = ClockSampler(dev)
             start.record()
         env.reset()
         for ply in range(PLIES):
@@ -256,7 +265,7 @@ def run_b200(args):
     h_act = actions.cpu().pin_memory()
     h_coin = coins.cpu().pin_memory()
     h_reward = torch.empty(E, dtype=torch.float32).pin_memory()
-    h_done = torch.empty(E, dtype=torch.uint8).pin_memory()
+    h_done = torch.empty(E, dtype=torch.bool).pin_memory()
     h_mask = torch.empty(E, dtype=torch.int64).pin_memory()
     e2e_K = max(1, min(K, args.e2e_steps))
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -271,7 +280,7 @@ def run_b200(args):
     barrier()
     e2e_ms = max_over_ranks(s2.elapsed_time(e2))
     e2e_value = sum_over_ranks(float(steps_per_pass)) * e2e_K / (e2e_ms * 1e-3)
-    assert int((h_done != 0).sum()) == E, "e2e pass did not finish every game"
+    assert int(h_done.sum()) == E, "e2e pass did not finish every game"
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * E * PLIES,
            "d2h_bytes_per_step": 13 * E * PLIES, "steps": e2e_K, "ms_per_step": e2e_ms / e2e_K,
            "api": "BatchedEnv.reset + 9 x BatchedEnv.step_host (pinned host actions/coins in, "

@@ -108,11 +108,17 @@ struct LutImage {
     uint64_t legal[512];    // free-square set -> 36-bit legal mask            (mcts.py:19-27)
     uint16_t pair[256];     // action index -> E mask of (i, j); 0 for index >= 36 (mcts.py:339-343)
     uint8_t  line[512];     // square set -> 1 if it contains one of the 8 lines (board.py:84-110)
+    uint32_t nrow[16][4];   // per len(moves): multipliers (see NRow)
     uint64_t spread[512];   // square set -> the same bits at a 4-bit stride
 };
-constexpr int kLutStepBytes = 512 * 8 + 256 * 2 + 512;   // legal + pair + line = 5120
-constexpr int kLutBytes = (int)sizeof(LutImage);        // 9216
-static_assert(sizeof(LutImage) == 9216, "LutImage layout");
+// Row n of LutImage::nrow: everything the transition needs that depends only on n = len(moves),
+// as multipliers so the work lands on the (otherwise idle) IMAD pipe:
+//   mx, my, mz : E << (bit offset of move slot n) == E * m? in the word that holds slot n (else 0)
+//   kp         : plane pattern of v = n + 1 for word w: (v&1) | (v&2)<<8 | (v&4)<<16
+struct NRow { uint32_t mx, my, mz, kp; };
+constexpr int kLutStepBytes = 512 * 8 + 256 * 2 + 512 + 256;   // legal + pair + line + nrow = 5376
+constexpr int kLutBytes = (int)sizeof(LutImage);        // 9472
+static_assert(sizeof(LutImage) == 9472, "LutImage layout");
 
 constexpr LutImage make_lut_image() {
     LutImage t{};
@@ -135,6 +141,13 @@ constexpr LutImage make_lut_image() {
     int k = 0;
     for (int i = 0; i < 9; ++i)
         for (int j = i + 1; j < 9; ++j, ++k) t.pair[k] = (uint16_t)((1u << i) | (1u << j));
+    for (uint32_t n = 0; n < 9; ++n) {
+        const uint32_t m = 1u << (9u * (n % 3u)), v = n + 1u;
+        t.nrow[n][0] = n < 3u ? m : 0u;
+        t.nrow[n][1] = (n >= 3u && n < 6u) ? m : 0u;
+        t.nrow[n][2] = n >= 6u ? m : 0u;
+        t.nrow[n][3] = (v & 1u) | ((v & 2u) << 8) | ((v & 4u) << 16);
+    }
     return t;
 }
 
@@ -142,6 +155,7 @@ struct Luts {
     const uint64_t* legal;
     const uint16_t* pair;
     const uint8_t*  line;
+    const NRow*     nrow;
     const uint64_t* spread;
 };
 QTTT_HD Luts luts_from_image(const void* img) {
@@ -150,6 +164,7 @@ QTTT_HD Luts luts_from_image(const void* img) {
     l.legal = t->legal;
     l.pair = t->pair;
     l.line = t->line;
+    l.nrow = reinterpret_cast<const NRow*>(t->nrow);
     l.spread = t->spread;
     return l;
 }
@@ -171,15 +186,17 @@ struct StepResult {
 // One breadth-first absorption of a live edge into the reached set R; T remembers the square
 // the edge brought in (its child endpoint when the tree is rooted at the start square).
 #if defined(__CUDA_ARCH__)
-// Three issue slots per edge: LOP3 with predicate output, then two predicated LOP3s
-// (T |= E & ~R  is  lop3 0xF4).  Written in PTX because the compiler otherwise turns the
-// conditional into six select-based instructions.
+// Written in PTX to pin the shape: one LOP3 with predicate output (does E touch R?), one
+// LOP3 for the not-yet-reached square c = E & ~R, and two predicated ADDs (c is disjoint
+// from R and from T, so add == or) that ptxas is free to place on the IMAD pipe.  Left to
+// itself the compiler emits select-based code on the ALU pipe only.
 #define QTTT_ABSORB(E, T)                                                     \
-    asm("{\n\t.reg .pred p;\n\t.reg .b32 h;\n\t"                            \
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 h, c;\n\t"                \
         "and.b32 h, %2, %1;\n\t"                                              \
         "setp.ne.u32 p, h, 0;\n\t"                                            \
-        "@p lop3.b32 %0, %0, %2, %1, 0xF4;\n\t"                               \
-        "@p or.b32 %1, %1, %2;\n\t}"                                          \
+        "lop3.b32 c, %2, %1, 0, 0x30;\n\t"                                    \
+        "@p add.u32 %0, %0, c;\n\t"                                           \
+        "@p add.u32 %1, %1, c;\n\t}"                                          \
         : "+r"(T), "+r"(R) : "r"(E));
 #else
 #define QTTT_ABSORB(E, T)                         \
@@ -189,15 +206,24 @@ struct StepResult {
     }
 #endif
 
+// Repeat forward sweeps over the first N move slots until the reached set stops growing.
+#define QTTT_BFS(BODY) do { before = R; BODY } while (R != before)
+
 // Board.make_move for one game.  `enew`: E mask of the requested pair (0 = malformed);
 // `coin`: 0 -> the closing move falls into its smaller square (qeval.py:35).
 //
 // kTargets: also report, per move index, the square set it collapsed into in this
 // measurement (tgt[0..8], zero when not part of it) -- eval()'s return value by move index.
+//
+// Instruction budget notes: the integer ALU pipe (LOP3/SHF/ISETP/SEL) is the binding resource
+// of the step kernel, so (a) the sweep touches only the n move slots that exist -- n is
+// uniform across a warp when a batch is stepped in lock-step, so the switch does not diverge
+// -- and (b) bit placement is written as multiply-add by table constants (IMAD pipe).
 template <bool kTargets = false>
-QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, uint32_t* tgt = nullptr) {
+QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, const Luts& L, uint32_t* tgt = nullptr) {
     const uint32_t x = s.x, y = s.y, z = s.z, w = s.w;
     const uint32_t n = (x >> 27) & 15u;
+    const NRow row = L.nrow[n];
     const uint32_t C = classical(s);
     const bool legal = (enew != 0u) & ((enew & C) == 0u) & (n < 9u);   // board.py:10-15
     enew = legal ? enew : 0u;
@@ -215,50 +241,70 @@ QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, uint32_t* t
     const uint32_t E6 = z & M9, E7 = (z >> 9) & M9;
     uint32_t T0 = 0, T1 = 0, T2 = 0, T3 = 0, T4 = 0, T5 = 0, T6 = 0, T7 = 0;
     uint32_t R = t, before;
-    do {
-        before = R;
-        QTTT_ABSORB(E0, T0) QTTT_ABSORB(E1, T1) QTTT_ABSORB(E2, T2) QTTT_ABSORB(E3, T3)
-        QTTT_ABSORB(E4, T4) QTTT_ABSORB(E5, T5) QTTT_ABSORB(E6, T6) QTTT_ABSORB(E7, T7)
-    } while (R != before);
+#define A0_ QTTT_ABSORB(E0, T0)
+#define A1_ QTTT_ABSORB(E1, T1)
+#define A2_ QTTT_ABSORB(E2, T2)
+#define A3_ QTTT_ABSORB(E3, T3)
+#define A4_ QTTT_ABSORB(E4, T4)
+#define A5_ QTTT_ABSORB(E5, T5)
+#define A6_ QTTT_ABSORB(E6, T6)
+#define A7_ QTTT_ABSORB(E7, T7)
+    switch (n) {
+        case 0: break;
+        case 1: A0_ break;
+        case 2: QTTT_BFS(A0_ A1_); break;
+        case 3: QTTT_BFS(A0_ A1_ A2_); break;
+        case 4: QTTT_BFS(A0_ A1_ A2_ A3_); break;
+        case 5: QTTT_BFS(A0_ A1_ A2_ A3_ A4_); break;
+        case 6: QTTT_BFS(A0_ A1_ A2_ A3_ A4_ A5_); break;
+        case 7: QTTT_BFS(A0_ A1_ A2_ A3_ A4_ A5_ A6_); break;
+        case 8: QTTT_BFS(A0_ A1_ A2_ A3_ A4_ A5_ A6_ A7_); break;
+        default: break;
+    }
+#undef A0_
+#undef A1_
+#undef A2_
+#undef A3_
+#undef A4_
+#undef A5_
+#undef A6_
+#undef A7_
 
-    const bool col = (R & o) != 0u;            // a, b already connected -> cycle (board.py:42)
-    const uint32_t cm = col ? 0xFFFFFFFFu : 0u;
+    // a, b already connected -> cycle (board.py:42); colf is the 0/1 multiplier form.
+    const uint32_t colf = (R & o) != 0u ? 1u : 0u;
 
     // board[square] = move index for every move of the component (board.py:53-54), written
-    // into the bit-planes of v = index + 1.  Old moves have static indices; the closing
-    // move has index n.
-    const uint32_t v = n + 1u;
-    uint32_t A0 = T0 | T2 | T4 | T6 | ((v & 1u) ? t : 0u);
-    uint32_t A1 = T1 | T2 | T5 | T6 | ((v & 2u) ? t : 0u);
-    uint32_t A2 = T3 | T4 | T5 | T6 | ((v & 4u) ? t : 0u);
-    uint32_t A3 = (T7 | ((v & 8u) ? t : 0u)) & cm;
-    uint32_t wn = w | ((A0 | (A1 << 9) | (A2 << 18)) & cm);
-    uint32_t Cn = C | (R & cm);
+    // into the bit-planes of v = index + 1.  The T_i are disjoint single squares, so the
+    // plane word is a sum of T_i * (plane pattern of i + 1); the closing move has index n.
+    uint32_t wsum = T0 * 0x00001u + T1 * 0x00200u + T2 * 0x00201u + T3 * 0x40000u +
+                    T4 * 0x40001u + T5 * 0x40200u + T6 * 0x40201u + t * row.kp;
+    uint32_t wn = w + wsum * colf;
+    uint32_t A3 = (T7 + ((n >= 7u) ? t : 0u)) * colf;      // v = 8, 9 carry plane 3
+    uint32_t Cn = C | (R * colf);
 
-    // moves.append((a, b, n))  (board.py:19)
-    const uint32_t q = (n * 11u) >> 5, r = n - 3u * q;
-    const uint32_t val = enew << (9u * r);
-    uint32_t xn = x | (q == 0u ? val : 0u);
-    uint32_t yn = y | (q == 1u ? val : 0u);
-    uint32_t zn = z | (q == 2u ? val : 0u);
+    // moves.append((a, b, n))  (board.py:19): slot n is empty, so add == or.
+    uint32_t xn = x + enew * row.mx;
+    uint32_t yn = y + enew * row.my;
+    uint32_t zn = z + enew * row.mz;
     uint32_t inc = legal ? 1u : 0u;
 
     // Autofill (board.py:21-25): one free square left.  Only reachable right after the
     // collapse triggered by move 7, so the entry is always (s, s, 8): v = 9 -> planes 0, 3.
     const uint32_t fr = ~Cn & M9;
-    const bool fill = col & (popc32(fr) == 1);
+    const bool fill = (colf != 0u) & (popc32(fr) == 1);
     const uint32_t fs = fill ? fr : 0u;
-    zn |= fs << 18;
-    wn |= fs;
-    A3 |= fs;
+    zn += fs << 18;
+    wn += fs;
+    A3 += fs;
     Cn |= fs;
     inc += fill ? 1u : 0u;
 
-    yn |= (A3 & 0x1Fu) << 27;
-    zn |= (A3 >> 5) << 27;
+    yn += A3 << 27;                 // squares 0..4 of plane 3 (higher bits fall off the word)
+    zn += (A3 >> 5) << 27;          // squares 5..8
     xn += inc << 27;
 
     if (kTargets) {
+        const uint32_t cm = 0u - colf;
         tgt[0] = T0 & cm; tgt[1] = T1 & cm; tgt[2] = T2 & cm; tgt[3] = T3 & cm;
         tgt[4] = T4 & cm; tgt[5] = T5 & cm; tgt[6] = T6 & cm; tgt[7] = T7 & cm;
         tgt[8] = 0u;
@@ -270,7 +316,7 @@ QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, uint32_t* t
     s.x = xn; s.y = yn; s.z = zn; s.w = wn;
     StepResult out;
     out.illegal = legal ? 0u : 1u;
-    out.collapsed = col ? 1u : 0u;
+    out.collapsed = colf;
     out.classical = Cn;
     out.n = n + inc;
     return out;
@@ -396,7 +442,7 @@ QTTT_HD StepResult playout_ply(State& s, uint32_t C, uint64_t seed, uint64_t gam
     policy_draw(seed, game, n_moves(s), domain, L.legal[~C & M9], act, c);
     if (act_out) *act_out = act;
     if (coin_out) *coin_out = c;
-    return step_core(s, (uint32_t)L.pair[act & 255u], c);
+    return step_core(s, (uint32_t)L.pair[act & 255u], c, L);
 }
 
 QTTT_HD int board_value(uint32_t P0, uint32_t P1, uint32_t P2, uint32_t P3, int sq) {
@@ -482,7 +528,7 @@ QTTT_HD void qeval_game(const State& s, uint32_t action, const Luts& L, State* n
     for (int c = 0; c < 2; ++c) {
         State t = s;
         uint32_t tgt[9];
-        const StepResult r = step_core<true>(t, enew, (uint32_t)c, tgt);
+        const StepResult r = step_core<true>(t, enew, (uint32_t)c, L, tgt);
         col = r.collapsed;
         State* nx = c ? next1 : next0;
         uint64_t* bd = c ? board1 : board0;

@@ -43,21 +43,28 @@ __global__ void __launch_bounds__(kThreads) k_reset(qttt_state* state, uint64_t*
 }
 
 // ------------------------------------------------------------------------------ K1 step
-// kFmt: QTTT_ACT_INDEX / QTTT_ACT_PAIR; kRandom: Philox policy instead of given actions.
-template <int kFmt, bool kRandom>
+template <class T>
+__device__ __forceinline__ T* elem(T* base, uint32_t i) { return base + i; }
+
+// kFmt: QTTT_ACT_INDEX / QTTT_ACT_PAIR; kRandom: Philox policy instead of given actions;
+// kFull: reward, done, mask and status are all requested (no per-game NULL tests).
+// Launched with n <= 2^31 so that game indices fit 32 bits.
+template <int kFmt, bool kRandom, bool kFull>
 __global__ void __launch_bounds__(kThreads)
 k_step(qttt_state* __restrict__ state, const uint8_t* __restrict__ action,
        const uint8_t* __restrict__ coin, uint64_t seed, uint64_t game_base,
        float* __restrict__ reward, uint8_t* __restrict__ done, uint64_t* __restrict__ mask,
        uint8_t* __restrict__ status, uint8_t* __restrict__ action_out,
-       uint8_t* __restrict__ coin_out, int64_t n) {
+       uint8_t* __restrict__ coin_out, uint32_t n) {
     __shared__ __align__(16) uint8_t smem[kLutStepBytes];
     stage_luts(smem, kLutStepBytes);
     const Luts L = luts_from_image(smem);
 
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-        State s = load_state(state, i);
+    const uint32_t stride = gridDim.x * kThreads;
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+        uint4* sp = reinterpret_cast<uint4*>(elem(state, i));
+        const uint4 sv = *sp;
+        State s{sv.x, sv.y, sv.z, sv.w};
         uint32_t enew, c, st_extra = 0u;
         if (kRandom) {
             const uint32_t C = classical(s);
@@ -67,17 +74,17 @@ k_step(qttt_state* __restrict__ state, const uint8_t* __restrict__ action,
             policy_draw(seed, game_base + (uint64_t)i, nm, 0u, L.legal[~C & M9], act, c);
             if (finished) { act = 255u; c = 0u; st_extra = QTTT_ST_FINISHED; }
             enew = L.pair[act];
-            if (action_out) action_out[i] = (uint8_t)act;
-            if (coin_out) coin_out[i] = (uint8_t)c;
+            if (action_out) *elem(action_out, i) = (uint8_t)act;
+            if (coin_out) *elem(coin_out, i) = (uint8_t)c;
         } else {
             if (kFmt == QTTT_ACT_INDEX) {
-                enew = L.pair[action[i]];
+                enew = L.pair[*elem(action, i)];
             } else {
-                const uchar2 ab = reinterpret_cast<const uchar2*>(action)[i];
+                const uchar2 ab = *elem(reinterpret_cast<const uchar2*>(action), i);
                 enew = pair_to_edge(ab.x, ab.y);
             }
             if (coin) {
-                c = coin[i] & 1u;
+                c = *elem(coin, i) & 1u;
             } else {
                 const uint64_t game = game_base + (uint64_t)i;
                 uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = n_moves(s), c3 = 0u;
@@ -85,9 +92,14 @@ k_step(qttt_state* __restrict__ state, const uint8_t* __restrict__ action,
                 c = c1 & 1u;
             }
         }
-        const StepResult r = step_core(s, enew, c);
-        store_state(state, i, s);
-        emit_step_outputs(s, r, st_extra ? st_extra : r.illegal, L, reward, done, mask, status, i);
+        const StepResult r = step_core(s, enew, c, L);
+        *sp = make_uint4(s.x, s.y, s.z, s.w);
+        const uint32_t win = any_line(s, r.classical, L);
+        const uint32_t st = st_extra ? st_extra : r.illegal;
+        if (kFull || reward) *elem(reward, i) = bits_to_float(reward_bits(win));             // env.py:49
+        if (kFull || done) *elem(done, i) = (uint8_t)((win != 0u) | (r.n > 8u));              // env.py:51
+        if (kFull || mask) *elem(mask, i) = L.legal[~r.classical & M9];                       // mcts.py:87-91
+        if (kFull || status) *elem(status, i) = (uint8_t)st;
     }
 }
 
@@ -257,44 +269,75 @@ const char* qttt_strerror(int rc) {
 }
 
 int qttt_reset(qttt_state* state, uint64_t* mask, int64_t n, void* stream) {
+    if (n == 0) return QTTT_OK;
     if (!state || n < 0) return QTTT_ERR_ARG;
     if (misaligned(state, 16) || misaligned(mask, 8)) return QTTT_ERR_ALIGN;
-    if (n == 0) return QTTT_OK;
     k_reset<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state, mask, n);
     return check_launch();
 }
 
+}  // extern "C"
+
+// Launches k_step over [0, n) in slices of at most 2^31 games (32-bit indices in the kernel).
+template <int kFmt, bool kRandom>
+static int launch_step(qttt_state* state, const uint8_t* action, const uint8_t* coin, uint64_t seed,
+                       uint64_t game_base, float* reward, uint8_t* done, uint64_t* mask,
+                       uint8_t* status, uint8_t* action_out, uint8_t* coin_out, int64_t n,
+                       cudaStream_t st) {
+    const int64_t kSlice = 1ll << 31;
+    const bool full = reward && done && mask && status;
+    for (int64_t lo = 0; lo < n; lo += kSlice) {
+        const int64_t m = n - lo < kSlice ? n - lo : kSlice;
+        const int act_bytes = kFmt == QTTT_ACT_PAIR ? 2 : 1;
+        qttt_state* s_ = state + lo;
+        const uint8_t* a_ = action ? action + act_bytes * lo : nullptr;
+        const uint8_t* c_ = coin ? coin + lo : nullptr;
+        float* r_ = reward ? reward + lo : nullptr;
+        uint8_t* d_ = done ? done + lo : nullptr;
+        uint64_t* m_ = mask ? mask + lo : nullptr;
+        uint8_t* t_ = status ? status + lo : nullptr;
+        uint8_t* ao = action_out ? action_out + lo : nullptr;
+        uint8_t* co = coin_out ? coin_out + lo : nullptr;
+        if (full)
+            k_step<kFmt, kRandom, true><<<grid_for(m), kThreads, 0, st>>>(s_, a_, c_, seed, game_base + (uint64_t)lo, r_, d_, m_, t_, ao, co, (uint32_t)m);
+        else
+            k_step<kFmt, kRandom, false><<<grid_for(m), kThreads, 0, st>>>(s_, a_, c_, seed, game_base + (uint64_t)lo, r_, d_, m_, t_, ao, co, (uint32_t)m);
+        const int rc = check_launch();
+        if (rc != QTTT_OK) return rc;
+    }
+    return QTTT_OK;
+}
+
+extern "C" {
+
 int qttt_step(qttt_state* state, const void* action, int action_format, const uint8_t* coin,
               uint64_t seed, uint64_t game_base, float* reward, uint8_t* done, uint64_t* mask,
               uint8_t* status, int64_t n, void* stream) {
-    if (!state || !action || n < 0) return QTTT_ERR_ARG;
     if (action_format != QTTT_ACT_INDEX && action_format != QTTT_ACT_PAIR) return QTTT_ERR_ARG;
+    if (n == 0) return QTTT_OK;
+    if (!state || !action || n < 0) return QTTT_ERR_ARG;
     if (misaligned(state, 16) || misaligned(mask, 8) || misaligned(reward, 4)) return QTTT_ERR_ALIGN;
     if (action_format == QTTT_ACT_PAIR && misaligned(action, 2)) return QTTT_ERR_ALIGN;
-    if (n == 0) return QTTT_OK;
     const uint8_t* act = static_cast<const uint8_t*>(action);
     cudaStream_t st = (cudaStream_t)stream;
     if (action_format == QTTT_ACT_INDEX)
-        k_step<QTTT_ACT_INDEX, false><<<grid_for(n), kThreads, 0, st>>>(state, act, coin, seed, game_base, reward, done, mask, status, nullptr, nullptr, n);
-    else
-        k_step<QTTT_ACT_PAIR, false><<<grid_for(n), kThreads, 0, st>>>(state, act, coin, seed, game_base, reward, done, mask, status, nullptr, nullptr, n);
-    return check_launch();
+        return launch_step<QTTT_ACT_INDEX, false>(state, act, coin, seed, game_base, reward, done, mask, status, nullptr, nullptr, n, st);
+    return launch_step<QTTT_ACT_PAIR, false>(state, act, coin, seed, game_base, reward, done, mask, status, nullptr, nullptr, n, st);
 }
 
 int qttt_step_random(qttt_state* state, uint64_t seed, uint64_t game_base, uint8_t* action_out,
                      uint8_t* coin_out, float* reward, uint8_t* done, uint64_t* mask,
                      uint8_t* status, int64_t n, void* stream) {
+    if (n == 0) return QTTT_OK;
     if (!state || n < 0) return QTTT_ERR_ARG;
     if (misaligned(state, 16) || misaligned(mask, 8) || misaligned(reward, 4)) return QTTT_ERR_ALIGN;
-    if (n == 0) return QTTT_OK;
-    k_step<QTTT_ACT_INDEX, true><<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(
-        state, nullptr, nullptr, seed, game_base, reward, done, mask, status, action_out, coin_out, n);
-    return check_launch();
+    return launch_step<QTTT_ACT_INDEX, true>(state, nullptr, nullptr, seed, game_base, reward, done, mask, status, action_out, coin_out, n, (cudaStream_t)stream);
 }
 
 int qttt_observe(const qttt_state* state, int8_t* classical, int8_t* moves, uint8_t* n_moves,
                  int8_t* q_p1, int8_t* q_p2, uint8_t* turn, int8_t* rounds, float* reward_p1,
                  uint8_t* winner, uint8_t* mask_bool, int64_t n, void* stream) {
+    if (n == 0) return QTTT_OK;
     if (!state || n < 0) return QTTT_ERR_ARG;
     if (misaligned(state, 16) || misaligned(reward_p1, 4)) return QTTT_ERR_ALIGN;
     if (n == 0) return QTTT_OK;
@@ -304,6 +347,7 @@ int qttt_observe(const qttt_state* state, int8_t* classical, int8_t* moves, uint
 
 int qttt_pack(qttt_state* state, const int8_t* classical, const int8_t* moves,
               const uint8_t* n_moves, int64_t n, void* stream) {
+    if (n == 0) return QTTT_OK;
     if (!state || !classical || !moves || !n_moves || n < 0) return QTTT_ERR_ARG;
     if (misaligned(state, 16)) return QTTT_ERR_ALIGN;
     if (n == 0) return QTTT_OK;
@@ -314,6 +358,7 @@ int qttt_pack(qttt_state* state, const int8_t* classical, const int8_t* moves,
 int qttt_qeval_both(const qttt_state* state, const uint8_t* action, qttt_state* next0,
                     qttt_state* next1, uint64_t* board0, uint64_t* board1, int8_t* sq0,
                     int8_t* sq1, uint8_t* closes, float* result_prob, int64_t n, void* stream) {
+    if (n == 0) return QTTT_OK;
     if (!state || !action || n < 0) return QTTT_ERR_ARG;
     if (misaligned(state, 16) || misaligned(next0, 16) || misaligned(next1, 16) ||
         misaligned(board0, 8) || misaligned(board1, 8) || misaligned(result_prob, 4))
@@ -325,6 +370,7 @@ int qttt_qeval_both(const qttt_state* state, const uint8_t* action, qttt_state* 
 
 int qttt_rollout(const qttt_state* roots, int64_t n_roots, int32_t n_rollouts, uint64_t seed,
                  int32_t* tallies, float* value, int64_t* steps_total, void* stream) {
+    if (n_roots == 0 && n_rollouts > 0) return QTTT_OK;
     if (!roots || n_roots < 0 || n_rollouts <= 0 || n_roots > 0x7FFFFFFF) return QTTT_ERR_ARG;
     if (misaligned(roots, 16) || misaligned(tallies, 4) || misaligned(value, 4) || misaligned(steps_total, 8))
         return QTTT_ERR_ALIGN;
@@ -335,7 +381,9 @@ int qttt_rollout(const qttt_state* roots, int64_t n_roots, int32_t n_rollouts, u
 }
 
 int qttt_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, int64_t* stats, void* stream) {
-    if (!stats || game_hi < game_lo) return QTTT_ERR_ARG;
+    if (game_hi < game_lo) return QTTT_ERR_ARG;
+    if (game_hi == game_lo) return QTTT_OK;
+    if (!stats) return QTTT_ERR_ARG;
     if (misaligned(stats, 8)) return QTTT_ERR_ALIGN;
     if (game_hi == game_lo) return QTTT_OK;
     k_sweep<<<grid_for(game_hi - game_lo), kThreads, 0, (cudaStream_t)stream>>>(

@@ -43,6 +43,8 @@ class BatchedEnv:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("qtttgym_b200 runs on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.num_envs = int(num_envs)
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.game_base = int(game_base)
@@ -50,7 +52,8 @@ class BatchedEnv:
         n, dev = self.num_envs, self.device
         self.state = torch.zeros((n, 4), dtype=torch.int32, device=dev)
         self.reward = torch.empty(n, dtype=torch.float32, device=dev)
-        self.done = torch.empty(n, dtype=torch.uint8, device=dev)
+        self.done = torch.empty(n, dtype=torch.bool, device=dev)      # kernel writes 0 / 1 bytes
+        self._never = torch.zeros(n, dtype=torch.bool, device=dev)    # ``truncated`` (Q8)
         self.mask = torch.empty(n, dtype=torch.int64, device=dev)     # 36-bit legal mask
         self.status = torch.empty(n, dtype=torch.uint8, device=dev)
         self._host_streams = None            # lazily created by step_host
@@ -70,7 +73,7 @@ class BatchedEnv:
 
         actions : uint8[N] action indices 0..35 (mcts.py:339-349) **or** int8[N,2] ``(a, b)``
                   pairs as passed to the reference's ``Env.step`` (any order).  Illegal actions
-                  are swallowed no-ops exactly as env.py:36-43 (``info["invalid"]``).
+                  are swallowed no-ops exactly as env.py:36-43 (``info["status"] == 1``, ``env.invalid()``).
         choices : uint8[N] forced collapse coins (0 -> the closing move falls into its smaller
                   square, qeval.py:35), consumed only by envs whose move closes a cycle;
                   ``None`` -> Philox coins.
@@ -116,7 +119,7 @@ class BatchedEnv:
         """``step`` for callers whose buffers live in (pinned) HOST memory -- the end-to-end path.
 
         actions_host uint8[N] action indices and choices_host uint8[N] coins are copied to the
-        device, the step kernel runs, and reward f32[N] / done uint8[N] / mask int64[N] are
+        device, the step kernel runs, and reward f32[N] / done bool[N] / mask int64[N] are
         copied back into the given host tensors.  The batch is cut into ``chunks`` slices that
         are pipelined over ``n_streams`` side streams so that host->device copies, kernels and
         device->host copies of different slices overlap (PCIe is full duplex).  Returns after
@@ -125,10 +128,10 @@ class BatchedEnv:
         """
         n, dev = self.num_envs, self.device
         for t, dt in ((actions_host, torch.uint8), (choices_host, torch.uint8),
-                      (reward_host, torch.float32), (done_host, torch.uint8), (mask_host, torch.int64)):
+                      (reward_host, torch.float32), (done_host, torch.bool), (mask_host, torch.int64)):
             if t.dtype != dt or t.numel() != n or t.device.type != "cpu" or not t.is_contiguous():
                 raise ValueError("step_host expects contiguous CPU tensors of N elements "
-                                 "(uint8 actions, uint8 coins, f32 reward, uint8 done, int64 mask)")
+                                 "(uint8 actions, uint8 coins, f32 reward, bool done, int64 mask)")
         if self._host_streams is None or len(self._host_streams) != n_streams:
             self._host_streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
             self._d_act = torch.empty(n, dtype=torch.uint8, device=dev)
@@ -214,10 +217,14 @@ class BatchedEnv:
             return {"packed": self.state}
         return self.observation()
 
+    def invalid(self):
+        """bool[N]: the last ``step`` was a swallowed illegal action for this env (env.py:41-43)."""
+        return self.status == 1
+
     def _result(self):
-        info = {"action_mask": self.mask, "status": self.status, "invalid": self.status == 1}
-        terminated = self.done.bool()
-        return self._obs(), self.reward, terminated, torch.zeros_like(terminated), info
+        # no extra kernels here: everything returned is a buffer the step kernel wrote
+        info = {"action_mask": self.mask, "status": self.status}
+        return self._obs(), self.reward, self.done, self._never, info
 
 
 def observe_states(state, extras: bool = False):
@@ -249,6 +256,8 @@ def pack_states(classical, moves, n_moves, device="cuda"):
     """Reference-shaped positions -> packed states int32[N,4] (see qttt_pack)."""
     lib = _lib.lib()
     dev = torch.device(device)
+    if dev.type == "cuda" and dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
     classical = torch.as_tensor(classical, dtype=torch.int8).to(dev).contiguous()
     moves = torch.as_tensor(moves, dtype=torch.int8).to(dev).contiguous()
     n_moves = torch.as_tensor(n_moves, dtype=torch.uint8).to(dev).contiguous()
@@ -291,7 +300,7 @@ class Env:
         ch = None if coin is None else torch.tensor([int(coin) & 1], dtype=torch.uint8,
                                                     device=self._device)
         _, reward, term, _, info = self._batched.step(act, ch)
-        if verbose and bool(info["invalid"][0]):
+        if verbose and int(info["status"][0]) == 1:
             print("noop (i.e. invalid) move...")
         return self._observation(), float(reward[0].item()), bool(term[0].item()), False, {}
 

@@ -75,6 +75,8 @@ class QEvalB200:
 
     def __init__(self, device="cuda", rng=None):
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.rng = rng if rng is not None else _random
         self.forced: list[int] = []
 

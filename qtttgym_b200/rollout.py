@@ -38,6 +38,8 @@ def selfplay_sweep(game_lo: int, game_hi: int, seed: int = 0, device="cuda", out
     """
     lib = _lib.lib()
     dev = torch.device(device)
+    if dev.type == "cuda" and dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
     stats = out if out is not None else torch.zeros(16, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.qttt_sweep(int(game_lo), int(game_hi), int(seed) & 0xFFFFFFFFFFFFFFFF,

@@ -162,7 +162,7 @@ class CudaGames:
         _, reward, term, _, info = res
         t = self.torch
         t.cuda.synchronize()
-        return dict(reward=reward.cpu().numpy().copy(), done=term.to(t.uint8).cpu().numpy(),
+        return dict(reward=reward.cpu().numpy().copy(), done=term.cpu().numpy().astype(np.uint8),
                     mask=info["action_mask"].cpu().numpy().astype(np.uint64),
                     status=info["status"].cpu().numpy().copy())
 

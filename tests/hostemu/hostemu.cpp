@@ -37,7 +37,7 @@ int emu_step(State* state, const void* action, int fmt, const uint8_t* coin, uin
             philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
             c = c1 & 1u;
         }
-        const StepResult r = step_core(s, enew, c);
+        const StepResult r = step_core(s, enew, c, L);
         state[i] = s;
         emit_step_outputs(s, r, r.illegal, L, reward, done, mask, status, i);
     }
@@ -57,7 +57,7 @@ int emu_step_random(State* state, uint64_t seed, uint64_t game_base, uint8_t* ac
         if (finished) { act = 255u; c = 0u; }
         if (action_out) action_out[i] = (uint8_t)act;
         if (coin_out) coin_out[i] = (uint8_t)c;
-        const StepResult r = step_core(s, (uint32_t)L.pair[act], c);
+        const StepResult r = step_core(s, (uint32_t)L.pair[act], c, L);
         state[i] = s;
         emit_step_outputs(s, r, finished ? 2u : r.illegal, L, reward, done, mask, status, i);
     }

@@ -201,3 +201,25 @@ def test_error_codes(cuda):
     with pytest.raises(RuntimeError):
         L.check(-1)
     torch.cuda.synchronize()
+
+
+def test_step_host_equals_step(cuda):
+    """The end-to-end entry (pinned host buffers, chunk-pipelined) gives the same results."""
+    import torch
+    import qtttgym_b200 as Q
+    n = 100_003
+    gen = Q.BatchedEnv(n, seed=9)
+    a = Q.BatchedEnv(n, seed=9)
+    b = Q.BatchedEnv(n, seed=9)
+    hr = torch.empty(n, dtype=torch.float32).pin_memory()
+    hd = torch.empty(n, dtype=torch.bool).pin_memory()
+    hm = torch.empty(n, dtype=torch.int64).pin_memory()
+    for ply in range(9):
+        info = gen.step_random(record=True)[4]
+        act, coin = info["action"].clone(), info["coin"].clone()
+        _, r, t, _, i2 = a.step(act, coin)
+        b.step_host(act.cpu().pin_memory(), coin.cpu().pin_memory(), hr, hd, hm, chunks=5, n_streams=3)
+        torch.cuda.synchronize()
+        assert torch.equal(r.cpu().view(torch.int32), hr.view(torch.int32))
+        assert torch.equal(t.cpu(), hd) and torch.equal(i2["action_mask"].cpu(), hm)
+        assert torch.equal(a.state, b.state) and torch.equal(a.state, gen.state)
