@@ -249,7 +249,9 @@ QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, const Luts&
 #define A5_ QTTT_ABSORB(E5, T5)
 #define A6_ QTTT_ABSORB(E6, T6)
 #define A7_ QTTT_ABSORB(E7, T7)
-    switch (n) {
+    // An illegal request (a swallowed no-op) has nothing to sweep: send it down the empty
+    // case so that idle games of other lengths do not make the warp run extra cases.
+    switch (legal ? n : 0u) {
         case 0: break;
         case 1: A0_ break;
         case 2: QTTT_BFS(A0_ A1_); break;

@@ -15,7 +15,6 @@ namespace qttt {
 __device__ const LutImage g_lut = make_lut_image();
 
 constexpr int kThreads = 256;
-constexpr int kBlocksPerSM = 8;   // 2048 resident threads per SM
 
 // Stage the first `bytes` of the table image into shared memory (16-byte vectors).
 __device__ __forceinline__ void stage_luts(uint8_t* smem, int bytes) {
@@ -93,7 +92,7 @@ k_step(qttt_state* __restrict__ state, const uint8_t* __restrict__ action,
             }
         }
         const StepResult r = step_core(s, enew, c, L);
-        *sp = make_uint4(s.x, s.y, s.z, s.w);
+        if (!r.illegal) *sp = make_uint4(s.x, s.y, s.z, s.w);     // a no-op leaves the state as it is
         const uint32_t win = any_line(s, r.classical, L);
         const uint32_t st = st_extra ? st_extra : r.illegal;
         if (kFull || reward) *elem(reward, i) = bits_to_float(reward_bits(win));             // env.py:49
@@ -187,8 +186,10 @@ k_rollout(const qttt_state* __restrict__ roots, int32_t n_rollouts, uint64_t see
     }
 }
 
-// K5: self-play sweep from the empty board.  Lanes refill: a thread that finishes a game
-// immediately starts its next one, so every lane executes a real ply on every iteration.
+// K5: self-play sweep from the empty board, entirely in registers.  The 32 games of a warp are
+// played in lock-step (ply p of all of them together), so len(moves) is uniform across the
+// active lanes and the transition's switch on it never diverges; lanes whose game ended
+// earlier (mean 8.29 of 9 plies) idle until the warp's last game ends.
 __global__ void __launch_bounds__(kThreads)
 k_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, unsigned long long* __restrict__ stats) {
     __shared__ __align__(16) uint8_t smem[kLutStepBytes];
@@ -199,47 +200,55 @@ k_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, unsigned long long* __r
     __syncthreads();
 
     const int64_t stride = (int64_t)gridDim.x * kThreads;
-    int64_t g = game_lo + (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    State s = empty_state();
-    uint32_t C = 0u, steps = 0u;
     uint32_t xw = 0, ow = 0, dr = 0, st = 0, co = 0, games = 0;
-    while (g < game_hi) {
-        const StepResult r = playout_ply(s, C, seed, (uint64_t)g, 0u, L);
-        C = r.classical;
-        ++steps;
-        co += r.collapsed;
-        bool terminal = r.n >= 9u;
-        uint32_t w = 0u;
-        if (r.collapsed) w = finished_winner(s, L, terminal);   // lines only appear through a collapse
-        if (terminal) {
-            xw += w == 1u; ow += w == 2u; dr += w == 0u;
-            st += steps; ++games;
-            atomicAdd(&sh[6 + steps], 1ull);
-            g += stride;
-            s = empty_state(); C = 0u; steps = 0u;
+    uint32_t h5 = 0, h6 = 0, h7 = 0, h8 = 0, h9 = 0;       // games by length (a game has 5..9 plies)
+    for (int64_t g = game_lo + (int64_t)blockIdx.x * kThreads + threadIdx.x;; g += stride) {
+        bool active = g < game_hi;
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        State s = empty_state();
+        uint32_t C = 0u;
+        games += active;
+#pragma unroll 1
+        for (uint32_t ply = 0; ply < 9u; ++ply) {
+            if (!__any_sync(0xFFFFFFFFu, active)) break;
+            if (active) {
+                const StepResult r = playout_ply(s, C, seed, (uint64_t)g, 0u, L);
+                C = r.classical;
+                co += r.collapsed;
+                bool terminal = r.n >= 9u;
+                uint32_t w = 0u;
+                if (r.collapsed) w = finished_winner(s, L, terminal);   // lines only appear through a collapse
+                if (terminal) {
+                    xw += w == 1u; ow += w == 2u; dr += w == 0u;
+                    st += ply + 1u;
+                    h5 += ply == 4u; h6 += ply == 5u; h7 += ply == 6u; h8 += ply == 7u; h9 += ply == 8u;
+                    active = false;
+                }
+            }
         }
     }
-    xw = __reduce_add_sync(0xFFFFFFFFu, xw);
-    ow = __reduce_add_sync(0xFFFFFFFFu, ow);
-    dr = __reduce_add_sync(0xFFFFFFFFu, dr);
-    co = __reduce_add_sync(0xFFFFFFFFu, co);
-    games = __reduce_add_sync(0xFFFFFFFFu, games);
-    st = __reduce_add_sync(0xFFFFFFFFu, st);
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&sh[0], (unsigned long long)xw); atomicAdd(&sh[1], (unsigned long long)ow);
-        atomicAdd(&sh[2], (unsigned long long)dr); atomicAdd(&sh[3], (unsigned long long)st);
-        atomicAdd(&sh[4], (unsigned long long)co); atomicAdd(&sh[5], (unsigned long long)games);
+    uint32_t vals[11] = {xw, ow, dr, st, co, games, h5, h6, h7, h8, h9};
+    const int slot[11] = {0, 1, 2, 3, 4, 5, 11, 12, 13, 14, 15};
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+        const uint32_t v = __reduce_add_sync(0xFFFFFFFFu, vals[k]);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sh[slot[k]], (unsigned long long)v);
     }
     __syncthreads();
     if (threadIdx.x < 16 && sh[threadIdx.x]) atomicAdd(&stats[threadIdx.x], sh[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------ launch helpers
-static int grid_for(int64_t n) {
-    int dev = 0, sms = 148;
+// Persistent grid: exactly as many blocks as are resident at once (SM count x occupancy of
+// this kernel), so the grid-stride loops finish in one balanced wave.
+template <class Kernel>
+static int grid_for(Kernel kernel, int64_t n) {
+    int dev = 0, sms = 148, per_sm = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 4;
     const int64_t want = (n + kThreads - 1) / kThreads;
-    const int64_t cap = (int64_t)sms * kBlocksPerSM;
+    const int64_t cap = (int64_t)sms * per_sm;
     return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 static int check_launch() {
@@ -272,7 +281,7 @@ int qttt_reset(qttt_state* state, uint64_t* mask, int64_t n, void* stream) {
     if (n == 0) return QTTT_OK;
     if (!state || n < 0) return QTTT_ERR_ARG;
     if (misaligned(state, 16) || misaligned(mask, 8)) return QTTT_ERR_ALIGN;
-    k_reset<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state, mask, n);
+    k_reset<<<grid_for(k_reset, n), kThreads, 0, (cudaStream_t)stream>>>(state, mask, n);
     return check_launch();
 }
 
@@ -299,9 +308,9 @@ static int launch_step(qttt_state* state, const uint8_t* action, const uint8_t* 
         uint8_t* ao = action_out ? action_out + lo : nullptr;
         uint8_t* co = coin_out ? coin_out + lo : nullptr;
         if (full)
-            k_step<kFmt, kRandom, true><<<grid_for(m), kThreads, 0, st>>>(s_, a_, c_, seed, game_base + (uint64_t)lo, r_, d_, m_, t_, ao, co, (uint32_t)m);
+            k_step<kFmt, kRandom, true><<<grid_for(k_step<kFmt, kRandom, true>, m), kThreads, 0, st>>>(s_, a_, c_, seed, game_base + (uint64_t)lo, r_, d_, m_, t_, ao, co, (uint32_t)m);
         else
-            k_step<kFmt, kRandom, false><<<grid_for(m), kThreads, 0, st>>>(s_, a_, c_, seed, game_base + (uint64_t)lo, r_, d_, m_, t_, ao, co, (uint32_t)m);
+            k_step<kFmt, kRandom, false><<<grid_for(k_step<kFmt, kRandom, false>, m), kThreads, 0, st>>>(s_, a_, c_, seed, game_base + (uint64_t)lo, r_, d_, m_, t_, ao, co, (uint32_t)m);
         const int rc = check_launch();
         if (rc != QTTT_OK) return rc;
     }
@@ -341,7 +350,7 @@ int qttt_observe(const qttt_state* state, int8_t* classical, int8_t* moves, uint
     if (!state || n < 0) return QTTT_ERR_ARG;
     if (misaligned(state, 16) || misaligned(reward_p1, 4)) return QTTT_ERR_ALIGN;
     if (n == 0) return QTTT_OK;
-    k_observe<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state, classical, moves, n_moves, q_p1, q_p2, turn, rounds, reward_p1, winner, mask_bool, n);
+    k_observe<<<grid_for(k_observe, n), kThreads, 0, (cudaStream_t)stream>>>(state, classical, moves, n_moves, q_p1, q_p2, turn, rounds, reward_p1, winner, mask_bool, n);
     return check_launch();
 }
 
@@ -351,7 +360,7 @@ int qttt_pack(qttt_state* state, const int8_t* classical, const int8_t* moves,
     if (!state || !classical || !moves || !n_moves || n < 0) return QTTT_ERR_ARG;
     if (misaligned(state, 16)) return QTTT_ERR_ALIGN;
     if (n == 0) return QTTT_OK;
-    k_pack<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state, classical, moves, n_moves, n);
+    k_pack<<<grid_for(k_pack, n), kThreads, 0, (cudaStream_t)stream>>>(state, classical, moves, n_moves, n);
     return check_launch();
 }
 
@@ -364,7 +373,7 @@ int qttt_qeval_both(const qttt_state* state, const uint8_t* action, qttt_state* 
         misaligned(board0, 8) || misaligned(board1, 8) || misaligned(result_prob, 4))
         return QTTT_ERR_ALIGN;
     if (n == 0) return QTTT_OK;
-    k_qeval_both<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state, action, next0, next1, board0, board1, sq0, sq1, closes, result_prob, n);
+    k_qeval_both<<<grid_for(k_qeval_both, n), kThreads, 0, (cudaStream_t)stream>>>(state, action, next0, next1, board0, board1, sq0, sq1, closes, result_prob, n);
     return check_launch();
 }
 
@@ -386,7 +395,7 @@ int qttt_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, int64_t* stats, 
     if (!stats) return QTTT_ERR_ARG;
     if (misaligned(stats, 8)) return QTTT_ERR_ALIGN;
     if (game_hi == game_lo) return QTTT_OK;
-    k_sweep<<<grid_for(game_hi - game_lo), kThreads, 0, (cudaStream_t)stream>>>(
+    k_sweep<<<grid_for(k_sweep, game_hi - game_lo), kThreads, 0, (cudaStream_t)stream>>>(
         game_lo, game_hi, seed, reinterpret_cast<unsigned long long*>(stats));
     return check_launch();
 }
