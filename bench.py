@@ -42,6 +42,9 @@ UNIT = "env-steps/s"
 BYTES_PER_STEP = 47            # 16 state in + 16 out + 1 action + 1 coin + 4 reward + 1 done + 8 mask
 BYTES_PER_BOARD_QEVAL = 33     # 16 state + 1 action + 2 x 8 boards
 PLIES = 9
+WORKLOAD = ("step API (K1): reset + 9 step launches per pass, random legal actions with forced "
+            "collapse coins, games played from the empty board to termination "
+            "(config 2 of BASELINE.json scaled to fill the GPU)")
 
 
 def measured_hbm_peak():
@@ -142,9 +145,11 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "python-int", "data": "synthetic",
-        "config": {"workload": "random-vs-random games to termination through Env.reset/step "
-                               "(config 1), CPU, all host cores", "envs_per_process": 1,
-                   "processes": cores},
+        "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs,
+                   "reference_sample": "the same workload (random-vs-random games from the empty board to "
+                                       "termination through Env.reset/step) on the CPU: one env per process, "
+                                       f"{cores} processes x {games_per_proc} games per step",
+                   "envs_per_process": 1, "processes": cores},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -363,8 +368,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "step API (K1): reset + 9 step launches per pass, random legal "
-                                   "actions with forced collapse coins (config 2 scaled to fill the GPU)",
+            "config": {"workload": WORKLOAD,
                        "envs_per_gpu": E, "global_envs": E * world, "plies_per_pass": PLIES,
                        "env_steps_per_pass_per_gpu": steps_per_pass,
                        "l2": "inputs exceed L2: 16 B x E state + 2 B x E actions/coins + 13 B x E outputs per launch "

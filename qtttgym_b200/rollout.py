@@ -52,11 +52,12 @@ def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
     return (total * rank) // world, (total * (rank + 1)) // world
 
 
-def sharded_sweep(total_games: int, seed: int = 0, device="cuda", group=None):
+def sharded_sweep(total_games: int, seed: int = 0, device="cuda", group=None, sweep_fn=None):
     """Config 5: every rank plays its slice of the global game-id range, then ONE
     ``all_reduce(SUM)`` of the int64[16] tallies (NCCL over NVLink when the process group is
-    nccl; gloo on CPU tensors in tests).  RNG is keyed on the global game id, so the result
-    is identical for any world size."""
+    nccl).  RNG is keyed on the global game id, so the result is identical for any world
+    size.  ``sweep_fn(lo, hi, seed, device) -> int64[16]`` defaults to ``selfplay_sweep`` (the
+    CUDA kernel); the CPU tests of this host logic inject a stand-in and a gloo group."""
     import torch.distributed as dist
 
     if dist.is_available() and dist.is_initialized():
@@ -64,7 +65,7 @@ def sharded_sweep(total_games: int, seed: int = 0, device="cuda", group=None):
     else:
         rank, world = 0, 1
     lo, hi = shard_range(total_games, rank, world)
-    stats = selfplay_sweep(lo, hi, seed, device)
+    stats = (sweep_fn or selfplay_sweep)(lo, hi, seed, device)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
     return stats
