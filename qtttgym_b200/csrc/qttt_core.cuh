@@ -183,31 +183,86 @@ struct StepResult {
     uint32_t n;           // len(moves) after the step
 };
 
-// One breadth-first absorption of a live edge into the reached set R; T remembers the square
-// the edge brought in (its child endpoint when the tree is rooted at the start square).
+// ------------------------------------------------------------------------------------
+// The absorption sweep.  absorb<I>() takes move slot I into the reached set R when it touches
+// it, and books the square c it brought in (its child endpoint when the tree is rooted at
+// the start square) straight into the bit-plane accumulators: move I owns c with index I,
+// i.e. v = I + 1, whose planes 0..2 are the constant pattern kPlane[I] for word w (plane 3,
+// only v = 8, goes to A3).  c is disjoint from everything accumulated so far, so add == or.
+// ------------------------------------------------------------------------------------
+template <int I> struct PlanePattern {
+    static constexpr uint32_t v = I + 1;
+    static constexpr uint32_t value = (v & 1u) | ((v & 2u) << 8) | ((v & 4u) << 16);
+};
+
+template <int I>
+QTTT_HD void absorb(uint32_t E, uint32_t& R, uint32_t& W, uint32_t& A3) {
 #if defined(__CUDA_ARCH__)
-// Written in PTX to pin the shape: one LOP3 with predicate output (does E touch R?), one
-// LOP3 for the not-yet-reached square c = E & ~R, and two predicated ADDs (c is disjoint
-// from R and from T, so add == or) that ptxas is free to place on the IMAD pipe.  Left to
-// itself the compiler emits select-based code on the ALU pipe only.
-#define QTTT_ABSORB(E, T)                                                     \
-    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 h, c;\n\t"                \
-        "and.b32 h, %2, %1;\n\t"                                              \
-        "setp.ne.u32 p, h, 0;\n\t"                                            \
-        "lop3.b32 c, %2, %1, 0, 0x30;\n\t"                                    \
-        "@p add.u32 %0, %0, c;\n\t"                                           \
-        "@p add.u32 %1, %1, c;\n\t}"                                          \
-        : "+r"(T), "+r"(R) : "r"(E));
+    // PTX pins the shape: LOP3 with predicate out (does E touch R?), LOP3 for c = E & ~R,
+    // then predicated multiply-add / add, which ptxas places on the IMAD pipe -- the integer
+    // ALU pipe is the binding resource of these kernels.  Left alone the compiler emits
+    // select-based code on the ALU pipe that is twice as long.
+    if (I < 7) {
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 h, c;\n\t"
+            "and.b32 h, %2, %1;\n\t"
+            "setp.ne.u32 p, h, 0;\n\t"
+            "lop3.b32 c, %2, %1, 0, 0x30;\n\t"
+            "@p mad.lo.u32 %0, c, %3, %0;\n\t"
+            "@p add.u32 %1, %1, c;\n\t}"
+            : "+r"(W), "+r"(R) : "r"(E), "n"(PlanePattern<I>::value));
+    } else {
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 h, c;\n\t"
+            "and.b32 h, %2, %1;\n\t"
+            "setp.ne.u32 p, h, 0;\n\t"
+            "lop3.b32 c, %2, %1, 0, 0x30;\n\t"
+            "@p add.u32 %0, %0, c;\n\t"
+            "@p add.u32 %1, %1, c;\n\t}"
+            : "+r"(A3), "+r"(R) : "r"(E));
+    }
 #else
-#define QTTT_ABSORB(E, T)                         \
-    if ((E) & R) {                                \
-        (T) |= (E) & ~R;                          \
-        R |= (E);                                 \
+    if (E & R) {
+        const uint32_t c = E & ~R;
+        if (I < 7) W += c * PlanePattern<I>::value; else A3 += c;
+        R |= c;
     }
 #endif
+}
 
-// Repeat forward sweeps over the first N move slots until the reached set stops growing.
-#define QTTT_BFS(BODY) do { before = R; BODY } while (R != before)
+template <int I> QTTT_HD uint32_t slot(uint32_t x, uint32_t y, uint32_t z) {
+    const uint32_t word = I < 3 ? x : (I < 6 ? y : z);
+    return (I % 3 == 0) ? (word & M9) : ((word >> (9 * (I % 3))) & M9);
+}
+
+// Forward sweeps over move slots 0..N-1 until the reached set stops growing.
+template <int N, bool kTargets>
+QTTT_HD void sweep(uint32_t x, uint32_t y, uint32_t z, uint32_t& R, uint32_t& W, uint32_t& A3, uint32_t* T) {
+    const uint32_t E0 = N > 0 ? slot<0>(x, y, z) : 0u, E1 = N > 1 ? slot<1>(x, y, z) : 0u;
+    const uint32_t E2 = N > 2 ? slot<2>(x, y, z) : 0u, E3 = N > 3 ? slot<3>(x, y, z) : 0u;
+    const uint32_t E4 = N > 4 ? slot<4>(x, y, z) : 0u, E5 = N > 5 ? slot<5>(x, y, z) : 0u;
+    const uint32_t E6 = N > 6 ? slot<6>(x, y, z) : 0u, E7 = N > 7 ? slot<7>(x, y, z) : 0u;
+    uint32_t before;
+    do {
+        before = R;
+        if (N > 0) absorb<0>(E0, R, W, A3);
+        if (N > 1) absorb<1>(E1, R, W, A3);
+        if (N > 2) absorb<2>(E2, R, W, A3);
+        if (N > 3) absorb<3>(E3, R, W, A3);
+        if (N > 4) absorb<4>(E4, R, W, A3);
+        if (N > 5) absorb<5>(E5, R, W, A3);
+        if (N > 6) absorb<6>(E6, R, W, A3);
+        if (N > 7) absorb<7>(E7, R, W, A3);
+    } while (N > 1 && R != before);
+    if (kTargets) {
+        // Which square did each absorbed edge bring in?  Only the qeval kernel asks: replay
+        // the rooting from the start square (T[8]) with plain code.
+        uint32_t Rr = T[8], Es[8] = {E0, E1, E2, E3, E4, E5, E6, E7}, prev;
+        do {
+            prev = Rr;
+            for (int i = 0; i < N; ++i)
+                if (Es[i] & Rr) { T[i] |= Es[i] & ~Rr; Rr |= Es[i]; }
+        } while (Rr != prev);
+    }
+}
 
 // Board.make_move for one game.  `enew`: E mask of the requested pair (0 = malformed);
 // `coin`: 0 -> the closing move falls into its smaller square (qeval.py:35).
@@ -236,52 +291,31 @@ QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, const Luts&
     // Live edges are exactly the moves whose squares are not classical; collapsed moves have
     // both squares classical and can never touch R (which starts on a free square), so the
     // raw E fields can be used unfiltered.
-    const uint32_t E0 = x & M9, E1 = (x >> 9) & M9, E2 = (x >> 18) & M9;
-    const uint32_t E3 = y & M9, E4 = (y >> 9) & M9, E5 = (y >> 18) & M9;
-    const uint32_t E6 = z & M9, E7 = (z >> 9) & M9;
-    uint32_t T0 = 0, T1 = 0, T2 = 0, T3 = 0, T4 = 0, T5 = 0, T6 = 0, T7 = 0;
-    uint32_t R = t, before;
-#define A0_ QTTT_ABSORB(E0, T0)
-#define A1_ QTTT_ABSORB(E1, T1)
-#define A2_ QTTT_ABSORB(E2, T2)
-#define A3_ QTTT_ABSORB(E3, T3)
-#define A4_ QTTT_ABSORB(E4, T4)
-#define A5_ QTTT_ABSORB(E5, T5)
-#define A6_ QTTT_ABSORB(E6, T6)
-#define A7_ QTTT_ABSORB(E7, T7)
+    uint32_t R = t;
+    uint32_t W = t * row.kp;          // planes 0..2 of the closing move (index n) on square t
+    uint32_t A3 = (n >= 7u) ? t : 0u; // plane 3: v = n + 1 in {8, 9}
+    uint32_t T[9] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, t};
     // An illegal request (a swallowed no-op) has nothing to sweep: send it down the empty
     // case so that idle games of other lengths do not make the warp run extra cases.
     switch (legal ? n : 0u) {
-        case 0: break;
-        case 1: A0_ break;
-        case 2: QTTT_BFS(A0_ A1_); break;
-        case 3: QTTT_BFS(A0_ A1_ A2_); break;
-        case 4: QTTT_BFS(A0_ A1_ A2_ A3_); break;
-        case 5: QTTT_BFS(A0_ A1_ A2_ A3_ A4_); break;
-        case 6: QTTT_BFS(A0_ A1_ A2_ A3_ A4_ A5_); break;
-        case 7: QTTT_BFS(A0_ A1_ A2_ A3_ A4_ A5_ A6_); break;
-        case 8: QTTT_BFS(A0_ A1_ A2_ A3_ A4_ A5_ A6_ A7_); break;
+        case 1: sweep<1, kTargets>(x, y, z, R, W, A3, T); break;
+        case 2: sweep<2, kTargets>(x, y, z, R, W, A3, T); break;
+        case 3: sweep<3, kTargets>(x, y, z, R, W, A3, T); break;
+        case 4: sweep<4, kTargets>(x, y, z, R, W, A3, T); break;
+        case 5: sweep<5, kTargets>(x, y, z, R, W, A3, T); break;
+        case 6: sweep<6, kTargets>(x, y, z, R, W, A3, T); break;
+        case 7: sweep<7, kTargets>(x, y, z, R, W, A3, T); break;
+        case 8: sweep<8, kTargets>(x, y, z, R, W, A3, T); break;
         default: break;
     }
-#undef A0_
-#undef A1_
-#undef A2_
-#undef A3_
-#undef A4_
-#undef A5_
-#undef A6_
-#undef A7_
 
     // a, b already connected -> cycle (board.py:42); colf is the 0/1 multiplier form.
     const uint32_t colf = (R & o) != 0u ? 1u : 0u;
 
-    // board[square] = move index for every move of the component (board.py:53-54), written
-    // into the bit-planes of v = index + 1.  The T_i are disjoint single squares, so the
-    // plane word is a sum of T_i * (plane pattern of i + 1); the closing move has index n.
-    uint32_t wsum = T0 * 0x00001u + T1 * 0x00200u + T2 * 0x00201u + T3 * 0x40000u +
-                    T4 * 0x40001u + T5 * 0x40200u + T6 * 0x40201u + t * row.kp;
-    uint32_t wn = w + wsum * colf;
-    uint32_t A3 = (T7 + ((n >= 7u) ? t : 0u)) * colf;      // v = 8, 9 carry plane 3
+    // board[square] = move index for every move of the component (board.py:53-54): the
+    // accumulated plane words are committed only when the move closed a cycle.
+    uint32_t wn = w + W * colf;
+    A3 *= colf;
     uint32_t Cn = C | (R * colf);
 
     // moves.append((a, b, n))  (board.py:19): slot n is empty, so add == or.
@@ -307,8 +341,8 @@ QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, const Luts&
 
     if (kTargets) {
         const uint32_t cm = 0u - colf;
-        tgt[0] = T0 & cm; tgt[1] = T1 & cm; tgt[2] = T2 & cm; tgt[3] = T3 & cm;
-        tgt[4] = T4 & cm; tgt[5] = T5 & cm; tgt[6] = T6 & cm; tgt[7] = T7 & cm;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tgt[i] = T[i] & cm;
         tgt[8] = 0u;
 #pragma unroll
         for (int i = 0; i < 9; ++i)
@@ -520,6 +554,7 @@ QTTT_HD uint64_t board_nibbles(const State& s, const Luts& L) {
 
 // Both measurement outcomes of one (position, action): board.py:42-56 + qeval.py:5-51 twice,
 // i.e. what MCTS._step enumerates by rejection sampling (mcts.py:233-267).
+template <bool kSquares = true>
 QTTT_HD void qeval_game(const State& s, uint32_t action, const Luts& L, State* next0, State* next1,
                         uint64_t* board0, uint64_t* board1, int8_t* sq0, int8_t* sq1,
                         uint8_t* closes, float* result_prob, int64_t i) {
@@ -530,14 +565,14 @@ QTTT_HD void qeval_game(const State& s, uint32_t action, const Luts& L, State* n
     for (int c = 0; c < 2; ++c) {
         State t = s;
         uint32_t tgt[9];
-        const StepResult r = step_core<true>(t, enew, (uint32_t)c, L, tgt);
+        const StepResult r = step_core<kSquares>(t, enew, (uint32_t)c, L, tgt);
         col = r.collapsed;
         State* nx = c ? next1 : next0;
         uint64_t* bd = c ? board1 : board0;
         int8_t* sq = c ? sq1 : sq0;
         if (nx) nx[i] = t;
         if (bd) bd[i] = board_nibbles(t, L);
-        if (sq) {
+        if (kSquares && sq) {
 #pragma unroll
             for (int m = 0; m < 9; ++m) sq[9 * i + m] = (int8_t)(tgt[m] ? ctz32(tgt[m]) : -1);
         }

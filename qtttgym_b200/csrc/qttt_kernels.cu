@@ -97,7 +97,7 @@ k_step(qttt_state* __restrict__ state, const uint8_t* __restrict__ action,
         const uint32_t st = st_extra ? st_extra : r.illegal;
         if (kFull || reward) *elem(reward, i) = bits_to_float(reward_bits(win));             // env.py:49
         if (kFull || done) *elem(done, i) = (uint8_t)((win != 0u) | (r.n > 8u));              // env.py:51
-        if (kFull || mask) *elem(mask, i) = L.legal[~r.classical & M9];                       // mcts.py:87-91
+        if (kFull || mask) *elem(mask, i) = L.legal[~r.classical & M9];  // mcts.py:87-91
         if (kFull || status) *elem(status, i) = (uint8_t)st;
     }
 }
@@ -127,6 +127,7 @@ k_pack(qttt_state* __restrict__ state, const int8_t* __restrict__ classical_in,
 }
 
 // ------------------------------------------------------------------------------ K3 qeval
+template <bool kSquares>
 __global__ void __launch_bounds__(kThreads)
 k_qeval_both(const qttt_state* __restrict__ state, const uint8_t* __restrict__ action,
              qttt_state* __restrict__ next0, qttt_state* __restrict__ next1,
@@ -138,7 +139,7 @@ k_qeval_both(const qttt_state* __restrict__ state, const uint8_t* __restrict__ a
     const Luts L = luts_from_image(smem);
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
-        qeval_game(load_state(state, i), action[i], L, reinterpret_cast<State*>(next0),
+        qeval_game<kSquares>(load_state(state, i), action[i], L, reinterpret_cast<State*>(next0),
                    reinterpret_cast<State*>(next1), board0, board1, sq0, sq1, closes, result_prob, i);
 }
 
@@ -373,7 +374,10 @@ int qttt_qeval_both(const qttt_state* state, const uint8_t* action, qttt_state* 
         misaligned(board0, 8) || misaligned(board1, 8) || misaligned(result_prob, 4))
         return QTTT_ERR_ALIGN;
     if (n == 0) return QTTT_OK;
-    k_qeval_both<<<grid_for(k_qeval_both, n), kThreads, 0, (cudaStream_t)stream>>>(state, action, next0, next1, board0, board1, sq0, sq1, closes, result_prob, n);
+    if (sq0 || sq1)
+        k_qeval_both<true><<<grid_for(k_qeval_both<true>, n), kThreads, 0, (cudaStream_t)stream>>>(state, action, next0, next1, board0, board1, sq0, sq1, closes, result_prob, n);
+    else
+        k_qeval_both<false><<<grid_for(k_qeval_both<false>, n), kThreads, 0, (cudaStream_t)stream>>>(state, action, next0, next1, board0, board1, sq0, sq1, closes, result_prob, n);
     return check_launch();
 }
 
