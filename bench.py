@@ -269,27 +269,42 @@ def run_b200(args):
     # ---- e2e: host buffers through the public API, copies inside the timed region
     h_act = actions.cpu().pin_memory()
     h_coin = coins.cpu().pin_memory()
+    h_ac = Q.pack_actions(actions, coins).cpu().pin_memory()          # 1 byte per env per ply
+    h_res = torch.empty(E, dtype=torch.int64).pin_memory()            # 8 bytes per env per ply
     h_reward = torch.empty(E, dtype=torch.float32).pin_memory()
     h_done = torch.empty(E, dtype=torch.bool).pin_memory()
     h_mask = torch.empty(E, dtype=torch.int64).pin_memory()
     e2e_K = max(1, min(K, args.e2e_steps))
-    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for it in range(2 + e2e_K):
-        if it == 2:
-            barrier()
-            s2.record()
-        env.reset()
-        for ply in range(PLIES):
-            env.step_host(h_act[ply], h_coin[ply], h_reward, h_done, h_mask)
-    e2.record()
-    barrier()
-    e2e_ms = max_over_ranks(s2.elapsed_time(e2))
-    e2e_value = sum_over_ranks(float(steps_per_pass)) * e2e_K / (e2e_ms * 1e-3)
+
+    def e2e_run(step_fn):
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(2 + e2e_K):
+            if it == 2:
+                barrier()
+                s2.record()
+            env.reset()
+            for ply in range(PLIES):
+                step_fn(ply)
+        e2.record()
+        barrier()
+        ms = max_over_ranks(s2.elapsed_time(e2))
+        return sum_over_ranks(float(steps_per_pass)) * e2e_K / (ms * 1e-3), ms / e2e_K
+
+    v_packed, ms_packed = e2e_run(lambda ply: env.step_host_packed(h_ac[ply], h_res))
+    _, term_chk, _, _ = Q.unpack_result(h_res)
+    assert int(term_chk.sum()) == E, "e2e pass did not finish every game"
+    v_sep, ms_sep = e2e_run(lambda ply: env.step_host(h_act[ply], h_coin[ply], h_reward, h_done, h_mask))
     assert int(h_done.sum()) == E, "e2e pass did not finish every game"
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * E * PLIES,
-           "d2h_bytes_per_step": 13 * E * PLIES, "steps": e2e_K, "ms_per_step": e2e_ms / e2e_K,
-           "api": "BatchedEnv.reset + 9 x BatchedEnv.step_host (pinned host actions/coins in, "
-                  "reward/done/mask out, chunk-pipelined over side streams)"}
+    launches += 2 * (2 + e2e_K) * (1 + PLIES * 8)
+    e2e = {"value": v_packed, "unit": UNIT, "h2d_bytes_per_step": 1 * E * PLIES,
+           "d2h_bytes_per_step": 8 * E * PLIES, "steps": e2e_K, "ms_per_step": ms_packed,
+           "api": "BatchedEnv.reset + 9 x BatchedEnv.step_host_packed (C ABI qttt_step_packed; pinned host "
+                  "buffers: 1 B action|coin in, one 64-bit result word (legal mask, terminated, line, status) "
+                  "out per env per ply; 8 slices pipelined over 4 side streams)",
+           "separate_arrays": {"value": v_sep, "ms_per_step": ms_sep, "h2d_bytes_per_step": 2 * E * PLIES,
+                               "d2h_bytes_per_step": 13 * E * PLIES,
+                               "api": "BatchedEnv.step_host (qttt_step): uint8 actions + coins in, f32 reward + "
+                                      "bool done + int64 mask out"}}
 
     # ---- extras: the other configs of BASELINE.json
     extra = {}
@@ -316,8 +331,14 @@ def run_b200(args):
             small.step(sa[p], sc[p])
     ms = timed(small_pass, 50)
     launches += 51 * (1 + PLIES)
-    extra["config2_4096_envs"] = {"env_steps_per_s": small_steps / (ms * 1e-3) * world, "ms_per_pass": ms,
-                                  "note": "launch-latency bound (10 launches per pass, 4096 threads each)"}
+    graph = small.capture_episode(sa, sc)
+    ms_graph = timed(graph.replay, 200)
+    launches += (201 + 2) * (1 + PLIES)
+    extra["config2_4096_envs"] = {"env_steps_per_s": small_steps / (ms_graph * 1e-3) * world,
+                                  "ms_per_pass_cuda_graph": ms_graph, "ms_per_pass_eager": ms,
+                                  "env_steps_per_s_eager": small_steps / (ms * 1e-3) * world,
+                                  "note": "launch-latency bound (10 launches of 4096 threads per pass); the whole "
+                                          "episode is captured in one CUDA graph (BatchedEnv.capture_episode)"}
 
     # config 5: fused self-play sweep (K5) + the one NCCL all_reduce of the tallies
     G = args.sweep_games

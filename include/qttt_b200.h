@@ -85,6 +85,17 @@ QTTT_API int qttt_step(qttt_state* state, const void* action, int action_format,
               uint64_t seed, uint64_t game_base, float* reward, uint8_t* done, uint64_t* mask,
               uint8_t* status, int64_t n, void* stream);
 
+/* qttt_step with compact I/O, for callers whose buffers live in HOST memory (there the PCIe
+ * link, not HBM, is the bound: 9 bytes per game cross it instead of 15).
+ *   action_coin uint8[n]  : bits 0..5 action index (QTTT_ACT_INDEX; 36..63 = illegal),
+ *                           bit 7 forced coin
+ *   result      uint64[n] : bits 0..35 legal mask of the new state, bit 36 terminated,
+ *                           bit 37 "a line exists" (reward = bit ? -1.0f : -0.0f, env.py:49),
+ *                           bits 38..39 status (QTTT_ST_*)
+ * Same transition, same outputs as qttt_step, bit for bit. */
+QTTT_API int qttt_step_packed(qttt_state* state, const uint8_t* action_coin, uint64_t* result,
+                              int64_t n, void* stream);
+
 /* Env.step driven by the uniform-random policy of MCTS._simulate (mcts.py:185-198,
  * 287-292): action ~ U(legal actions), coin ~ U{0,1}, both from Philox4x32-10 with counter
  * (game_lo, game_hi, len(moves), 0) and key seed.  Terminated games (mcts.py:52-65) are left

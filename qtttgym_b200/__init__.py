@@ -9,13 +9,13 @@ displayBoard, Env) for the parts on the hot path: ``Env`` (single-env adapter), 
 importing this package without that library works, using it does not.
 """
 from .actions import NUM_ACTIONS, PAIRS, ind2move, move2ind
-from .env import BatchedEnv, Env, observe_states, pack_states
+from .env import BatchedEnv, Env, observe_states, pack_actions, pack_states, unpack_result
 from .qeval import QEvalB200, qeval_both, square_probabilities
 from .rollout import STAT_NAMES, rollout_eval, selfplay_sweep, shard_range, sharded_sweep
 
 __all__ = [
     "NUM_ACTIONS", "PAIRS", "ind2move", "move2ind",
-    "BatchedEnv", "Env", "observe_states", "pack_states",
+    "BatchedEnv", "Env", "observe_states", "pack_states", "pack_actions", "unpack_result",
     "QEvalB200", "qeval_both", "square_probabilities",
     "STAT_NAMES", "rollout_eval", "selfplay_sweep", "shard_range", "sharded_sweep",
 ]

@@ -102,6 +102,28 @@ k_step(qttt_state* __restrict__ state, const uint8_t* __restrict__ action,
     }
 }
 
+// K1 with compact I/O (one byte in, one 64-bit word out per game): see qttt_step_packed.
+__global__ void __launch_bounds__(kThreads)
+k_step_packed(qttt_state* __restrict__ state, const uint8_t* __restrict__ action_coin,
+              unsigned long long* __restrict__ result, uint32_t n) {
+    __shared__ __align__(16) uint8_t smem[kLutStepBytes];
+    stage_luts(smem, kLutStepBytes);
+    const Luts L = luts_from_image(smem);
+    const uint32_t stride = gridDim.x * kThreads;
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+        uint4* sp = reinterpret_cast<uint4*>(state + i);
+        const uint4 sv = *sp;
+        State s{sv.x, sv.y, sv.z, sv.w};
+        const uint32_t ac = action_coin[i];
+        const StepResult r = step_core(s, (uint32_t)L.pair[ac & 63u], ac >> 7, L);
+        if (!r.illegal) *sp = make_uint4(s.x, s.y, s.z, s.w);
+        const unsigned long long win = any_line(s, r.classical, L) != 0u;
+        const unsigned long long term = win | (unsigned long long)(r.n > 8u);
+        result[i] = L.legal[~r.classical & M9] | (term << 36) | (win << 37) |
+                    ((unsigned long long)r.illegal << 38);
+    }
+}
+
 // ------------------------------------------------------------------------------ observe / pack
 __global__ void __launch_bounds__(kThreads)
 k_observe(const qttt_state* __restrict__ state, int8_t* __restrict__ classical_out,
@@ -333,6 +355,22 @@ int qttt_step(qttt_state* state, const void* action, int action_format, const ui
     if (action_format == QTTT_ACT_INDEX)
         return launch_step<QTTT_ACT_INDEX, false>(state, act, coin, seed, game_base, reward, done, mask, status, nullptr, nullptr, n, st);
     return launch_step<QTTT_ACT_PAIR, false>(state, act, coin, seed, game_base, reward, done, mask, status, nullptr, nullptr, n, st);
+}
+
+int qttt_step_packed(qttt_state* state, const uint8_t* action_coin, uint64_t* result, int64_t n,
+                     void* stream) {
+    if (n == 0) return QTTT_OK;
+    if (!state || !action_coin || !result || n < 0) return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(result, 8)) return QTTT_ERR_ALIGN;
+    const int64_t kSlice = 1ll << 31;
+    for (int64_t lo = 0; lo < n; lo += kSlice) {
+        const int64_t m = n - lo < kSlice ? n - lo : kSlice;
+        k_step_packed<<<grid_for(k_step_packed, m), kThreads, 0, (cudaStream_t)stream>>>(
+            state + lo, action_coin + lo, reinterpret_cast<unsigned long long*>(result) + lo, (uint32_t)m);
+        const int rc = check_launch();
+        if (rc != QTTT_OK) return rc;
+    }
+    return QTTT_OK;
 }
 
 int qttt_step_random(qttt_state* state, uint64_t seed, uint64_t game_base, uint8_t* action_out,

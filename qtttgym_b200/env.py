@@ -167,6 +167,63 @@ class BatchedEnv:
                 cur.wait_event(fin)
         return reward_host, done_host, mask_host
 
+    def step_host_packed(self, action_coin_host, result_host, chunks: int = 8, n_streams: int = 4):
+        """``step_host`` with compact I/O (``qttt_step_packed``): 1 byte in and 8 bytes out per
+        env cross PCIe instead of 2 + 13.  ``action_coin_host`` uint8[N] from ``pack_actions``;
+        ``result_host`` int64[N], decoded with ``unpack_result``.  Same transition, bit for bit.
+        """
+        n, dev = self.num_envs, self.device
+        for t, dt in ((action_coin_host, torch.uint8), (result_host, torch.int64)):
+            if t.dtype != dt or t.numel() != n or t.device.type != "cpu" or not t.is_contiguous():
+                raise ValueError("step_host_packed expects contiguous CPU uint8[N] / int64[N] tensors")
+        if self._host_streams is None or len(self._host_streams) != n_streams:
+            self._host_streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
+            self._d_act = torch.empty(n, dtype=torch.uint8, device=dev)
+            self._d_coin = torch.empty(n, dtype=torch.uint8, device=dev)
+        cur = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        chunks = max(1, min(chunks, (n + 255) // 256))
+        per = -(-(-(-n // chunks)) // 256) * 256
+        with torch.cuda.device(dev):
+            for c in range(chunks):
+                lo, hi = c * per, min(n, (c + 1) * per)
+                if lo >= hi:
+                    break
+                st = self._host_streams[c % n_streams]
+                st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    self._d_act[lo:hi].copy_(action_coin_host[lo:hi], non_blocking=True)
+                    _lib.check(self.lib.qttt_step_packed(
+                        self.state.data_ptr() + 16 * lo, self._d_act.data_ptr() + lo,
+                        self.mask.data_ptr() + 8 * lo, hi - lo, st.cuda_stream))
+                    result_host[lo:hi].copy_(self.mask[lo:hi], non_blocking=True)
+            for st in self._host_streams:
+                fin = torch.cuda.Event()
+                fin.record(st)
+                cur.wait_event(fin)
+        return result_host
+
+    def capture_episode(self, actions, choices):
+        """Records ``reset`` + ``len(actions)`` steps (uint8[T,N] action indices and coins, on
+        the device) into ONE CUDA graph and returns it; ``graph.replay()`` then plays the whole
+        episode with a single launch call -- for small batches, where a step is a few
+        microseconds of GPU work and launch latency dominates."""
+        if actions.dtype != torch.uint8 or choices.dtype != torch.uint8 or actions.shape != choices.shape \
+                or actions.dim() != 2 or actions.shape[1] != self.num_envs or actions.device != self.device:
+            raise ValueError("capture_episode expects uint8[T,N] device tensors")
+        actions, choices = actions.contiguous(), choices.contiguous()
+        self._graph_inputs = (actions, choices)        # keep the captured buffers alive
+        self.reset()
+        self.step(actions[0], choices[0])              # warm-up outside the capture
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.reset()
+            for t in range(actions.shape[0]):
+                self.step(actions[t], choices[t])
+        return graph
+
     def turn(self):
         """env.py:65-66: len(moves) per env (uint8[N])."""
         return ((self.state[:, 0] >> 27) & 15).to(torch.uint8)
@@ -225,6 +282,26 @@ class BatchedEnv:
         # no extra kernels here: everything returned is a buffer the step kernel wrote
         info = {"action_mask": self.mask, "status": self.status}
         return self._obs(), self.reward, self.done, self._never, info
+
+
+def pack_actions(actions, choices):
+    """uint8 action indices (0..35; anything else becomes an illegal action) and coin bits ->
+    the one-byte-per-env input of ``step_host_packed``."""
+    a = torch.where(actions < 36, actions, torch.full_like(actions, 63))
+    return (a | ((choices & 1) << 7)).to(torch.uint8)
+
+
+def unpack_result(result):
+    """int64 result words of ``step_host_packed`` -> (reward f32, terminated bool, mask int64,
+    status uint8), identical to what ``step`` returns."""
+    mask = result & ((1 << 36) - 1)
+    terminated = ((result >> 36) & 1).bool()
+    win = ((result >> 37) & 1).bool()
+    neg_one = torch.tensor(-1.0, dtype=torch.float32, device=result.device)
+    neg_zero = torch.tensor(-0.0, dtype=torch.float32, device=result.device)
+    reward = torch.where(win, neg_one, neg_zero)
+    status = ((result >> 38) & 3).to(torch.uint8)
+    return reward, terminated, mask, status
 
 
 def observe_states(state, extras: bool = False):
@@ -327,4 +404,4 @@ class Env:
         return float(self._batched.observation(extras=True)["reward_p1"][0].item())
 
 
-__all__ = ["BatchedEnv", "Env", "observe_states", "pack_states", "PAIRS"]
+__all__ = ["BatchedEnv", "Env", "observe_states", "pack_states", "pack_actions", "unpack_result", "PAIRS"]

@@ -82,6 +82,12 @@ class EmuGames:
                           C.c_int64(self.n))
         return o
 
+    def step_packed(self, action_coin):
+        ac = np.ascontiguousarray(action_coin, dtype=np.uint8)
+        res = np.empty(self.n, np.uint64)
+        self.lib.emu_step_packed(_p(self.state), _p(ac), _p(res), C.c_int64(self.n))
+        return res
+
     def step_random(self, seed, game_base=0):
         o = self._outs()
         o["action"] = np.empty(self.n, np.uint8)
@@ -178,6 +184,14 @@ class CudaGames:
         ac = t.from_numpy(np.ascontiguousarray(actions, np.uint8)).cuda()
         co = None if coins is None else t.from_numpy(np.ascontiguousarray(coins, np.uint8)).cuda()
         return self._outs(self.env.step(ac, co))
+
+    def step_packed(self, action_coin):
+        t = self.torch
+        ac = t.from_numpy(np.ascontiguousarray(action_coin, np.uint8)).pin_memory()
+        res = t.empty(self.n, dtype=t.int64).pin_memory()
+        self.env.step_host_packed(ac, res, chunks=3, n_streams=2)
+        t.cuda.synchronize()
+        return res.numpy().astype(np.uint64)
 
     def step_random(self, seed, game_base=0):
         self.env.seed, self.env.game_base = seed, game_base

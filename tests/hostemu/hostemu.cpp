@@ -44,6 +44,20 @@ int emu_step(State* state, const void* action, int fmt, const uint8_t* coin, uin
     return 0;
 }
 
+int emu_step_packed(State* state, const uint8_t* action_coin, uint64_t* result, int64_t n) {
+    const Luts L = luts();
+    for (int64_t i = 0; i < n; ++i) {
+        State s = state[i];
+        const uint32_t ac = action_coin[i];
+        const StepResult r = step_core(s, (uint32_t)L.pair[ac & 63u], ac >> 7, L);
+        if (!r.illegal) state[i] = s;
+        const uint64_t win = any_line(s, r.classical, L) != 0u;
+        const uint64_t term = win | (uint64_t)(r.n > 8u);
+        result[i] = L.legal[~r.classical & M9] | (term << 36) | (win << 37) | ((uint64_t)r.illegal << 38);
+    }
+    return 0;
+}
+
 int emu_step_random(State* state, uint64_t seed, uint64_t game_base, uint8_t* action_out,
                     uint8_t* coin_out, float* reward, uint8_t* done, uint64_t* mask,
                     uint8_t* status, int64_t n) {

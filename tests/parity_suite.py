@@ -347,3 +347,31 @@ def check_philox_coin(backend, n_games=3000, seed=99, game_base=1234):
         assert_same_step(o, r, f"philox coin ply {ply}")
         mask = r["mask"]
     assert_same_obs(dut.observe(), ref.observe(), "philox coin final")
+
+
+def check_packed_step(backend, n_games=5000, seed=31):
+    """qttt_step_packed: one byte in (action | coin << 7), one word out (mask | terminated << 36 |
+    line << 37 | status << 38) -- same transition as the oracle, bit for bit."""
+    rng = np.random.default_rng(seed)
+    ref = CO.Games(n_games)
+    dut = backend.games(n_games)
+    mask = np.full(n_games, (1 << 36) - 1, np.uint64)
+    for ply in range(11):
+        legal = expand_mask(mask)
+        k = (rng.random((n_games, 36)) * legal).argmax(1).astype(np.uint8)
+        k[~legal.any(1)] = 63
+        bad = rng.random(n_games) < 0.08
+        k[bad] = rng.integers(0, 64, int(bad.sum())).astype(np.uint8)       # random index, often illegal
+        coins = rng.integers(0, 2, n_games).astype(np.uint8)
+        pairs = np.full((n_games, 2), -1, np.int8)
+        pairs[k < 36] = PAIRS[k[k < 36]]
+        r = ref.step(pairs, coins)
+        res = dut.step_packed(k | (coins << 7))
+        where = f"{backend.name} packed ply {ply}"
+        assert np.array_equal(res & np.uint64((1 << 36) - 1), r["mask"]), where
+        assert np.array_equal((res >> np.uint64(36)) & np.uint64(1), r["done"].astype(np.uint64)), where
+        win = (r["reward"].view(np.uint32) == 0xBF800000).astype(np.uint64)
+        assert np.array_equal((res >> np.uint64(37)) & np.uint64(1), win), where
+        assert np.array_equal((res >> np.uint64(38)) & np.uint64(3), r["status"].astype(np.uint64)), where
+        assert_same_obs(dut.observe(), ref.observe(), where)
+        mask = r["mask"]

@@ -223,3 +223,46 @@ def test_step_host_equals_step(cuda):
         assert torch.equal(r.cpu().view(torch.int32), hr.view(torch.int32))
         assert torch.equal(t.cpu(), hd) and torch.equal(i2["action_mask"].cpu(), hm)
         assert torch.equal(a.state, b.state) and torch.equal(a.state, gen.state)
+
+
+def test_packed_step_host(cuda):
+    S.check_packed_step(cuda, 40_001)
+
+
+def test_pack_unpack_helpers_match_step(cuda):
+    import torch
+    import qtttgym_b200 as Q
+    n = 10_000
+    gen, a, b = Q.BatchedEnv(n, seed=4), Q.BatchedEnv(n, seed=4), Q.BatchedEnv(n, seed=4)
+    res = torch.empty(n, dtype=torch.int64).pin_memory()
+    for ply in range(9):
+        info = gen.step_random(record=True)[4]
+        act, coin = info["action"].clone(), info["coin"].clone()
+        _, r, t, _, i2 = a.step(act, coin)
+        b.step_host_packed(Q.pack_actions(act, coin).cpu().pin_memory(), res)
+        torch.cuda.synchronize()
+        r2, t2, m2, s2 = Q.unpack_result(res)
+        assert torch.equal(r.cpu().view(torch.int32), r2.view(torch.int32)) and torch.equal(t.cpu(), t2)
+        assert torch.equal(i2["action_mask"].cpu(), m2) and torch.equal(i2["status"].cpu(), s2)
+        assert torch.equal(a.state, b.state)
+
+
+def test_episode_cuda_graph(cuda):
+    """A whole episode (reset + 9 steps) captured in one CUDA graph replays to the same states."""
+    import torch
+    import qtttgym_b200 as Q
+    n = 4096
+    gen = Q.BatchedEnv(n, seed=21)
+    acts, coins = [], []
+    for _ in range(9):
+        info = gen.step_random(record=True)[4]
+        acts.append(info["action"].clone()); coins.append(info["coin"].clone())
+    acts, coins = torch.stack(acts), torch.stack(coins)
+    env = Q.BatchedEnv(n, seed=21)
+    graph = env.capture_episode(acts, coins)
+    for _ in range(3):
+        env.state.fill_(-1)                  # garbage: the graph's reset must overwrite it
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(env.state, gen.state)
+        assert torch.equal(env.done, gen.done) and torch.equal(env.mask, gen.mask)

@@ -56,3 +56,7 @@ def test_step_random(emu):
 
 def test_philox_coin(emu):
     S.check_philox_coin(emu, 1500)
+
+
+def test_packed_step(emu):
+    S.check_packed_step(emu)
