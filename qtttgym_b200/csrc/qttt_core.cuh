@@ -110,6 +110,8 @@ struct LutImage {
     uint8_t  line[512];     // square set -> 1 if it contains one of the 8 lines (board.py:84-110)
     uint32_t nrow[16][4];   // per len(moves): multipliers (see NRow)
     uint64_t spread[512];   // square set -> the same bits at a 4-bit stride
+    uint8_t  rankpair[10][40];  // [f][k] -> r1 | r2 << 4: the k-th pair (r1 < r2) of f items, lexicographic
+    uint16_t nthbit[512][9];    // [square set][r] -> one-hot of its r-th member (0 past the end)
 };
 // Row n of LutImage::nrow: everything the transition needs that depends only on n = len(moves),
 // as multipliers so the work lands on the (otherwise idle) IMAD pipe:
@@ -117,8 +119,11 @@ struct LutImage {
 //   kp         : plane pattern of v = n + 1 for word w: (v&1) | (v&2)<<8 | (v&4)<<16
 struct NRow { uint32_t mx, my, mz, kp; };
 constexpr int kLutStepBytes = 512 * 8 + 256 * 2 + 512 + 256;   // legal + pair + line + nrow = 5376
-constexpr int kLutBytes = (int)sizeof(LutImage);        // 9472
-static_assert(sizeof(LutImage) == 9472, "LutImage layout");
+constexpr int kLutQevalBytes = kLutStepBytes + 512 * 8;                // + spread = 9472
+constexpr int kLutPolicyBytes = kLutQevalBytes + 400 + 512 * 9 * 2;    // + rankpair + nthbit = 19088 (whole image)
+constexpr int kLutBytes = (int)sizeof(LutImage);        // 19088
+static_assert(sizeof(LutImage) == 9472 + 400 + 9216, "LutImage layout");
+static_assert(kLutPolicyBytes % 16 == 0 && kLutStepBytes % 16 == 0, "staged in 16-byte vectors");
 
 constexpr LutImage make_lut_image() {
     LutImage t{};
@@ -148,6 +153,16 @@ constexpr LutImage make_lut_image() {
         t.nrow[n][2] = n >= 6u ? m : 0u;
         t.nrow[n][3] = (v & 1u) | ((v & 2u) << 8) | ((v & 4u) << 16);
     }
+    for (int f = 0; f < 10; ++f) {
+        int kk = 0;
+        for (int r1 = 0; r1 < f; ++r1)
+            for (int r2 = r1 + 1; r2 < f; ++r2, ++kk) t.rankpair[f][kk] = (uint8_t)(r1 | (r2 << 4));
+    }
+    for (uint32_t m = 0; m < 512; ++m) {
+        int r = 0;
+        for (int sq = 0; sq < 9; ++sq)
+            if (m >> sq & 1u) t.nthbit[m][r++] = (uint16_t)(1u << sq);
+    }
     return t;
 }
 
@@ -156,6 +171,8 @@ struct Luts {
     const uint16_t* pair;
     const uint8_t*  line;
     const NRow*     nrow;
+    const uint8_t*  rankpair;
+    const uint16_t* nthbit;
     const uint64_t* spread;
 };
 QTTT_HD Luts luts_from_image(const void* img) {
@@ -165,6 +182,8 @@ QTTT_HD Luts luts_from_image(const void* img) {
     l.pair = t->pair;
     l.line = t->line;
     l.nrow = reinterpret_cast<const NRow*>(t->nrow);
+    l.rankpair = &t->rankpair[0][0];
+    l.nthbit = &t->nthbit[0][0];
     l.spread = t->spread;
     return l;
 }
@@ -427,6 +446,21 @@ QTTT_HD uint32_t nth_set_bit36(uint64_t m, uint32_t k) {
     return base;
 }
 
+// The same draw by table: the legal actions are the unordered pairs of free squares, and the
+// action-index order (mcts.py:339-349) restricted to them is the lexicographic order of rank
+// pairs (r1 < r2) over the free squares.  So the floor(x0 * m / 2^32)-th legal action is the
+// pair of the r1-th and r2-th free squares, with (r1, r2) the k-th pair of f = |free| items.
+// Returns the E mask of the chosen pair (0 when fewer than two squares are free).
+QTTT_HD uint32_t policy_edge(uint32_t free_set, uint32_t x0, const Luts& L) {
+    const uint32_t f = (uint32_t)popc32(free_set);
+    const uint32_t m = (f * (f - 1u)) >> 1;
+    const uint32_t k = mulhi32(x0, m);
+    const uint32_t rp = L.rankpair[f * 40u + k];
+    const uint16_t* row = L.nthbit + free_set * 9u;
+    const uint32_t e = (uint32_t)row[rp & 15u] | (uint32_t)row[rp >> 4];
+    return m ? e : 0u;
+}
+
 // uniform-random legal action + coin for (seed, game, ply, domain)
 QTTT_HD void policy_draw(uint64_t seed, uint64_t game, uint32_t ply, uint32_t domain,
                          uint64_t legal_mask, uint32_t& action, uint32_t& coin) {
@@ -472,13 +506,12 @@ QTTT_HD uint32_t finished_winner(const State& s, const Luts& L, bool& terminal) 
 }
 
 // One ply of MCTS._simulate (mcts.py:188-196): action ~ U(legal), coin ~ U{0,1}.
+// Needs the policy tables (kLutPolicyBytes staged).
 QTTT_HD StepResult playout_ply(State& s, uint32_t C, uint64_t seed, uint64_t game, uint32_t domain,
-                               const Luts& L, uint32_t* act_out = nullptr, uint32_t* coin_out = nullptr) {
-    uint32_t act, c;
-    policy_draw(seed, game, n_moves(s), domain, L.legal[~C & M9], act, c);
-    if (act_out) *act_out = act;
-    if (coin_out) *coin_out = c;
-    return step_core(s, (uint32_t)L.pair[act & 255u], c, L);
+                               const Luts& L) {
+    uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = n_moves(s), c3 = domain;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return step_core(s, policy_edge(~C & M9, c0, L), c1 & 1u, L);
 }
 
 QTTT_HD int board_value(uint32_t P0, uint32_t P1, uint32_t P2, uint32_t P3, int sq) {
@@ -602,15 +635,17 @@ QTTT_HD uint32_t plies_of(const State& s) {
 // One uniform-random playout to a terminal state (mcts.py:185-208).  Returns the winner.
 QTTT_HD uint32_t playout_game(State s, uint64_t seed, uint64_t game, uint32_t domain, const Luts& L,
                               uint32_t& steps, uint32_t& collapses) {
-    bool terminal;
-    uint32_t w = finished_winner(s, L, terminal);
+    uint32_t C = classical(s);
+    bool terminal = (any_line(s, C, L) != 0u) | (n_moves(s) >= 9u);          // mcts.py:52-65
     while (!terminal) {
-        const StepResult r = playout_ply(s, classical(s), seed, game, domain, L);
+        const StepResult r = playout_ply(s, C, seed, game, domain, L);
+        C = r.classical;
         ++steps;
         collapses += r.collapsed;
-        w = finished_winner(s, L, terminal);
+        terminal = (any_line(s, C, L) != 0u) | (r.n >= 9u);
     }
-    return w;
+    bool t2;
+    return finished_winner(s, L, t2);       // who has the earlier line: only needed at the end
 }
 
 }  // namespace qttt

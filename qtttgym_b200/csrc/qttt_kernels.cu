@@ -156,8 +156,8 @@ k_qeval_both(const qttt_state* __restrict__ state, const uint8_t* __restrict__ a
              uint64_t* __restrict__ board0, uint64_t* __restrict__ board1,
              int8_t* __restrict__ sq0, int8_t* __restrict__ sq1, uint8_t* __restrict__ closes,
              float* __restrict__ result_prob, int64_t n) {
-    __shared__ __align__(16) uint8_t smem[kLutBytes];
-    stage_luts(smem, kLutBytes);
+    __shared__ __align__(16) uint8_t smem[kLutQevalBytes];
+    stage_luts(smem, kLutQevalBytes);
     const Luts L = luts_from_image(smem);
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
@@ -171,10 +171,10 @@ __global__ void __launch_bounds__(kThreads)
 k_rollout(const qttt_state* __restrict__ roots, int32_t n_rollouts, uint64_t seed,
           int32_t* __restrict__ tallies, float* __restrict__ value,
           unsigned long long* __restrict__ steps_total) {
-    __shared__ __align__(16) uint8_t smem[kLutStepBytes];
+    __shared__ __align__(16) uint8_t smem[kLutPolicyBytes];
     __shared__ int sh_tally[3];
     __shared__ unsigned long long sh_steps;
-    stage_luts(smem, kLutStepBytes);
+    stage_luts(smem, kLutPolicyBytes);
     const Luts L = luts_from_image(smem);
     if (threadIdx.x < 3) sh_tally[threadIdx.x] = 0;
     if (threadIdx.x == 0) sh_steps = 0ull;
@@ -215,9 +215,9 @@ k_rollout(const qttt_state* __restrict__ roots, int32_t n_rollouts, uint64_t see
 // earlier (mean 8.29 of 9 plies) idle until the warp's last game ends.
 __global__ void __launch_bounds__(kThreads)
 k_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, unsigned long long* __restrict__ stats) {
-    __shared__ __align__(16) uint8_t smem[kLutStepBytes];
+    __shared__ __align__(16) uint8_t smem[kLutPolicyBytes];
     __shared__ unsigned long long sh[16];
-    stage_luts(smem, kLutStepBytes);
+    stage_luts(smem, kLutPolicyBytes);
     const Luts L = luts_from_image(smem);
     if (threadIdx.x < 16) sh[threadIdx.x] = 0ull;
     __syncthreads();
@@ -238,10 +238,10 @@ k_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, unsigned long long* __r
                 const StepResult r = playout_ply(s, C, seed, (uint64_t)g, 0u, L);
                 C = r.classical;
                 co += r.collapsed;
-                bool terminal = r.n >= 9u;
-                uint32_t w = 0u;
-                if (r.collapsed) w = finished_winner(s, L, terminal);   // lines only appear through a collapse
+                const bool terminal = (any_line(s, C, L) != 0u) | (r.n >= 9u);   // mcts.py:52-65
                 if (terminal) {
+                    bool t2;
+                    const uint32_t w = finished_winner(s, L, t2);   // who has the earlier line
                     xw += w == 1u; ow += w == 2u; dr += w == 0u;
                     st += ply + 1u;
                     h5 += ply == 4u; h6 += ply == 5u; h7 += ply == 6u; h8 += ply == 7u; h9 += ply == 8u;
