@@ -121,6 +121,13 @@ QTTT_API int qttt_observe(const qttt_state* state, int8_t* classical, int8_t* mo
                  int8_t* q_p1, int8_t* q_p2, uint8_t* turn, int8_t* rounds, float* reward_p1,
                  uint8_t* winner, uint8_t* mask_bool, int64_t n, void* stream);
 
+/* GameState.to_vector (mcts.py:67-85): the (18, 10) float feature matrix the reference feeds
+ * its policy/value net, for n games -> features float[n][18][10] (16-byte aligned).
+ * Rows 0..8: one-hot of board[square] (column 9 = not classical); rows 9..17: 1/sqrt(9) at
+ * [square, t] for every move t on that square, 1.0 in column 9 for squares in no entangled
+ * component.  (nn.Model.get_mask, nn.py:44-61, is the complement of the legal mask.) */
+QTTT_API int qttt_features(const qttt_state* state, float* features, int64_t n, void* stream);
+
 /* Inverse of qttt_observe for (classical, moves, n_moves): builds packed states from
  * reference-shaped positions (what MCTS.reset does with game.board / game.moves,
  * mcts.py:139-164 -- but the entanglement is re-derived, so mid-game roots are handled

@@ -14,6 +14,8 @@ Fixtures
   mcts_step_v1.json.gz     MCTS._step(node, action): children (board, moves, turn, winner,
                            terminal) incl. both collapse outcomes; action lists / masks
   population_v1.json       tallies of 20,000 reference random games (MT19937 seed 12345)
+  features_v1.json.gz      GameState.to_vector() (mcts.py:67-85) and displayBoard() text
+                           (qtttgym/display.py:4-32) along random MCTS._step walks
 """
 from __future__ import annotations
 
@@ -143,6 +145,31 @@ def main():
             })
             node = kids[rng.randrange(len(kids))]
     _dump("mcts_step_v1.json.gz", steps)
+
+    # ---- to_vector / displayBoard along _step walks (children carry their qstructs)
+    import contextlib
+    import io
+    feats = []
+    rng = random.Random(13)
+    for _ in range(60):
+        mc = M()
+        mc.reset(ns.qtttgym.Board(ns.qtttgym.QEvalClassic()))
+        node = mc.root
+        while True:
+            vec = node.to_vector()
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                ns.qtttgym.displayBoard(node)
+            feats.append({"board": list(node.board), "moves": [list(m) for m in node.moves],
+                          "nonzero": [[int(i), float(v)] for i, v in enumerate(vec.flatten()) if v != 0.0],
+                          "display": buf.getvalue()})
+            if node.terminal:
+                break
+            ns.coin.bits.clear()
+            ns.coin.feed(0, 1)
+            kids = mc._step(node, int(rng.choice(node.actions)))
+            node = kids[rng.randrange(len(kids))]
+    _dump("features_v1.json.gz", feats)
 
     # ---- population tallies with the reference's own MT19937 coin
     ns.qeval_module.random = ns.real_random

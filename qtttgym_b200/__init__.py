@@ -8,14 +8,18 @@ displayBoard, Env) for the parts on the hot path: ``Env`` (single-env adapter), 
 ``selfplay_sweep``.  Everything computes in libqttt_b200.so (hand-written CUDA for sm_100a);
 importing this package without that library works, using it does not.
 """
+from .arena import BatchedStrategy, RandomStrategy, RolloutStrategy, eval_strats, play_games
 from .actions import NUM_ACTIONS, PAIRS, ind2move, move2ind
-from .env import BatchedEnv, Env, observe_states, pack_actions, pack_states, unpack_result
+from .env import (BatchedEnv, Env, observe_states, pack_actions, pack_states, render_text, to_vector,
+                  unpack_result)
 from .qeval import QEvalB200, qeval_both, square_probabilities
 from .rollout import STAT_NAMES, rollout_eval, selfplay_sweep, shard_range, sharded_sweep
 
 __all__ = [
     "NUM_ACTIONS", "PAIRS", "ind2move", "move2ind",
     "BatchedEnv", "Env", "observe_states", "pack_states", "pack_actions", "unpack_result",
+    "to_vector", "render_text",
     "QEvalB200", "qeval_both", "square_probabilities",
+    "BatchedStrategy", "RandomStrategy", "RolloutStrategy", "eval_strats", "play_games",
     "STAT_NAMES", "rollout_eval", "selfplay_sweep", "shard_range", "sharded_sweep",
 ]

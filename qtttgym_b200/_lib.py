@@ -23,6 +23,7 @@ _SIGNATURES = {
     "qttt_step_packed": ([_vp, _vp, _vp, _i64, _vp], _int),
     "qttt_step_random": ([_vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp], _int),
     "qttt_observe": ([_vp] * 11 + [_i64, _vp], _int),
+    "qttt_features": ([_vp, _vp, _i64, _vp], _int),
     "qttt_pack": ([_vp, _vp, _vp, _vp, _i64, _vp], _int),
     "qttt_qeval_both": ([_vp] * 10 + [_i64, _vp], _int),
     "qttt_rollout": ([_vp, _i64, _i32, _u64, _vp, _vp, _vp, _vp], _int),

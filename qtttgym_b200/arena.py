@@ -1,0 +1,121 @@
+"""Batched tournament harness around the transition path (reference: strategy.py:3-36 the
+``Strategy`` interface, strat_eval.py:21-95 ``check_win`` / ``play_game`` / ``eval_strats`` and
+its (strat1 wins, strat2 wins, draws) tally convention).
+
+A strategy here plays N games at once: ``choose()`` returns one action index per env.  Two
+are provided: ``RandomStrategy`` (the uniform-random policy of ``MCTS._simulate``) and
+``RolloutStrategy`` (flat Monte-Carlo: every legal action is scored by random rollouts from
+both of its collapse outcomes -- ``qeval_both`` + ``rollout_eval`` -- i.e. the leaf evaluator
+of mcts.py:166-173 applied one ply deep, without the tree).
+"""
+from __future__ import annotations
+
+import torch
+
+from .env import BatchedEnv
+from .qeval import qeval_both
+from .rollout import rollout_eval
+
+
+class BatchedStrategy:
+    """strategy.py:3-36 for a batch: reset / contemplate / choose / sync."""
+
+    def reset(self, env: BatchedEnv):
+        self.env = env
+
+    def contemplate(self, thinking_time=None):
+        """spend some time planning the move (no-op by default)"""
+
+    def choose(self) -> torch.Tensor:
+        """uint8[N] action index per env (255 for envs that are already terminated)"""
+        raise NotImplementedError
+
+    def sync(self, actions: torch.Tensor):
+        """told which actions were played (stateless strategies ignore it)"""
+
+
+def _finished(env: BatchedEnv) -> torch.Tensor:
+    return env.done
+
+
+class RandomStrategy(BatchedStrategy):
+    """mcts.py:287-292: uniform over the legal actions."""
+
+    def __init__(self, seed: int = 0):
+        self.gen = None
+        self.seed = seed
+
+    def reset(self, env):
+        super().reset(env)
+        self.gen = torch.Generator(device=env.device)
+        self.gen.manual_seed(self.seed)
+
+    def choose(self):
+        legal = self.env.action_mask().float()
+        none = legal.sum(1) == 0
+        legal[none, 0] = 1.0
+        a = torch.multinomial(legal, 1, generator=self.gen).squeeze(1).to(torch.uint8)
+        a[none | _finished(self.env)] = 255
+        return a
+
+
+class RolloutStrategy(BatchedStrategy):
+    """Flat Monte-Carlo player.  For every env and every legal action: both collapse children
+    (mcts.py:233-267), ``n_rollouts`` uniform-random playouts from each (mcts.py:185-208), the
+    action's score is the mean child value seen from the mover (children are scored from their
+    own side to move, mcts.py:171, hence the sign flip as in ``_backpropogate``, mcts.py:179)."""
+
+    def __init__(self, n_rollouts: int = 32, seed: int = 0):
+        self.n_rollouts = int(n_rollouts)
+        self.seed = int(seed)
+        self.calls = 0
+
+    def choose(self):
+        env = self.env
+        n, dev = env.num_envs, env.device
+        legal = env.action_mask()                                      # bool[N,36]
+        states = env.state.unsqueeze(1).expand(n, 36, 4).reshape(n * 36, 4).contiguous()
+        acts = torch.arange(36, device=dev, dtype=torch.uint8).repeat(n)
+        kids = qeval_both(states, acts, want_boards=False, want_probs=False)
+        self.calls += 1
+        v0 = rollout_eval(kids["next0"], self.n_rollouts, self.seed + 2 * self.calls)[1]
+        v1 = rollout_eval(kids["next1"], self.n_rollouts, self.seed + 2 * self.calls + 1)[1]
+        score = (-(v0 + v1) * 0.5).view(n, 36)
+        score = torch.where(legal, score, torch.full_like(score, -2.0))
+        a = score.argmax(1).to(torch.uint8)
+        a[(~legal.any(1)) | _finished(env)] = 255
+        return a
+
+
+def play_games(strat_x: BatchedStrategy, strat_o: BatchedStrategy, n_games: int, seed: int = 0,
+               device="cuda"):
+    """strat_eval.py:34-63 for ``n_games`` games at once: X (player 1) and O alternate until a
+    line exists or 9 moves are on the board.  Returns (env, winner uint8[N]: 0 draw, 1 X, 2 O)."""
+    env = BatchedEnv(n_games, device=device, seed=seed)
+    strat_x.reset(env)
+    strat_o.reset(env)
+    env.done.zero_()
+    for ply in range(9):
+        mover = strat_x if ply % 2 == 0 else strat_o
+        mover.contemplate()
+        actions = mover.choose()
+        env.step(actions)
+        strat_x.sync(actions)
+        strat_o.sync(actions)
+        if bool(env.done.all()):
+            break
+    winner = env.observation(extras=True)["winner"]
+    return env, winner
+
+
+def eval_strats(strat1: BatchedStrategy, strat2: BatchedStrategy, num_games: int = 200, seed: int = 0,
+                device="cuda"):
+    """strat_eval.py:65-95: half of the games with strat1 moving first, half with strat2;
+    returns {"strat1_wins", "strat2_wins", "draws", "games"} in the reference's convention."""
+    half = num_games // 2
+    _, w_a = play_games(strat1, strat2, half, seed, device)
+    _, w_b = play_games(strat2, strat1, half, seed + 1, device)
+    s1 = int((w_a == 1).sum() + (w_b == 2).sum())
+    s2 = int((w_a == 2).sum() + (w_b == 1).sum())
+    draws = int((w_a == 0).sum() + (w_b == 0).sum())
+    return {"strat1_wins": s1, "strat2_wins": s2, "draws": draws, "games": 2 * half}

@@ -625,6 +625,32 @@ QTTT_HD void qeval_game(const State& s, uint32_t action, const Luts& L, State* n
     }
 }
 
+// Squares that carry at least one live (uncollapsed) spooky mark = union of Board.qstructs.
+QTTT_HD uint32_t live_squares(const State& s) {
+    const uint32_t C = classical(s);
+    uint32_t live = 0u;
+#pragma unroll
+    for (uint32_t m = 0; m < 9u; ++m) {
+        const uint32_t E = edge_dyn(s, m);
+        live |= (E & C) ? 0u : E;
+    }
+    return live;
+}
+
+// One element of GameState.to_vector() (mcts.py:67-85): an (18, 10) matrix; rows 0..8 one-hot
+// of board[row] (column 9 for "not classical"), rows 9..17: 1/sqrt(9) at [square, t] for every
+// move t that names the square (collapsed ones and the autofill entry included), and 1.0 in
+// column 9 for squares outside every entangled component.
+QTTT_HD float feature_element(const State& s, uint32_t live, uint32_t row, uint32_t col) {
+    if (row < 9u) {
+        const int b = board_value(plane0(s), plane1(s), plane2(s), plane3(s), (int)row);
+        return ((b < 0 ? 9 : b) == (int)col) ? 1.0f : 0.0f;
+    }
+    const uint32_t sq = row - 9u;
+    if (col == 9u) return (live >> sq & 1u) ? 0.0f : 1.0f;
+    return (col < n_moves(s) && (edge_dyn(s, col) >> sq & 1u)) ? (1.0f / 3.0f) : 0.0f;
+}
+
 // Number of plies behind a position: the autofill entry (s, s, 8) is not a ply (mcts.py:243).
 QTTT_HD uint32_t plies_of(const State& s) {
     const uint32_t nm = n_moves(s);

@@ -148,6 +148,41 @@ k_pack(qttt_state* __restrict__ state, const int8_t* __restrict__ classical_in,
         store_state(state, i, pack_game(classical_in, moves, nmoves, i));
 }
 
+// ------------------------------------------------------------------------------ features
+// GameState.to_vector for n games -> float[n][18][10].  720 B per game are written, so the
+// kernel is store-bound: a warp owns 32 consecutive games (23 KB of contiguous output) and
+// writes it as float4 vectors, lane-contiguous, fetching the owning game's state by shuffle.
+__global__ void __launch_bounds__(kThreads)
+k_features(const qttt_state* __restrict__ state, float* __restrict__ out, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * kThreads) >> 5;
+    for (int64_t base = warp0 * 32; base < n; base += n_warps * 32) {
+        const int64_t g = base + lane;
+        State s = empty_state();
+        if (g < n) s = load_state(state, g);
+        const uint32_t live = live_squares(s);
+        const int games_here = (int)((n - base) < 32 ? (n - base) : 32);
+        float4* dst = reinterpret_cast<float4*>(out + base * 180);
+        for (int q0 = 0; q0 < games_here * 45; q0 += 32) {     // warp-uniform trip count (shuffles inside)
+            const int q = q0 + lane;
+            const bool valid = q < games_here * 45;
+            const int owner = valid ? q / 45 : 0, e0 = (q - owner * 45) * 4;
+            State t;
+            t.x = __shfl_sync(0xFFFFFFFFu, s.x, owner); t.y = __shfl_sync(0xFFFFFFFFu, s.y, owner);
+            t.z = __shfl_sync(0xFFFFFFFFu, s.z, owner); t.w = __shfl_sync(0xFFFFFFFFu, s.w, owner);
+            const uint32_t lv = __shfl_sync(0xFFFFFFFFu, live, owner);
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t e = valid ? (uint32_t)(e0 + k) : 0u;
+                v[k] = feature_element(t, lv, e / 10u, e % 10u);
+            }
+            if (valid) dst[q] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ K3 qeval
 template <bool kSquares>
 __global__ void __launch_bounds__(kThreads)
@@ -390,6 +425,14 @@ int qttt_observe(const qttt_state* state, int8_t* classical, int8_t* moves, uint
     if (misaligned(state, 16) || misaligned(reward_p1, 4)) return QTTT_ERR_ALIGN;
     if (n == 0) return QTTT_OK;
     k_observe<<<grid_for(k_observe, n), kThreads, 0, (cudaStream_t)stream>>>(state, classical, moves, n_moves, q_p1, q_p2, turn, rounds, reward_p1, winner, mask_bool, n);
+    return check_launch();
+}
+
+int qttt_features(const qttt_state* state, float* features, int64_t n, void* stream) {
+    if (n == 0) return QTTT_OK;
+    if (!state || !features || n < 0) return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(features, 16)) return QTTT_ERR_ALIGN;
+    k_features<<<grid_for(k_features, n), kThreads, 0, (cudaStream_t)stream>>>(state, features, n);
     return check_launch();
 }
 

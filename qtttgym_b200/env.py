@@ -329,6 +329,44 @@ def observe_states(state, extras: bool = False):
     return out
 
 
+def to_vector(state):
+    """``GameState.to_vector`` (mcts.py:67-85) for packed states int32[N,4] -> float32[N,18,10]:
+    the feature matrix the reference's policy/value net consumes (nn.py:30-42).  The reference
+    computes it in float64; 1/sqrt(9) is rounded to float32 here (|diff| < 2e-8)."""
+    lib = _lib.lib()
+    n, dev = state.shape[0], state.device
+    out = torch.empty((n, 18, 10), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.qttt_features(state.data_ptr(), out.data_ptr(), n, _stream_ptr(dev)))
+    return out
+
+
+def render_text(classical, moves, n_moves) -> str:
+    """The 3x3-of-3x3 ASCII board of ``displayBoard`` (qtttgym/display.py:4-32) for ONE
+    position given as reference-shaped lists: spooky mark of move i in sub-cell i of both its
+    squares; a classical square shows its x / o pattern with the move index in the centre."""
+    cells = [[" "] * 9 for _ in range(9)]
+    for i in range(int(n_moves)):
+        a, b = int(moves[i][0]), int(moves[i][1])
+        cells[a][i] = str(i)
+        cells[b][i] = str(i)
+    for sq, owner in enumerate(classical):
+        owner = int(owner)
+        if owner >= 0:
+            mark = "x" if owner % 2 == 0 else "o"
+            for j in range(9):
+                cells[sq][j] = mark if j % 2 == owner % 2 else " "
+            cells[sq][4] = str(owner)
+    out = ""
+    for i in range(3):
+        out += "+---+---+---+\n"
+        for k in range(3):
+            for j in range(3):
+                out += "|" + "".join(cells[3 * i + j][3 * k:3 * k + 3])
+            out += "|\n"
+    return out + "+---+---+---+\n"
+
+
 def pack_states(classical, moves, n_moves, device="cuda"):
     """Reference-shaped positions -> packed states int32[N,4] (see qttt_pack)."""
     lib = _lib.lib()
@@ -391,7 +429,9 @@ class Env:
         return self._batched.action_mask()[0].cpu().numpy()
 
     def render(self):
-        print(self._observation())
+        """env.py:59-60 -> displayBoard (display.py:4-32)."""
+        o = self._batched.observation(extras=True)
+        print(render_text(o["classical"][0].tolist(), o["moves"][0].tolist(), int(o["n_moves"][0])))
 
     def _observation(self):
         o = self._batched.observation()
@@ -404,4 +444,5 @@ class Env:
         return float(self._batched.observation(extras=True)["reward_p1"][0].item())
 
 
-__all__ = ["BatchedEnv", "Env", "observe_states", "pack_states", "pack_actions", "unpack_result", "PAIRS"]
+__all__ = ["BatchedEnv", "Env", "observe_states", "pack_states", "pack_actions", "unpack_result",
+           "to_vector", "render_text", "PAIRS"]

@@ -109,6 +109,11 @@ class EmuGames:
                              _p(o["reward_p1"]), _p(o["winner"]), _p(o["mask_bool"]), C.c_int64(n))
         return o
 
+    def features(self):
+        out = np.empty((self.n, 18, 10), np.float32)
+        self.lib.emu_features(_p(self.state), _p(out), C.c_int64(self.n))
+        return out
+
     def load(self, classical, moves, n_moves):
         cl = np.ascontiguousarray(classical, np.int8)
         mv = np.ascontiguousarray(moves, np.int8)
@@ -207,6 +212,9 @@ class CudaGames:
         out["q_p1"], out["q_p2"] = out.pop("q_states_p1"), out.pop("q_states_p2")
         out["mask_bool"] = out.pop("action_mask").astype(np.uint8)
         return out
+
+    def features(self):
+        return self.Q.to_vector(self.env.state).cpu().numpy()
 
     def load(self, classical, moves, n_moves):
         self.env.load_positions(np.asarray(classical, np.int8), np.asarray(moves, np.int8),

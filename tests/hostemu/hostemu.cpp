@@ -88,6 +88,14 @@ int emu_observe(const State* state, int8_t* classical_out, int8_t* moves, uint8_
     return 0;
 }
 
+int emu_features(const State* state, float* out, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) {
+        const uint32_t live = live_squares(state[i]);
+        for (uint32_t e = 0; e < 180; ++e) out[180 * i + e] = feature_element(state[i], live, e / 10u, e % 10u);
+    }
+    return 0;
+}
+
 int emu_pack(State* state, const int8_t* classical_in, const int8_t* moves, const uint8_t* nmoves,
              int64_t n) {
     for (int64_t i = 0; i < n; ++i) state[i] = pack_game(classical_in, moves, nmoves, i);

@@ -375,3 +375,23 @@ def check_packed_step(backend, n_games=5000, seed=31):
         assert np.array_equal((res >> np.uint64(38)) & np.uint64(3), r["status"].astype(np.uint64)), where
         assert_same_obs(dut.observe(), ref.observe(), where)
         mask = r["mask"]
+
+
+def check_golden_features(backend):
+    """GameState.to_vector (mcts.py:67-85) recorded from the live reference; float32 vs the
+    reference's float64 within 1e-6."""
+    recs = load_golden("features_v1.json.gz")
+    n = len(recs)
+    classical = np.array([r["board"] for r in recs], np.int8)
+    moves = np.full((n, 9, 2), -1, np.int8)
+    n_moves = np.array([len(r["moves"]) for r in recs], np.uint8)
+    for i, r in enumerate(recs):
+        for m in r["moves"]:
+            moves[i, m[2]] = m[:2]
+    got = backend.games(n).load(classical, moves, n_moves).features().reshape(n, 180).astype(np.float64)
+    want = np.zeros((n, 180))
+    for i, r in enumerate(recs):
+        for idx, v in r["nonzero"]:
+            want[i, idx] = v
+    assert np.abs(got - want).max() <= 1e-6
+    assert ((got != 0) == (want != 0)).all()

@@ -27,7 +27,7 @@ def built_lib():
 def test_header_declares_the_expected_surface():
     assert _declared_symbols() == {
         "qttt_abi_version", "qttt_strerror", "qttt_reset", "qttt_step", "qttt_step_packed", "qttt_step_random",
-        "qttt_observe", "qttt_pack", "qttt_qeval_both", "qttt_rollout", "qttt_sweep"}
+        "qttt_observe", "qttt_features", "qttt_pack", "qttt_qeval_both", "qttt_rollout", "qttt_sweep"}
 
 
 def test_library_exports_every_declared_symbol(built_lib):

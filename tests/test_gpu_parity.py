@@ -266,3 +266,55 @@ def test_episode_cuda_graph(cuda):
         torch.cuda.synchronize()
         assert torch.equal(env.state, gen.state)
         assert torch.equal(env.done, gen.done) and torch.equal(env.mask, gen.mask)
+
+
+def test_golden_features(cuda):
+    S.check_golden_features(cuda)
+
+
+def test_features_ragged_and_large(cuda):
+    """to_vector on ragged sizes vs the host formula applied to observe() output."""
+    import torch
+    import qtttgym_b200 as Q
+    for n in (1, 33, 1000, 70_001):
+        env = Q.BatchedEnv(n, seed=n)
+        for _ in range(6):
+            env.step_random()
+        f = Q.to_vector(env.state).cpu().numpy()
+        o = {k: v.cpu().numpy() for k, v in env.observation(extras=True).items()}
+        want = np.zeros((n, 18, 10), np.float32)
+        idx = np.arange(n)
+        for sq in range(9):
+            col = np.where(o["classical"][:, sq] < 0, 9, o["classical"][:, sq])
+            want[idx, sq, col] = 1.0
+        live = np.zeros((n, 9), bool)
+        for t in range(9):
+            has = o["n_moves"] > t
+            a, b = o["moves"][:, t, 0], o["moves"][:, t, 1]
+            want[idx[has], 9 + a[has], t] = np.float32(1 / 3)
+            want[idx[has], 9 + b[has], t] = np.float32(1 / 3)
+            uncollapsed = has & (o["classical"][idx, np.maximum(a, 0)] < 0)
+            live[idx[uncollapsed], a[uncollapsed]] = True
+            live[idx[uncollapsed], b[uncollapsed]] = True
+        want[:, 9:, 9] = ~live
+        assert np.array_equal(f, want), n
+
+
+def test_arena_random_vs_random_matches_reference_population(cuda):
+    """strat_eval tally convention: random vs random reproduces the reference's win/draw rates."""
+    import qtttgym_b200 as Q
+    ref = load_golden("population_v1.json")
+    n = 200_000
+    _, winner = Q.play_games(Q.RandomStrategy(1), Q.RandomStrategy(2), n, seed=3)
+    w = np.bincount(winner.cpu().numpy(), minlength=3)
+    m = ref["games"]
+    for got, key in ((w[1], "x"), (w[2], "o"), (w[0], "draw")):
+        p, q = got / n, ref[key] / m
+        assert abs(p - q) < 5 * (q * (1 - q) * (1 / n + 1 / m)) ** 0.5, (key, p, q)
+
+
+def test_arena_rollout_player_beats_random(cuda):
+    import qtttgym_b200 as Q
+    res = Q.eval_strats(Q.RolloutStrategy(n_rollouts=24, seed=5), Q.RandomStrategy(7), num_games=4000, seed=9)
+    assert res["games"] == 4000 and res["strat1_wins"] + res["strat2_wins"] + res["draws"] == 4000
+    assert res["strat1_wins"] > 0.8 * 4000, res

@@ -60,3 +60,18 @@ def test_philox_coin(emu):
 
 def test_packed_step(emu):
     S.check_packed_step(emu)
+
+
+def test_golden_features(emu):
+    S.check_golden_features(emu)
+
+
+def test_render_text_matches_reference_display():
+    import qtttgym_b200 as Q
+    from helpers import load_golden
+    for r in load_golden("features_v1.json.gz"):
+        moves = [[-1, -1]] * 9
+        for m in r["moves"]:
+            moves[m[2]] = m[:2]
+        # displayBoard prints the string followed by print()'s own newline
+        assert Q.render_text(r["board"], moves, len(r["moves"])) + "\n" == r["display"]
