@@ -117,6 +117,23 @@ class ClockSampler:
                 "how": "NVML SM clock + clock-event reasons sampled every ~2 ms inside the timed region"}
 
 
+def bind_to_gpu_numa(torch_device):
+    """Pins this rank's CPU affinity to the cores NVML reports as local to its GPU, so that the
+    pinned host buffers of the e2e path are allocated on the GPU's own NUMA node (with 8 ranks
+    the PCIe copies otherwise cross the socket interconnect)."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(torch_device).uuid)
+        uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+        handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return sorted(os.sched_getaffinity(0))
+    except Exception as e:   # best effort
+        return f"unavailable ({e!r})"
+
+
 # ----------------------------------------------------------------------------- reference arm
 def run_reference(args):
     """The reference's own CPU implementation of the path on the host cores.  The reference is
@@ -191,6 +208,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     import qtttgym_b200 as Q
+    affinity = bind_to_gpu_numa(dev) if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -381,6 +399,9 @@ def run_b200(args):
                                          "env_steps_per_s": rsteps / (ms * 1e-3) * world, "ms": ms}
     if cpu_c:
         extra["cpu_c_oracle"] = cpu_c
+    if affinity is not None:
+        extra["rank0_cpu_affinity"] = (f"{len(affinity)} cores local to the GPU (NVML)"
+                                       if isinstance(affinity, list) else affinity)
     extra["population"] = {"x_wins": int(final_winner[1]), "o_wins": int(final_winner[2]),
                            "draws": int(final_winner[0]), "games": E}
 

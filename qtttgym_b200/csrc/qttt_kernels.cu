@@ -264,7 +264,8 @@ k_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, unsigned long long* __r
         bool active = g < game_hi;
         if (!__any_sync(0xFFFFFFFFu, active)) break;
         State s = empty_state();
-        uint32_t C = 0u;
+        uint32_t C = 0u, len = 0u;
+        const bool mine = active;
         games += active;
 #pragma unroll 1
         for (uint32_t ply = 0; ply < 9u; ++ply) {
@@ -273,17 +274,16 @@ k_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, unsigned long long* __r
                 const StepResult r = playout_ply(s, C, seed, (uint64_t)g, 0u, L);
                 C = r.classical;
                 co += r.collapsed;
-                const bool terminal = (any_line(s, C, L) != 0u) | (r.n >= 9u);   // mcts.py:52-65
-                if (terminal) {
-                    bool t2;
-                    const uint32_t w = finished_winner(s, L, t2);   // who has the earlier line
-                    xw += w == 1u; ow += w == 2u; dr += w == 0u;
-                    st += ply + 1u;
-                    h5 += ply == 4u; h6 += ply == 5u; h7 += ply == 6u; h8 += ply == 7u; h9 += ply == 8u;
-                    active = false;
-                }
+                len = ply + 1u;
+                active = !((any_line(s, C, L) != 0u) | (r.n >= 9u));          // mcts.py:52-65
             }
         }
+        // every lane's game is over: who has the earlier line (mcts.py:52-65), once, undiverged
+        bool t2;
+        const uint32_t w = finished_winner(s, L, t2);
+        xw += mine & (w == 1u); ow += mine & (w == 2u); dr += mine & (w == 0u);
+        st += len;
+        h5 += len == 5u; h6 += len == 6u; h7 += len == 7u; h8 += len == 8u; h9 += len == 9u;
     }
     uint32_t vals[11] = {xw, ow, dr, st, co, games, h5, h6, h7, h8, h9};
     const int slot[11] = {0, 1, 2, 3, 4, 5, 11, 12, 13, 14, 15};
