@@ -47,6 +47,16 @@ WORKLOAD = ("step API (K1): reset + 9 step launches per pass, random legal actio
             "(config 2 of BASELINE.json scaled to fill the GPU)")
 
 
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per k_step launch from the committed
+    `ncu --set full` capture (profiles/k_step_traffic.json, written by profiles/summarize.py)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k_step_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def measured_hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -244,7 +254,7 @@ def run_b200(args):
         coins[ply].copy_(info["coin"])
         accepted.append(int((info["status"] == 0).sum().item()))
     steps_per_pass = sum(accepted)
-    final_winner = torch.bincount(env.observation(extras=True)["winner"].long(), minlength=3)
+    final_winner = torch.bincount(env.winner().long(), minlength=3)
 
     # ---- value: inputs resident in HBM
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2 * PLIES)] for _ in range(K)]
@@ -270,7 +280,7 @@ def run_b200(args):
     total_steps = sum_over_ranks(float(steps_per_pass)) * K
     value = total_steps / (t_ms * 1e-3)
     # the state after the timed passes must be the state the trace generation ended in
-    w_check = torch.bincount(env.observation(extras=True)["winner"].long(), minlength=3)
+    w_check = torch.bincount(env.winner().long(), minlength=3)
     assert torch.equal(w_check, final_winner), "timed replay diverged from the generated trace"
 
     kdur_ms = [ev[k][2 * p].elapsed_time(ev[k][2 * p + 1]) for k in range(K) for p in range(PLIES)]
@@ -280,9 +290,28 @@ def run_b200(args):
     achieved = BYTES_PER_STEP * (steps_per_pass / PLIES) / (avg_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_step<QTTT_ACT_INDEX,false>", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": args.traffic_bytes, "algorithmic_bytes_per_launch": BYTES_PER_STEP * steps_per_pass / PLIES,
+                "traffic": (args.traffic_bytes if args.traffic_bytes is not None else
+                            (profiled_traffic() or {}).get("dram_bytes_per_launch")),
+                "traffic_source": (profiled_traffic() or {}).get("source"),
+                "algorithmic_bytes_per_launch": BYTES_PER_STEP * steps_per_pass / PLIES,
                 "avg_launch_ms": avg_launch_ms, "launch_ms_by_ply": per_ply_ms,
                 "bytes_per_env_step": BYTES_PER_STEP}
+
+    # ---- the same pass as ONE CUDA graph (BatchedEnv.capture_episode): no per-launch CPU work
+    graph_full = env.capture_episode(actions, coins)
+    for _ in range(W):
+        graph_full.replay()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    g0.record()
+    for _ in range(K):
+        graph_full.replay()
+    g1.record()
+    barrier()
+    graph_ms = max_over_ranks(g0.elapsed_time(g1))
+    launches += (K + W + 2) * (1 + PLIES)
+    value_graph = total_steps / (graph_ms * 1e-3)
+    assert torch.equal(torch.bincount(env.winner().long(), minlength=3), final_winner)
 
     # ---- e2e: host buffers through the public API, copies inside the timed region
     h_act = actions.cpu().pin_memory()
@@ -407,8 +436,8 @@ def run_b200(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": value_graph, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": graph_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "envs_per_gpu": E, "global_envs": E * world, "plies_per_pass": PLIES,
@@ -416,6 +445,9 @@ def run_b200(args):
                        "l2": "inputs exceed L2: 16 B x E state + 2 B x E actions/coins + 13 B x E outputs per launch "
                              f"= {31 * E / 1e6:.0f} MB vs 126 MB L2" if 31 * E > 126e6 else "inputs fit in L2 (small E)",
                        "parallelism": f"dp{world} (independent games per rank, no data-path collective)"},
+            "value_eager": {"value": value, "ms_per_step": t_ms / K,
+                            "note": "the same pass issued as 10 separate BatchedEnv.reset/step calls per pass "
+                                    "(the loop the per-launch roofline events are recorded in)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks, "extra": extra,
         }

@@ -61,6 +61,20 @@ def launches(tag):
             f.write(f"| `{k[:90]}` | {v[0]} | {v[1] / 1e6:.3f} | {100 * v[1] / tot:.1f}% |\n")
         ours = sum(v[1] for k, v in agg.items() if "qttt::" in k)
         f.write(f"\nqttt:: kernels: {100 * ours / tot:.1f}% of the captured GPU time.\n")
+        # the timed region of `value` is a sequence of passes: k_reset followed by 9 x k_step<0,0,1>
+        names = [r["Kernel Name"].split("(")[0] for r in rows]
+        durs = [float(r["Metric Value"]) for r in rows]
+        passes = []
+        for i, nm in enumerate(names):
+            if nm.endswith("k_reset") and i + 9 < len(names) and all("k_step<0, 0, 1>" in x for x in names[i + 1:i + 10]):
+                passes.append((durs[i], durs[i + 1:i + 10]))
+        if passes:
+            reset = sum(p[0] for p in passes) / len(passes)
+            steps = [sum(p[1][k] for p in passes) / len(passes) for k in range(9)]
+            f.write(f"\n## One pass of the step API (the bench step), mean of {len(passes)} captured passes\n\n"
+                    f"k_reset {reset / 1e3:.1f} us + 9 x k_step = {sum(steps) / 1e3:.1f} us "
+                    f"(by ply: {', '.join(f'{x / 1e3:.0f}' for x in steps)} us).  "
+                    f"k_step share of the pass: {100 * sum(steps) / (reset + sum(steps)):.1f}%.\n")
 
 
 def full(tag, which):
@@ -70,6 +84,15 @@ def full(tag, which):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
+    if which == "step" and "dram__bytes_read.sum" in hdr:
+        import json
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        per = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in data]
+        with open(os.path.join(OUT, "k_step_traffic.json"), "w") as jf:
+            json.dump({"dram_bytes_per_launch": sum(per) / len(per),
+                       "source": f"profiles/{tag}_step_ncu_full.md (dram__bytes_read.sum + dram__bytes_write.sum, "
+                                 f"mean of {len(per)} launches of 2^24 envs)"}, jf)
     with open(os.path.join(OUT, f"{tag}_{which}_ncu_full.md"), "w") as f:
         f.write(f"# ncu --set full, kernel k_{which} ({tag})\n\nOne column per captured launch.\n\n| metric | unit | "
                 + " | ".join(f"launch {i}" for i in range(len(data))) + " |\n|---|---|" + "---:|" * len(data) + "\n")

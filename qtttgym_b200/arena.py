@@ -104,7 +104,7 @@ def play_games(strat_x: BatchedStrategy, strat_o: BatchedStrategy, n_games: int,
         strat_o.sync(actions)
         if bool(env.done.all()):
             break
-    winner = env.observation(extras=True)["winner"]
+    winner = env.winner()
     return env, winner
 
 

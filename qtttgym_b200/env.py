@@ -238,6 +238,15 @@ class BatchedEnv:
         ``winner`` (0 none, 1 X, 2 O) and ``action_mask`` bool[N,36]."""
         return observe_states(self.state, extras=extras)
 
+    def winner(self):
+        """mcts.py:52-65 / strat_eval.py:21-32 per env: uint8[N], 0 none or draw, 1 X, 2 O."""
+        out = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.qttt_observe(self.state.data_ptr(), None, None, None, None, None, None,
+                                             None, None, out.data_ptr(), None, self.num_envs,
+                                             _stream_ptr(self.device)))
+        return out
+
     def action_mask(self):
         """mcts.py:87-91 for every env: bool[N,36]."""
         bits = torch.arange(36, device=self.device, dtype=torch.int64)
