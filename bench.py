@@ -274,7 +274,6 @@ def run_b200(args):
                 ev[it - W][2 * ply + 1].record()
     end.record()
     barrier()
-    clocks = sampler.stop() if sampler else {}
     t_ms = max_over_ranks(start.elapsed_time(end))
     launches += K * (1 + PLIES)
     total_steps = sum_over_ranks(float(steps_per_pass)) * K
@@ -308,6 +307,7 @@ def run_b200(args):
         graph_full.replay()
     g1.record()
     barrier()
+    clocks = sampler.stop() if sampler else {}      # sampled over the eager and the graph timed regions
     graph_ms = max_over_ranks(g0.elapsed_time(g1))
     launches += (K + W + 2) * (1 + PLIES)
     value_graph = total_steps / (graph_ms * 1e-3)
@@ -426,6 +426,17 @@ def run_b200(args):
     rsteps = int(box["r"][2].item())
     extra["config4_rollout_1024x256"] = {"playouts_per_s": 1024 * 256 / (ms * 1e-3) * world,
                                          "env_steps_per_s": rsteps / (ms * 1e-3) * world, "ms": ms}
+    # a9 observation decode (env.py:68-85 + extras) and the to_vector feature encoder
+    ms = timed(lambda: env.observation(extras=True), 5)
+    launches += 6
+    extra["observe_all_outputs"] = {"ms": ms, "envs": E, "bytes_per_env": 16 + 90,
+                                    "gb_per_s": E * (16 + 90) / (ms * 1e-3) / 1e9,
+                                    "note": "qttt_observe, every output (classical, moves, n_moves, q lists, turn, "
+                                            "rounds, reward_p1, winner, bool mask); includes torch.empty of the outputs"}
+    ms = timed(lambda: Q.to_vector(qenv.state), 20)
+    launches += 21
+    extra["to_vector_1M_states"] = {"ms": ms, "states_per_s": nb / (ms * 1e-3) * world,
+                                    "gb_per_s": nb * 736 / (ms * 1e-3) / 1e9}
     if cpu_c:
         extra["cpu_c_oracle"] = cpu_c
     if affinity is not None:

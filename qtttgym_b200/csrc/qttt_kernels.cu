@@ -125,6 +125,25 @@ k_step_packed(qttt_state* __restrict__ state, const uint8_t* __restrict__ action
 }
 
 // ------------------------------------------------------------------------------ observe / pack
+// Copies one block's worth of a staged output array (kBytesPerGame bytes per game, `valid`
+// games) from shared memory to its place in the global array, as 16-byte vectors when the
+// destination allows it.
+template <int kBytesPerGame>
+__device__ __forceinline__ void copy_out(const uint8_t* sm, void* dst, int64_t block_start, int valid) {
+    if (!dst) return;
+    uint8_t* g = static_cast<uint8_t*>(dst) + block_start * kBytesPerGame;
+    if (valid == kThreads && (reinterpret_cast<uintptr_t>(g) & 15u) == 0u) {
+        const uint4* s16 = reinterpret_cast<const uint4*>(sm);
+        uint4* g16 = reinterpret_cast<uint4*>(g);
+        for (int v = threadIdx.x; v < kThreads * kBytesPerGame / 16; v += kThreads) g16[v] = s16[v];
+    } else {
+        for (int v = threadIdx.x; v < valid * kBytesPerGame; v += kThreads) g[v] = sm[v];
+    }
+}
+
+// Env._observation & co. for n games.  Every output is a few BYTES per game at an odd stride
+// (9, 18, 10, 8, 36 ...), so each block of 256 games is decoded into shared memory first and
+// then written out with coalesced 16-byte stores.
 __global__ void __launch_bounds__(kThreads)
 k_observe(const qttt_state* __restrict__ state, int8_t* __restrict__ classical_out,
           int8_t* __restrict__ moves, uint8_t* __restrict__ nmoves, int8_t* __restrict__ q1,
@@ -132,12 +151,42 @@ k_observe(const qttt_state* __restrict__ state, int8_t* __restrict__ classical_o
           float* __restrict__ reward_p1, uint8_t* __restrict__ winner,
           uint8_t* __restrict__ mask_bool, int64_t n) {
     __shared__ __align__(16) uint8_t smem[kLutStepBytes];
+    __shared__ __align__(16) uint8_t st_classical[kThreads * 9];
+    __shared__ __align__(16) uint8_t st_moves[kThreads * 18];
+    __shared__ __align__(16) uint8_t st_q1[kThreads * 10];
+    __shared__ __align__(16) uint8_t st_q2[kThreads * 8];
+    __shared__ __align__(16) uint8_t st_mask[kThreads * 36];
+    __shared__ __align__(16) uint8_t st_rounds[kThreads * 2];
+    __shared__ __align__(16) float   st_reward[kThreads];
+    __shared__ __align__(16) uint8_t st_n[kThreads], st_turn[kThreads], st_winner[kThreads];
     stage_luts(smem, kLutStepBytes);
     const Luts L = luts_from_image(smem);
     const int64_t stride = (int64_t)gridDim.x * kThreads;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
-        observe_game(load_state(state, i), L, classical_out, moves, nmoves, q1, q2, turn, rounds,
-                     reward_p1, winner, mask_bool, i);
+    for (int64_t block_start = (int64_t)blockIdx.x * kThreads; block_start < n; block_start += stride) {
+        const int valid = (int)((n - block_start) < kThreads ? (n - block_start) : kThreads);
+        const int t = threadIdx.x;
+        if (t < valid)
+            observe_game(load_state(state, block_start + t), L,
+                         classical_out ? reinterpret_cast<int8_t*>(st_classical) : nullptr,
+                         moves ? reinterpret_cast<int8_t*>(st_moves) : nullptr, nmoves ? st_n : nullptr,
+                         q1 ? reinterpret_cast<int8_t*>(st_q1) : nullptr,
+                         q2 ? reinterpret_cast<int8_t*>(st_q2) : nullptr, turn ? st_turn : nullptr,
+                         rounds ? reinterpret_cast<int8_t*>(st_rounds) : nullptr,
+                         reward_p1 ? st_reward : nullptr, winner ? st_winner : nullptr,
+                         mask_bool ? st_mask : nullptr, t);
+        __syncthreads();
+        copy_out<9>(st_classical, classical_out, block_start, valid);
+        copy_out<18>(st_moves, moves, block_start, valid);
+        copy_out<1>(st_n, nmoves, block_start, valid);
+        copy_out<10>(st_q1, q1, block_start, valid);
+        copy_out<8>(st_q2, q2, block_start, valid);
+        copy_out<1>(st_turn, turn, block_start, valid);
+        copy_out<2>(st_rounds, rounds, block_start, valid);
+        copy_out<4>(reinterpret_cast<const uint8_t*>(st_reward), reward_p1, block_start, valid);
+        copy_out<1>(st_winner, winner, block_start, valid);
+        copy_out<36>(st_mask, mask_bool, block_start, valid);
+        __syncthreads();
+    }
 }
 
 __global__ void __launch_bounds__(kThreads)
