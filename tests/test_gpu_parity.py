@@ -318,3 +318,23 @@ def test_arena_rollout_player_beats_random(cuda):
     res = Q.eval_strats(Q.RolloutStrategy(n_rollouts=24, seed=5), Q.RandomStrategy(7), num_games=4000, seed=9)
     assert res["games"] == 4000 and res["strat1_wins"] + res["strat2_wins"] + res["draws"] == 4000
     assert res["strat1_wins"] > 0.8 * 4000, res
+
+
+def test_config5_full_size_sweep_properties(cuda):
+    """config 5 at BASELINE.json's full size (1.25e8 games, ~1.04e9 env-steps): size-independent
+    properties -- tallies partition the games, the length histogram accounts for every game and
+    every step, an 8-way shard split adds up bit-exactly (the multi-GPU invariant), and the
+    rates match the reference's population."""
+    import qtttgym_b200 as Q
+    g, seed = 125_000_000, 20261018
+    full = Q.selfplay_sweep(0, g, seed).cpu().numpy()
+    assert full[0] + full[1] + full[2] == g == full[5]
+    assert full[6:].sum() == g and (full[6:] * np.arange(10)).sum() == full[3]
+    assert full[6:11].sum() == 0                      # no game ends before its 5th ply
+    assert 1.0e9 < full[3] < 1.1e9
+    parts = sum(Q.selfplay_sweep(*Q.shard_range(g, r, 8), seed).cpu().numpy() for r in range(8))
+    assert parts.tolist() == full.tolist()
+    ref = load_golden("population_v1.json")
+    for k, key in enumerate(("x", "o", "draw")):
+        q = ref[key] / ref["games"]
+        assert abs(full[k] / g - q) < 5 * (q * (1 - q) / ref["games"]) ** 0.5
