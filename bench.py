@@ -426,6 +426,22 @@ def run_b200(args):
     rsteps = int(box["r"][2].item())
     extra["config4_rollout_1024x256"] = {"playouts_per_s": 1024 * 256 / (ms * 1e-3) * world,
                                          "env_steps_per_s": rsteps / (ms * 1e-3) * world, "ms": ms}
+    # MCTS search around the leaf evaluator (next row #1): 1024 mid-game roots, the reference's
+    # default num_simulations=10, 500 rollouts per root; and the config-4 shape (256 playouts per leaf)
+    for name, n_roll, n_sim in (("mcts_1024_roots_500x10", 500, 10), ("mcts_1024_roots_100x256", 100, 256)):
+        mc = Q.BatchedMCTS(rollouts=n_roll, num_simulations=n_sim, seed=seed, root_base=rank * 1024, device=dev)
+
+        def search():
+            mc.reset(roots, total_rollouts=n_roll)
+            mc.contemplate(n_roll)
+        ms = timed(search, 3)
+        launches += 4 * 2
+        assert int(mc.errors().max().item()) == 0
+        extra[name] = {"ms": ms, "rollouts_per_s": 1024 * n_roll / (ms * 1e-3) * world,
+                       "playouts_per_s": 1024 * n_roll * n_sim / (ms * 1e-3) * world,
+                       "nodes_per_tree_mean": float(mc.node_counts().float().mean().item())}
+        del mc
+
     # a9 observation decode (env.py:68-85 + extras) and the to_vector feature encoder
     ms = timed(lambda: env.observation(extras=True), 5)
     launches += 6

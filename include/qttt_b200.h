@@ -158,6 +158,33 @@ QTTT_API int qttt_qeval_both(const qttt_state* state, const uint8_t* action, qtt
 QTTT_API int qttt_rollout(const qttt_state* roots, int64_t n_roots, int32_t n_rollouts, uint64_t seed,
                  int32_t* tallies, float* value, int64_t* steps_total, void* stream);
 
+/* ---- MCTS search around the leaf evaluator (mcts.py:132-337), one tree per root ------------
+ * The caller provides the node pool: n_roots * capacity nodes of qttt_mcts_node_bytes() bytes
+ * (16-byte aligned) and meta int32[n_roots][8].  A search of R rollouts needs at most
+ * 1 + 2 * R nodes (+ 2 per sync); if the pool runs out meta[r][3] gets bit 0 set and the tree
+ * stops growing.  Random choices follow the keyed Philox stream of oracle/mcts_oracle.py
+ * (pinned to the unmodified reference MCTS), so the statistics are bit-identical to the
+ * reference's for the same stream.  root_base + n_roots <= 2^20, num_simulations <= 4096. */
+QTTT_API int qttt_mcts_node_bytes(void);
+/* MCTS.reset (mcts.py:139-164) for every root. */
+QTTT_API int qttt_mcts_init(void* pool, int64_t capacity, int32_t* meta, const qttt_state* roots,
+                            int64_t n_roots, void* stream);
+/* n_rollouts x MCTS._rollout (mcts.py:166-173): PUCT select (269-285), expansion with both
+ * collapse outcomes (210-267), num_simulations random playouts of the leaf (185-208),
+ * backpropagation (175-183).  c_puct = 1.0 in the reference (mcts.py:134). */
+QTTT_API int qttt_mcts_run(void* pool, int64_t capacity, int32_t* meta, int32_t n_rollouts,
+                           int32_t num_simulations, double c_puct, uint64_t seed, uint64_t root_base,
+                           int64_t n_roots, void* stream);
+/* root.N / root.Q / root.Ntot and MCTS.choose (mcts.py:308-315): n_visits int32[n][36],
+ * q_values double[n][36], n_total int32[n], choose uint8[n]; any may be NULL. */
+QTTT_API int qttt_mcts_stats(const void* pool, int64_t capacity, const int32_t* meta,
+                             int32_t* n_visits, double* q_values, int32_t* n_total, uint8_t* choose,
+                             int64_t n_roots, void* stream);
+/* MCTS.sync (mcts.py:317-337): the root moves to the child of action[r] whose position is
+ * now[r] (expanding it if needed); meta[r][3] bit 1 is set when there is no such child. */
+QTTT_API int qttt_mcts_sync(void* pool, int64_t capacity, int32_t* meta, const uint8_t* action,
+                            const qttt_state* now, int64_t n_roots, void* stream);
+
 /* Random self-play sweep (strat_eval.py:66-94 tally convention): plays games with global
  * ids [game_lo, game_hi) from the empty board to termination with the random policy
  * (domain 0), entirely in registers.  stats int64[16] is ADDED to:

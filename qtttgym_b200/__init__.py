@@ -12,6 +12,7 @@ from .arena import BatchedStrategy, RandomStrategy, RolloutStrategy, eval_strats
 from .actions import NUM_ACTIONS, PAIRS, ind2move, move2ind
 from .env import (BatchedEnv, Env, observe_states, pack_actions, pack_states, render_text, to_vector,
                   unpack_result)
+from .mcts import BatchedMCTS
 from .qeval import QEvalB200, qeval_both, square_probabilities
 from .rollout import STAT_NAMES, rollout_eval, selfplay_sweep, shard_range, sharded_sweep
 
@@ -19,7 +20,7 @@ __all__ = [
     "NUM_ACTIONS", "PAIRS", "ind2move", "move2ind",
     "BatchedEnv", "Env", "observe_states", "pack_states", "pack_actions", "unpack_result",
     "to_vector", "render_text",
-    "QEvalB200", "qeval_both", "square_probabilities",
+    "BatchedMCTS", "QEvalB200", "qeval_both", "square_probabilities",
     "BatchedStrategy", "RandomStrategy", "RolloutStrategy", "eval_strats", "play_games",
     "STAT_NAMES", "rollout_eval", "selfplay_sweep", "shard_range", "sharded_sweep",
 ]

@@ -27,6 +27,11 @@ _SIGNATURES = {
     "qttt_pack": ([_vp, _vp, _vp, _vp, _i64, _vp], _int),
     "qttt_qeval_both": ([_vp] * 10 + [_i64, _vp], _int),
     "qttt_rollout": ([_vp, _i64, _i32, _u64, _vp, _vp, _vp, _vp], _int),
+    "qttt_mcts_node_bytes": ([], _int),
+    "qttt_mcts_init": ([_vp, _i64, _vp, _vp, _i64, _vp], _int),
+    "qttt_mcts_run": ([_vp, _i64, _vp, _i32, _i32, C.c_double, _u64, _u64, _i64, _vp], _int),
+    "qttt_mcts_stats": ([_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp], _int),
+    "qttt_mcts_sync": ([_vp, _i64, _vp, _vp, _vp, _i64, _vp], _int),
     "qttt_sweep": ([_i64, _i64, _u64, _vp, _vp], _int),
 }
 

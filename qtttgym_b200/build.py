@@ -9,7 +9,7 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 SOURCES = [os.path.join(CSRC, "qttt_kernels.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, "qttt_core.cuh"),
+DEPS = SOURCES + [os.path.join(CSRC, "qttt_core.cuh"), os.path.join(CSRC, "qttt_mcts.cuh"),
                   os.path.join(os.path.dirname(CSRC), "..", "include", "qttt_b200.h")]
 LIB = os.path.join(CSRC, "libqttt_b200.so")
 

@@ -9,6 +9,7 @@
 
 #include "../../include/qttt_b200.h"
 #include "qttt_core.cuh"
+#include "qttt_mcts.cuh"
 
 namespace qttt {
 
@@ -345,6 +346,86 @@ k_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, unsigned long long* __r
     if (threadIdx.x < 16 && sh[threadIdx.x]) atomicAdd(&stats[threadIdx.x], sh[threadIdx.x]);
 }
 
+// ------------------------------------------------------------------------------ MCTS
+__global__ void __launch_bounds__(kThreads)
+k_mcts_init(MctsNode* __restrict__ pool, int64_t capacity, int32_t* __restrict__ meta,
+            const qttt_state* __restrict__ roots, int64_t n_roots) {
+    __shared__ __align__(16) uint8_t smem[kLutStepBytes];
+    stage_luts(smem, kLutStepBytes);
+    const Luts L = luts_from_image(smem);
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x; r < n_roots; r += stride)
+        mcts_init_root(pool + r * capacity, meta + r * kMetaStride, load_state(roots, r), L);
+}
+
+// One block per root.  A rollout is: thread 0 walks the tree (PUCT select, expanding one
+// (node, action) when needed), all threads play the leaf's num_simulations playouts in
+// parallel, a block reduction gives r_tot, thread 0 backs the value up.  Trees of different
+// roots advance independently in different blocks.
+__global__ void __launch_bounds__(kThreads)
+k_mcts_run(MctsNode* __restrict__ pool, int64_t capacity, int32_t* __restrict__ meta,
+           int32_t n_rollouts, int32_t num_sims, double c_puct, uint64_t seed, uint64_t root_base) {
+    __shared__ __align__(16) uint8_t smem[kLutPolicyBytes];
+    __shared__ int sh_path_node[12], sh_path_act[12], sh_depth, sh_leaf, sh_rtot;
+    stage_luts(smem, kLutPolicyBytes);
+    const Luts L = luts_from_image(smem);
+    const int64_t root = blockIdx.x;
+    MctsNode* tree = pool + root * capacity;
+    int32_t* m = meta + root * kMetaStride;
+    const uint64_t root_id = (root_base + (uint64_t)root) << 32;
+    const int first = m[kMetaRollouts];
+    for (int it = 0; it < n_rollouts; ++it) {
+        const uint64_t base = root_id + (uint64_t)(uint32_t)(first + it);
+        if (threadIdx.x == 0) {
+            int depth;
+            sh_leaf = mcts_select(tree, m, capacity, seed, base, c_puct, L, sh_path_node, sh_path_act, depth);
+            sh_depth = depth;
+            sh_rtot = 0;
+        }
+        __syncthreads();
+        const MctsNode& leaf = tree[sh_leaf];
+        int r = 0;
+        for (int sim = threadIdx.x; sim < num_sims; sim += blockDim.x)
+            r += mcts_sim_reward(leaf, seed, base, (uint32_t)sim, L);
+        r = __reduce_add_sync(0xFFFFFFFFu, r);
+        if ((threadIdx.x & 31) == 0 && r) atomicAdd(&sh_rtot, r);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (!tree[sh_leaf].terminal) tree[sh_leaf].has_p = 1;             // mcts.py:189-191
+            mcts_backprop(tree, sh_path_node, sh_path_act, sh_depth, sh_rtot, num_sims);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) m[kMetaRollouts] = first + n_rollouts;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_mcts_stats(const MctsNode* __restrict__ pool, int64_t capacity, const int32_t* __restrict__ meta,
+             int32_t* __restrict__ n_out, double* __restrict__ q_out, int32_t* __restrict__ ntot_out,
+             uint8_t* __restrict__ choose_out, int64_t n_roots) {
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x; r < n_roots; r += stride) {
+        const MctsNode& root = pool[r * capacity + meta[r * kMetaStride + kMetaRoot]];
+        for (int a = 0; a < 36; ++a) {
+            if (n_out) n_out[36 * r + a] = (int32_t)root.n[a];
+            if (q_out) q_out[36 * r + a] = root.n[a] ? d_div(root.w[a], (double)root.n[a]) : 0.0;
+        }
+        if (ntot_out) ntot_out[r] = (int32_t)root.ntot;
+        if (choose_out) choose_out[r] = (uint8_t)mcts_choose(root);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_mcts_sync(MctsNode* __restrict__ pool, int64_t capacity, int32_t* __restrict__ meta,
+            const uint8_t* __restrict__ action, const qttt_state* __restrict__ now, int64_t n_roots) {
+    __shared__ __align__(16) uint8_t smem[kLutStepBytes];
+    stage_luts(smem, kLutStepBytes);
+    const Luts L = luts_from_image(smem);
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x; r < n_roots; r += stride)
+        mcts_sync(pool + r * capacity, meta + r * kMetaStride, capacity, (int)action[r], load_state(now, r), L);
+}
+
 // ------------------------------------------------------------------------------ launch helpers
 // Persistent grid: exactly as many blocks as are resident at once (SM count x occupancy of
 // this kernel), so the grid-stride loops finish in one balanced wave.
@@ -520,6 +601,54 @@ int qttt_rollout(const qttt_state* roots, int64_t n_roots, int32_t n_rollouts, u
     if (n_roots == 0) return QTTT_OK;
     k_rollout<<<(int)n_roots, kThreads, 0, (cudaStream_t)stream>>>(
         roots, n_rollouts, seed, tallies, value, reinterpret_cast<unsigned long long*>(steps_total));
+    return check_launch();
+}
+
+int qttt_mcts_node_bytes(void) { return (int)sizeof(MctsNode); }
+
+int qttt_mcts_init(void* pool, int64_t capacity, int32_t* meta, const qttt_state* roots,
+                   int64_t n_roots, void* stream) {
+    if (n_roots == 0) return QTTT_OK;
+    if (!pool || !meta || !roots || capacity < 1 || n_roots < 0) return QTTT_ERR_ARG;
+    if (misaligned(pool, 16) || misaligned(roots, 16) || misaligned(meta, 4)) return QTTT_ERR_ALIGN;
+    k_mcts_init<<<grid_for(k_mcts_init, n_roots), kThreads, 0, (cudaStream_t)stream>>>(
+        static_cast<MctsNode*>(pool), capacity, meta, roots, n_roots);
+    return check_launch();
+}
+
+int qttt_mcts_run(void* pool, int64_t capacity, int32_t* meta, int32_t n_rollouts,
+                  int32_t num_simulations, double c_puct, uint64_t seed, uint64_t root_base,
+                  int64_t n_roots, void* stream) {
+    if (n_roots == 0 || n_rollouts == 0) return QTTT_OK;
+    if (!pool || !meta || capacity < 1 || n_roots < 0 || n_rollouts < 0 || num_simulations < 1 ||
+        num_simulations > (int32_t)kMaxSims || n_roots > 0x7FFFFFFF || root_base + (uint64_t)n_roots > (1ull << 20))
+        return QTTT_ERR_ARG;
+    if (misaligned(pool, 16) || misaligned(meta, 4)) return QTTT_ERR_ALIGN;
+    int threads = ((num_simulations + 31) / 32) * 32;
+    threads = threads > kThreads ? kThreads : threads;
+    k_mcts_run<<<(int)n_roots, threads, 0, (cudaStream_t)stream>>>(
+        static_cast<MctsNode*>(pool), capacity, meta, n_rollouts, num_simulations, c_puct, seed, root_base);
+    return check_launch();
+}
+
+int qttt_mcts_stats(const void* pool, int64_t capacity, const int32_t* meta, int32_t* n_visits,
+                    double* q_values, int32_t* n_total, uint8_t* choose, int64_t n_roots, void* stream) {
+    if (n_roots == 0) return QTTT_OK;
+    if (!pool || !meta || capacity < 1 || n_roots < 0) return QTTT_ERR_ARG;
+    if (misaligned(pool, 16) || misaligned(q_values, 8) || misaligned(n_visits, 4) || misaligned(n_total, 4))
+        return QTTT_ERR_ALIGN;
+    k_mcts_stats<<<grid_for(k_mcts_stats, n_roots), kThreads, 0, (cudaStream_t)stream>>>(
+        static_cast<const MctsNode*>(pool), capacity, meta, n_visits, q_values, n_total, choose, n_roots);
+    return check_launch();
+}
+
+int qttt_mcts_sync(void* pool, int64_t capacity, int32_t* meta, const uint8_t* action,
+                   const qttt_state* now, int64_t n_roots, void* stream) {
+    if (n_roots == 0) return QTTT_OK;
+    if (!pool || !meta || !action || !now || capacity < 1 || n_roots < 0) return QTTT_ERR_ARG;
+    if (misaligned(pool, 16) || misaligned(now, 16)) return QTTT_ERR_ALIGN;
+    k_mcts_sync<<<grid_for(k_mcts_sync, n_roots), kThreads, 0, (cudaStream_t)stream>>>(
+        static_cast<MctsNode*>(pool), capacity, meta, action, now, n_roots);
     return check_launch();
 }
 

@@ -51,6 +51,40 @@ class EmuBackend:
         self.lib().emu_sweep(C.c_int64(lo), C.c_int64(hi), C.c_uint64(seed), _p(stats))
         return stats
 
+    def mcts(self, states, num_simulations, seed, root_base, budget):
+        return EmuMCTS(self.lib(), states, num_simulations, seed, root_base, budget)
+
+
+class EmuMCTS:
+    def __init__(self, lib, states, num_simulations, seed, root_base, budget):
+        self.lib, self.sims, self.seed, self.base = lib, num_simulations, seed, root_base
+        self.states = np.ascontiguousarray(states, np.uint32).reshape(-1, 4)
+        self.n = self.states.shape[0]
+        self.cap = 1 + 2 * budget + 18
+        self.pool = np.zeros(self.n * self.cap * lib.emu_mcts_node_bytes(), np.uint8)
+        self.meta = np.zeros((self.n, 8), np.int32)
+        lib.emu_mcts_init(_p(self.pool), C.c_int64(self.cap), _p(self.meta), _p(self.states), C.c_int64(self.n))
+
+    def contemplate(self, n_rollouts):
+        self.lib.emu_mcts_run(_p(self.pool), C.c_int64(self.cap), _p(self.meta), C.c_int32(n_rollouts),
+                              C.c_int32(self.sims), C.c_double(1.0), C.c_uint64(self.seed),
+                              C.c_uint64(self.base), C.c_int64(self.n))
+
+    def stats(self):
+        n = np.zeros((self.n, 36), np.int32); q = np.zeros((self.n, 36), np.float64)
+        ntot = np.zeros(self.n, np.int32); ch = np.zeros(self.n, np.uint8)
+        self.lib.emu_mcts_stats(_p(self.pool), C.c_int64(self.cap), _p(self.meta), _p(n), _p(q), _p(ntot),
+                                _p(ch), C.c_int64(self.n))
+        return n, q, ntot, ch
+
+    def sync(self, actions, states):
+        ac = np.ascontiguousarray(actions, np.uint8)
+        st = np.ascontiguousarray(states, np.uint32).reshape(-1, 4)
+        self.lib.emu_mcts_sync(_p(self.pool), C.c_int64(self.cap), _p(self.meta), _p(ac), _p(st), C.c_int64(self.n))
+
+    def errors(self):
+        return self.meta[:, 3].copy()
+
 
 class EmuGames:
     def __init__(self, n):
@@ -159,6 +193,34 @@ class CudaBackend:
     def sweep(self, lo, hi, seed):
         import qtttgym_b200 as Q
         return Q.selfplay_sweep(lo, hi, seed).cpu().numpy()
+
+    def mcts(self, states, num_simulations, seed, root_base, budget):
+        return CudaMCTS(states, num_simulations, seed, root_base, budget)
+
+
+class CudaMCTS:
+    def __init__(self, states, num_simulations, seed, root_base, budget):
+        import torch
+        import qtttgym_b200 as Q
+        self.torch = torch
+        st = torch.from_numpy(np.ascontiguousarray(states).view(np.int32).reshape(-1, 4)).cuda()
+        self.m = Q.BatchedMCTS(rollouts=budget, num_simulations=num_simulations, seed=seed, root_base=root_base)
+        self.m.reset(st, total_rollouts=budget)
+
+    def contemplate(self, n_rollouts):
+        self.m.contemplate(n_rollouts)
+
+    def stats(self):
+        n, q, ntot, ch = self.m.root_stats()
+        return n.cpu().numpy(), q.cpu().numpy(), ntot.cpu().numpy(), ch.cpu().numpy()
+
+    def sync(self, actions, states):
+        t = self.torch
+        self.m.sync(t.from_numpy(np.ascontiguousarray(actions, np.uint8)).cuda(),
+                    t.from_numpy(np.ascontiguousarray(states).view(np.int32).reshape(-1, 4)).cuda())
+
+    def errors(self):
+        return self.m.errors().cpu().numpy()
 
 
 class CudaGames:

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include "../../qtttgym_b200/csrc/qttt_core.cuh"
+#include "../../qtttgym_b200/csrc/qttt_mcts.cuh"
 
 using namespace qttt;
 
@@ -140,6 +141,58 @@ int emu_sweep(int64_t lo, int64_t hi, uint64_t seed, int64_t* stats) {
         stats[w == 1u ? 0 : (w == 2u ? 1 : 2)]++;
         stats[3] += steps; stats[4] += cols; stats[5]++; stats[6 + steps]++;
     }
+    return 0;
+}
+
+int emu_mcts_node_bytes(void) { return (int)sizeof(MctsNode); }
+
+int emu_mcts_init(MctsNode* pool, int64_t capacity, int32_t* meta, const State* roots, int64_t n_roots) {
+    const Luts L = luts();
+    for (int64_t r = 0; r < n_roots; ++r) mcts_init_root(pool + r * capacity, meta + r * kMetaStride, roots[r], L);
+    return 0;
+}
+
+int emu_mcts_run(MctsNode* pool, int64_t capacity, int32_t* meta, int32_t n_rollouts, int32_t num_sims,
+                 double c_puct, uint64_t seed, uint64_t root_base, int64_t n_roots) {
+    const Luts L = luts();
+    for (int64_t root = 0; root < n_roots; ++root) {
+        MctsNode* tree = pool + root * capacity;
+        int32_t* m = meta + root * kMetaStride;
+        const uint64_t root_id = (root_base + (uint64_t)root) << 32;
+        const int first = m[kMetaRollouts];
+        for (int it = 0; it < n_rollouts; ++it) {
+            const uint64_t base = root_id + (uint64_t)(uint32_t)(first + it);
+            int path_node[12], path_act[12], depth;
+            const int leaf = mcts_select(tree, m, capacity, seed, base, c_puct, L, path_node, path_act, depth);
+            int r_tot = 0;
+            for (int sim = 0; sim < num_sims; ++sim) r_tot += mcts_sim_reward(tree[leaf], seed, base, (uint32_t)sim, L);
+            if (!tree[leaf].terminal) tree[leaf].has_p = 1;
+            mcts_backprop(tree, path_node, path_act, depth, r_tot, num_sims);
+        }
+        m[kMetaRollouts] = first + n_rollouts;
+    }
+    return 0;
+}
+
+int emu_mcts_stats(const MctsNode* pool, int64_t capacity, const int32_t* meta, int32_t* n_out,
+                   double* q_out, int32_t* ntot_out, uint8_t* choose_out, int64_t n_roots) {
+    for (int64_t r = 0; r < n_roots; ++r) {
+        const MctsNode& root = pool[r * capacity + meta[r * kMetaStride + kMetaRoot]];
+        for (int a = 0; a < 36; ++a) {
+            if (n_out) n_out[36 * r + a] = (int32_t)root.n[a];
+            if (q_out) q_out[36 * r + a] = root.n[a] ? root.w[a] / (double)root.n[a] : 0.0;
+        }
+        if (ntot_out) ntot_out[r] = (int32_t)root.ntot;
+        if (choose_out) choose_out[r] = (uint8_t)mcts_choose(root);
+    }
+    return 0;
+}
+
+int emu_mcts_sync(MctsNode* pool, int64_t capacity, int32_t* meta, const uint8_t* action,
+                  const State* now, int64_t n_roots) {
+    const Luts L = luts();
+    for (int64_t r = 0; r < n_roots; ++r)
+        mcts_sync(pool + r * capacity, meta + r * kMetaStride, capacity, (int)action[r], now[r], L);
     return 0;
 }
 

@@ -395,3 +395,72 @@ def check_golden_features(backend):
             want[i, idx] = v
     assert np.abs(got - want).max() <= 1e-6
     assert ((got != 0) == (want != 0)).all()
+
+
+def _pack_oracle_games(backend, games):
+    """oracle Game objects -> packed states via the backend's pack."""
+    n = len(games)
+    classical = np.array([g.board for g in games], np.int8)
+    moves = np.full((n, 9, 2), -1, np.int8)
+    nm = np.array([len(g.moves) for g in games], np.uint8)
+    for i, g in enumerate(games):
+        for a, b, idx in g.moves:
+            moves[i, idx] = (a, b)
+    return np.asarray(backend.games(n).load(classical, moves, nm).state).copy()
+
+
+def check_golden_mcts_search(backend):
+    """Search statistics recorded from the live reference MCTS (keyed stream): N, Q (float64,
+    bit-exact), Ntot and choose() after every contemplate, across sync()s."""
+    cases = load_golden("mcts_search_v1.json.gz")
+    for case in cases:
+        g = O.Game()
+        for a, b, c in case["prefix"]:
+            g.place(a, b, lambda: c)
+        budget = sum(st["rollouts"] for st in case["stages"])
+        s = backend.mcts(_pack_oracle_games(backend, [g]), case["num_simulations"], case["seed"],
+                         case["root_index"], budget)
+        for st in case["stages"]:
+            s.contemplate(st["rollouts"])
+            n, q, ntot, ch = s.stats()
+            assert n[0].tolist() == st["N"], case["root_index"]
+            assert q[0].tolist() == st["Q"], case["root_index"]          # float64, exact
+            assert int(ntot[0]) == st["Ntot"] and int(ch[0]) == st["choose"]
+            if st["move"] is None:
+                break
+            act, c = st["move"]
+            a, b = O.PAIRS[act]
+            g.place(a, b, lambda: c)
+            s.sync(np.array([act], np.uint8), _pack_oracle_games(backend, [g]))
+        assert int(s.errors()[0]) == 0
+
+
+def check_mcts_batch_vs_oracle(backend, n_roots=24, rollouts=80, sims=8, seed=4242, root_base=100):
+    """A batch of different mid-game roots searched concurrently == the oracle searching each
+    root alone (root_base + index keys the stream)."""
+    from oracle import mcts_oracle as MO
+    import random
+    rng = random.Random(seed)
+    games = []
+    while len(games) < n_roots:
+        g = O.Game()
+        for _ in range(rng.randrange(0, 6)):
+            if g.terminal():
+                break
+            a, b = O.PAIRS[rng.choice(g.legal_actions())]
+            c = rng.randrange(2)
+            g.place(a, b, lambda: c)
+        games.append(g)                       # terminal roots included on purpose
+    s = backend.mcts(_pack_oracle_games(backend, games), sims, seed, root_base, rollouts)
+    s.contemplate(rollouts // 2)
+    s.contemplate(rollouts - rollouts // 2)   # two calls continue the same stream
+    n, q, ntot, ch = s.stats()
+    for i, g in enumerate(games):
+        m = MO.MCTS(rollouts, sims, seed, root_base + i)
+        m.reset(g)
+        m.contemplate()
+        wn, wq, wt = m.root_stats()
+        assert n[i].tolist() == wn and q[i].tolist() == wq and int(ntot[i]) == wt, i
+        want = m.choose()
+        assert int(ch[i]) == (255 if want is None else want)
+    assert (s.errors() == 0).all()

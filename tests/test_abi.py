@@ -27,7 +27,8 @@ def built_lib():
 def test_header_declares_the_expected_surface():
     assert _declared_symbols() == {
         "qttt_abi_version", "qttt_strerror", "qttt_reset", "qttt_step", "qttt_step_packed", "qttt_step_random",
-        "qttt_observe", "qttt_features", "qttt_pack", "qttt_qeval_both", "qttt_rollout", "qttt_sweep"}
+        "qttt_observe", "qttt_features", "qttt_pack", "qttt_qeval_both", "qttt_rollout", "qttt_sweep",
+        "qttt_mcts_node_bytes", "qttt_mcts_init", "qttt_mcts_run", "qttt_mcts_stats", "qttt_mcts_sync"}
 
 
 def test_library_exports_every_declared_symbol(built_lib):
@@ -56,12 +57,25 @@ def test_sass_is_sm100_only(built_lib):
 
 
 def test_no_cpu_fallback_in_package():
-    """The product never imports the oracle or the host emulation."""
+    """The product never imports the oracle or the host emulation (docstrings may cite them)."""
+    import ast
     pkg = os.path.join(ROOT, "qtttgym_b200")
     for path in glob.glob(os.path.join(pkg, "**", "*.py"), recursive=True):
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            for name in names:
+                assert not name.split(".")[0] in ("oracle", "hostemu", "tests"), (path, name)
         text = open(path).read()
-        assert "oracle" not in text.replace("# oracle", ""), path
-        assert "hostemu" not in text, path
+        assert "libqttt_oracle" not in text and "libqttt_hostemu" not in text and "CDLL(" not in text.replace(
+            "C.CDLL(LIB)", ""), path
+    for path in glob.glob(os.path.join(pkg, "csrc", "*.cu*")):
+        text = open(path).read()
+        assert "qttt_oracle" not in text and "hostemu.cpp" not in text, path
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

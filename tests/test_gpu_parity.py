@@ -338,3 +338,52 @@ def test_config5_full_size_sweep_properties(cuda):
     for k, key in enumerate(("x", "o", "draw")):
         q = ref[key] / ref["games"]
         assert abs(full[k] / g - q) < 5 * (q * (1 - q) / ref["games"]) ** 0.5
+
+
+def test_golden_mcts_search(cuda):
+    S.check_golden_mcts_search(cuda)
+
+
+def test_mcts_batch_vs_oracle(cuda):
+    S.check_mcts_batch_vs_oracle(cuda, n_roots=64, rollouts=150, sims=10)
+    S.check_mcts_batch_vs_oracle(cuda, n_roots=8, rollouts=40, sims=300, seed=7, root_base=0)
+
+
+def test_mcts_pool_exhaustion_is_flagged(cuda):
+    import torch
+    import qtttgym_b200 as Q
+    env = Q.BatchedEnv(4)
+    m = Q.BatchedMCTS(rollouts=10, num_simulations=4, seed=1)
+    m.reset(env.state, total_rollouts=10)
+    m.contemplate(400)                       # far beyond the pool
+    assert bool((m.errors() & 1).all()) and bool((m.node_counts() <= m.capacity).all())
+
+
+def test_mcts_player_beats_random(cuda):
+    """The searched move, played through the step API with sync(), beats the random policy."""
+    import torch
+    import qtttgym_b200 as Q
+    n = 512
+    env = Q.BatchedEnv(n, seed=11)
+    rnd = Q.RandomStrategy(3)
+    rnd.reset(env)
+    m = Q.BatchedMCTS(rollouts=150, num_simulations=8, seed=5)
+    m.reset(env.state)
+    for ply in range(9):
+        if ply % 2 == 0:
+            m.contemplate()
+            act = m.choose()
+            act = torch.where(env.done, torch.full_like(act, 255), act)
+        else:
+            act = rnd.choose()
+        live = ~env.done
+        env.step(act)
+        # only live trees are synced to a real move; finished games keep their root
+        safe = torch.where(live, act, torch.zeros_like(act))
+        if bool(live.any()):
+            keep = env.state.clone()
+            m.sync(safe, keep)
+        if bool(env.done.all()):
+            break
+    w = torch.bincount(env.winner().long(), minlength=3).tolist()
+    assert w[1] > 0.72 * n, w      # random-vs-random X wins 58 %

@@ -75,3 +75,11 @@ def test_render_text_matches_reference_display():
             moves[m[2]] = m[:2]
         # displayBoard prints the string followed by print()'s own newline
         assert Q.render_text(r["board"], moves, len(r["moves"])) + "\n" == r["display"]
+
+
+def test_golden_mcts_search(emu):
+    S.check_golden_mcts_search(emu)
+
+
+def test_mcts_batch_vs_oracle(emu):
+    S.check_mcts_batch_vs_oracle(emu)
