@@ -8,7 +8,8 @@ displayBoard, Env) for the parts on the hot path: ``Env`` (single-env adapter), 
 ``selfplay_sweep``.  Everything computes in libqttt_b200.so (hand-written CUDA for sm_100a);
 importing this package without that library works, using it does not.
 """
-from .arena import BatchedStrategy, RandomStrategy, RolloutStrategy, eval_strats, play_games
+from .arena import (BatchedStrategy, MCTSStrategy, RandomStrategy, RolloutStrategy, eval_strats,
+                    play_games)
 from .actions import NUM_ACTIONS, PAIRS, ind2move, move2ind
 from .env import (BatchedEnv, Env, observe_states, pack_actions, pack_states, render_text, to_vector,
                   unpack_result)
@@ -21,6 +22,6 @@ __all__ = [
     "BatchedEnv", "Env", "observe_states", "pack_states", "pack_actions", "unpack_result",
     "to_vector", "render_text",
     "BatchedMCTS", "QEvalB200", "qeval_both", "square_probabilities",
-    "BatchedStrategy", "RandomStrategy", "RolloutStrategy", "eval_strats", "play_games",
+    "BatchedStrategy", "MCTSStrategy", "RandomStrategy", "RolloutStrategy", "eval_strats", "play_games",
     "STAT_NAMES", "rollout_eval", "selfplay_sweep", "shard_range", "sharded_sweep",
 ]

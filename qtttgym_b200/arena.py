@@ -87,6 +87,36 @@ class RolloutStrategy(BatchedStrategy):
         return a
 
 
+class MCTSStrategy(BatchedStrategy):
+    """The reference's ``MCTS`` strategy (mcts.py:132-337) for a batch: ``contemplate`` runs
+    ``rollouts`` rollouts per live game, ``choose`` returns the best root action, ``sync``
+    re-roots every tree on the move actually played (own and opponent's)."""
+
+    def __init__(self, rollouts: int = 200, num_simulations: int = 10, seed: int = 0):
+        from .mcts import BatchedMCTS
+        self.search = BatchedMCTS(rollouts=rollouts, num_simulations=num_simulations, seed=seed)
+
+    def reset(self, env):
+        super().reset(env)
+        self.search.device = env.device
+        self.search.reset(env.state)
+        self._live = ~env.done.clone()
+
+    def contemplate(self, thinking_time=None):
+        self.search.contemplate()
+
+    def choose(self):
+        a = self.search.choose()
+        return torch.where(_finished(self.env), torch.full_like(a, 255), a)
+
+    def sync(self, actions):
+        # trees of games that were still running before this move follow it; finished games
+        # keep their last root (their action is the 255 filler)
+        live = actions < 36
+        safe = torch.where(live, actions, torch.zeros_like(actions))
+        self.search.sync(safe, self.env.state)
+
+
 def play_games(strat_x: BatchedStrategy, strat_o: BatchedStrategy, n_games: int, seed: int = 0,
                device="cuda"):
     """strat_eval.py:34-63 for ``n_games`` games at once: X (player 1) and O alternate until a

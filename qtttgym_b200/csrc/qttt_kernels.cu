@@ -358,7 +358,74 @@ k_mcts_init(MctsNode* __restrict__ pool, int64_t capacity, int32_t* __restrict__
         mcts_init_root(pool + r * capacity, meta + r * kMetaStride, load_state(roots, r), L);
 }
 
-// One block per root.  A rollout is: thread 0 walks the tree (PUCT select, expanding one
+// ---- warp-cooperative forms of mcts_uct_select / mcts_expand / mcts_select (qttt_mcts.cuh):
+// the same arithmetic in the same order per action, spread over the 32 lanes of warp 0.
+__device__ __forceinline__ int warp_uct_select(const MctsNode& nd, double c_puct, int lane) {
+    const uint64_t legal = nd.legal;
+    const int m = popc32((uint32_t)legal) + popc32((uint32_t)(legal >> 32));
+    const double ps = d_mul(d_div(1.0, (double)m), d_sqrt((double)nd.ntot));
+    int best = 64;
+    double best_v = 0.0;
+    for (int a = lane; a < 36; a += 32) {
+        if (!(legal >> a & 1ull)) continue;
+        const uint32_t na = nd.n[a];
+        const double u = d_div(ps, (double)(1u + na));
+        const double q = na ? d_div(nd.w[a], (double)na) : 0.0;
+        const double v = d_add(q, d_mul(c_puct, u));
+        if (best == 64 || v > best_v) { best = a; best_v = v; }
+    }
+    // first maximum in ascending action order == (greater value) or (equal value, smaller action)
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const double ov = __shfl_xor_sync(0xFFFFFFFFu, best_v, off);
+        const int oa = __shfl_xor_sync(0xFFFFFFFFu, best, off);
+        if (oa != 64 && (best == 64 || ov > best_v || (ov == best_v && oa < best))) { best = oa; best_v = ov; }
+    }
+    return best;
+}
+
+__device__ __forceinline__ void warp_init_node(MctsNode& nd, const State& s, bool turn, const Luts& L, int lane) {
+    for (int a = lane; a < 36; a += 32) { nd.n[a] = 0u; nd.child[a][0] = -1; nd.child[a][1] = -1; nd.w[a] = 0.0; }
+    if (lane == 0) {
+        nd.state = s;
+        nd.ntot = 0u;
+        nd.has_p = 0;
+        bool terminal;
+        nd.winner = (uint8_t)finished_winner(s, L, terminal);
+        nd.terminal = terminal ? 1 : 0;
+        nd.turn = turn ? 1 : 0;
+        nd.legal = L.legal[~classical(s) & M9];
+    }
+}
+
+__device__ __forceinline__ bool warp_expand(MctsNode* tree, int32_t* meta, int64_t capacity, int node, int a,
+                                            const Luts& L, int lane) {
+    const uint32_t enew = L.pair[a];
+    State s0 = tree[node].state, s1 = s0;                    // every lane computes the same children
+    const StepResult r0 = step_core(s0, enew, 0u, L);
+    const int need = r0.collapsed ? 2 : 1;
+    const int c0 = meta[kMetaCount];
+    if ((int64_t)c0 + need > capacity) {
+        if (lane == 0) meta[kMetaError] |= kMctsErrPoolFull;
+        return false;
+    }
+    const bool turn = !tree[node].turn;
+    warp_init_node(tree[c0], s0, turn, L, lane);
+    if (r0.collapsed) {
+        step_core(s1, enew, 1u, L);
+        warp_init_node(tree[c0 + 1], s1, turn, L, lane);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        tree[node].child[a][0] = c0;
+        if (r0.collapsed) tree[node].child[a][1] = c0 + 1;
+        meta[kMetaCount] = c0 + need;
+    }
+    __syncwarp();
+    return true;
+}
+
+// One block per root.  A rollout is: warp 0 walks the tree (PUCT select, expanding one
 // (node, action) when needed), all threads play the leaf's num_simulations playouts in
 // parallel, a block reduction gives r_tot, thread 0 backs the value up.  Trees of different
 // roots advance independently in different blocks.
@@ -374,13 +441,22 @@ k_mcts_run(MctsNode* __restrict__ pool, int64_t capacity, int32_t* __restrict__ 
     int32_t* m = meta + root * kMetaStride;
     const uint64_t root_id = (root_base + (uint64_t)root) << 32;
     const int first = m[kMetaRollouts];
+    const int lane = threadIdx.x & 31;
     for (int it = 0; it < n_rollouts; ++it) {
         const uint64_t base = root_id + (uint64_t)(uint32_t)(first + it);
-        if (threadIdx.x == 0) {
-            int depth;
-            sh_leaf = mcts_select(tree, m, capacity, seed, base, c_puct, L, sh_path_node, sh_path_act, depth);
-            sh_depth = depth;
-            sh_rtot = 0;
+        if (threadIdx.x < 32) {                                            // mcts.py:269-277
+            int node = m[kMetaRoot], depth = 0;
+            while (tree[node].has_p && !tree[node].terminal) {
+                const int a = warp_uct_select(tree[node], c_puct, lane);
+                if (tree[node].child[a][0] < 0 && !warp_expand(tree, m, capacity, node, a, L, lane)) break;
+                if (lane == 0) { sh_path_node[depth] = node; sh_path_act[depth] = a; }
+                uint32_t c0 = (uint32_t)base, c1 = (uint32_t)(base >> 32), c2 = (uint32_t)depth, c3 = kDomainSelect;
+                philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+                const int second = tree[node].child[a][1];
+                node = (second >= 0 && (c1 & 1u)) ? second : tree[node].child[a][0];
+                ++depth;
+            }
+            if (lane == 0) { sh_leaf = node; sh_depth = depth; sh_rtot = 0; }
         }
         __syncthreads();
         const MctsNode& leaf = tree[sh_leaf];
@@ -388,7 +464,7 @@ k_mcts_run(MctsNode* __restrict__ pool, int64_t capacity, int32_t* __restrict__ 
         for (int sim = threadIdx.x; sim < num_sims; sim += blockDim.x)
             r += mcts_sim_reward(leaf, seed, base, (uint32_t)sim, L);
         r = __reduce_add_sync(0xFFFFFFFFu, r);
-        if ((threadIdx.x & 31) == 0 && r) atomicAdd(&sh_rtot, r);
+        if (lane == 0 && r) atomicAdd(&sh_rtot, r);
         __syncthreads();
         if (threadIdx.x == 0) {
             if (!tree[sh_leaf].terminal) tree[sh_leaf].has_p = 1;             // mcts.py:189-191

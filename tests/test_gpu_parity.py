@@ -360,30 +360,9 @@ def test_mcts_pool_exhaustion_is_flagged(cuda):
 
 
 def test_mcts_player_beats_random(cuda):
-    """The searched move, played through the step API with sync(), beats the random policy."""
-    import torch
+    """strat_eval.py:34-95 with the searched player: MCTS (150 rollouts x 8 playouts per move,
+    re-rooted with sync() after every ply) against the random policy, both colours."""
     import qtttgym_b200 as Q
-    n = 512
-    env = Q.BatchedEnv(n, seed=11)
-    rnd = Q.RandomStrategy(3)
-    rnd.reset(env)
-    m = Q.BatchedMCTS(rollouts=150, num_simulations=8, seed=5)
-    m.reset(env.state)
-    for ply in range(9):
-        if ply % 2 == 0:
-            m.contemplate()
-            act = m.choose()
-            act = torch.where(env.done, torch.full_like(act, 255), act)
-        else:
-            act = rnd.choose()
-        live = ~env.done
-        env.step(act)
-        # only live trees are synced to a real move; finished games keep their root
-        safe = torch.where(live, act, torch.zeros_like(act))
-        if bool(live.any()):
-            keep = env.state.clone()
-            m.sync(safe, keep)
-        if bool(env.done.all()):
-            break
-    w = torch.bincount(env.winner().long(), minlength=3).tolist()
-    assert w[1] > 0.72 * n, w      # random-vs-random X wins 58 %
+    res = Q.eval_strats(Q.MCTSStrategy(rollouts=150, num_simulations=8, seed=5), Q.RandomStrategy(3),
+                        num_games=1024, seed=11)
+    assert res["strat1_wins"] > 0.72 * res["games"], res     # random-vs-random: X wins 58 %, O 29 %
