@@ -317,7 +317,7 @@ def run_b200(args):
     h_act = actions.cpu().pin_memory()
     h_coin = coins.cpu().pin_memory()
     h_ac = Q.pack_actions(actions, coins).cpu().pin_memory()          # 1 byte per env per ply
-    h_res = torch.empty(E, dtype=torch.int64).pin_memory()            # 8 bytes per env per ply
+    h_res = torch.empty(E, dtype=torch.int16).pin_memory()            # 2 bytes per env per ply
     h_reward = torch.empty(E, dtype=torch.float32).pin_memory()
     h_done = torch.empty(E, dtype=torch.bool).pin_memory()
     h_mask = torch.empty(E, dtype=torch.int64).pin_memory()
@@ -342,12 +342,12 @@ def run_b200(args):
     assert int(term_chk.sum()) == E, "e2e pass did not finish every game"
     v_sep, ms_sep = e2e_run(lambda ply: env.step_host(h_act[ply], h_coin[ply], h_reward, h_done, h_mask))
     assert int(h_done.sum()) == E, "e2e pass did not finish every game"
-    launches += 2 * (2 + e2e_K) * (1 + PLIES * 8)
+    launches += 2 * (2 + e2e_K) * (1 + PLIES * 8)   # 8 slices per ply
     e2e = {"value": v_packed, "unit": UNIT, "h2d_bytes_per_step": 1 * E * PLIES,
-           "d2h_bytes_per_step": 8 * E * PLIES, "steps": e2e_K, "ms_per_step": ms_packed,
-           "api": "BatchedEnv.reset + 9 x BatchedEnv.step_host_packed (C ABI qttt_step_packed; pinned host "
-                  "buffers: 1 B action|coin in, one 64-bit result word (legal mask, terminated, line, status) "
-                  "out per env per ply; 8 slices pipelined over 4 side streams)",
+           "d2h_bytes_per_step": 2 * E * PLIES, "steps": e2e_K, "ms_per_step": ms_packed,
+           "api": "BatchedEnv.reset + 9 x BatchedEnv.step_host_packed (C ABI qttt_step_packed_host; pinned host "
+                  "buffers: 1 B action|coin in, one 16-bit result word (free-square set = legal mask, "
+                  "terminated, line, status) out per env per ply; 8 slices pipelined over 4 side streams)",
            "separate_arrays": {"value": v_sep, "ms_per_step": ms_sep, "h2d_bytes_per_step": 2 * E * PLIES,
                                "d2h_bytes_per_step": 13 * E * PLIES,
                                "api": "BatchedEnv.step_host (qttt_step): uint8 actions + coins in, f32 reward + "

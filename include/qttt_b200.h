@@ -86,15 +86,27 @@ QTTT_API int qttt_step(qttt_state* state, const void* action, int action_format,
               uint8_t* status, int64_t n, void* stream);
 
 /* qttt_step with compact I/O, for callers whose buffers live in HOST memory (there the PCIe
- * link, not HBM, is the bound: 9 bytes per game cross it instead of 15).
+ * link, not HBM, is the bound: 3 bytes per game cross it instead of 15).
  *   action_coin uint8[n]  : bits 0..5 action index (QTTT_ACT_INDEX; 36..63 = illegal),
  *                           bit 7 forced coin
- *   result      uint64[n] : bits 0..35 legal mask of the new state, bit 36 terminated,
- *                           bit 37 "a line exists" (reward = bit ? -1.0f : -0.0f, env.py:49),
- *                           bits 38..39 status (QTTT_ST_*)
- * Same transition, same outputs as qttt_step, bit for bit. */
-QTTT_API int qttt_step_packed(qttt_state* state, const uint8_t* action_coin, uint64_t* result,
+ *   result      uint16[n] : bits 0..8 the free (non-classical) squares of the new state -- the
+ *                           36-bit legal mask is a function of it (legal[k] = both squares of
+ *                           pair k free, mcts.py:19-27; qtttgym_b200.unpack_result expands it
+ *                           with a 512-entry table) --, bit 9 terminated, bit 10 "a line
+ *                           exists" (reward = bit ? -1.0f : -0.0f, env.py:49), bits 11..12
+ *                           status (QTTT_ST_*)
+ * Same transition, same information as qttt_step, bit for bit. */
+QTTT_API int qttt_step_packed(qttt_state* state, const uint8_t* action_coin, uint16_t* result,
                               int64_t n, void* stream);
+
+/* The host-buffer form of qttt_step_packed: action_coin_host / result_host are PINNED HOST
+ * arrays; in_dev (uint8[n]) / out_dev (uint16[n]) are caller-provided device staging buffers.
+ * The batch is cut into slices of `slice` games; slice k is copied in, stepped and copied out
+ * on streams[k % n_streams], so that host->device copies, kernels and device->host copies of
+ * different slices overlap.  The caller orders the streams against its own work. */
+QTTT_API int qttt_step_packed_host(qttt_state* state, const uint8_t* action_coin_host,
+                                   uint16_t* result_host, uint8_t* in_dev, uint16_t* out_dev,
+                                   int64_t n, int64_t slice, void* const* streams, int n_streams);
 
 /* Env.step driven by the uniform-random policy of MCTS._simulate (mcts.py:185-198,
  * 287-292): action ~ U(legal actions), coin ~ U{0,1}, both from Philox4x32-10 with counter

@@ -103,10 +103,10 @@ k_step(qttt_state* __restrict__ state, const uint8_t* __restrict__ action,
     }
 }
 
-// K1 with compact I/O (one byte in, one 64-bit word out per game): see qttt_step_packed.
+// K1 with compact I/O (one byte in, one 16-bit word out per game): see qttt_step_packed.
 __global__ void __launch_bounds__(kThreads)
 k_step_packed(qttt_state* __restrict__ state, const uint8_t* __restrict__ action_coin,
-              unsigned long long* __restrict__ result, uint32_t n) {
+              uint16_t* __restrict__ result, uint32_t n) {
     __shared__ __align__(16) uint8_t smem[kLutStepBytes];
     stage_luts(smem, kLutStepBytes);
     const Luts L = luts_from_image(smem);
@@ -118,10 +118,9 @@ k_step_packed(qttt_state* __restrict__ state, const uint8_t* __restrict__ action
         const uint32_t ac = action_coin[i];
         const StepResult r = step_core(s, (uint32_t)L.pair[ac & 63u], ac >> 7, L);
         if (!r.illegal) *sp = make_uint4(s.x, s.y, s.z, s.w);
-        const unsigned long long win = any_line(s, r.classical, L) != 0u;
-        const unsigned long long term = win | (unsigned long long)(r.n > 8u);
-        result[i] = L.legal[~r.classical & M9] | (term << 36) | (win << 37) |
-                    ((unsigned long long)r.illegal << 38);
+        const uint32_t win = any_line(s, r.classical, L) != 0u;
+        const uint32_t term = win | (uint32_t)(r.n > 8u);
+        result[i] = (uint16_t)((~r.classical & M9) | (term << 9) | (win << 10) | (r.illegal << 11));
     }
 }
 
@@ -598,18 +597,41 @@ int qttt_step(qttt_state* state, const void* action, int action_format, const ui
     return launch_step<QTTT_ACT_PAIR, false>(state, act, coin, seed, game_base, reward, done, mask, status, nullptr, nullptr, n, st);
 }
 
-int qttt_step_packed(qttt_state* state, const uint8_t* action_coin, uint64_t* result, int64_t n,
+int qttt_step_packed(qttt_state* state, const uint8_t* action_coin, uint16_t* result, int64_t n,
                      void* stream) {
     if (n == 0) return QTTT_OK;
     if (!state || !action_coin || !result || n < 0) return QTTT_ERR_ARG;
-    if (misaligned(state, 16) || misaligned(result, 8)) return QTTT_ERR_ALIGN;
+    if (misaligned(state, 16) || misaligned(result, 2)) return QTTT_ERR_ALIGN;
     const int64_t kSlice = 1ll << 31;
     for (int64_t lo = 0; lo < n; lo += kSlice) {
         const int64_t m = n - lo < kSlice ? n - lo : kSlice;
         k_step_packed<<<grid_for(k_step_packed, m), kThreads, 0, (cudaStream_t)stream>>>(
-            state + lo, action_coin + lo, reinterpret_cast<unsigned long long*>(result) + lo, (uint32_t)m);
+            state + lo, action_coin + lo, result + lo, (uint32_t)m);
         const int rc = check_launch();
         if (rc != QTTT_OK) return rc;
+    }
+    return QTTT_OK;
+}
+
+int qttt_step_packed_host(qttt_state* state, const uint8_t* action_coin_host, uint16_t* result_host,
+                          uint8_t* in_dev, uint16_t* out_dev, int64_t n, int64_t slice,
+                          void* const* streams, int n_streams) {
+    if (n == 0) return QTTT_OK;
+    if (!state || !action_coin_host || !result_host || !in_dev || !out_dev || !streams || n < 0 ||
+        slice < 1 || slice > (1ll << 31) || n_streams < 1)
+        return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(out_dev, 2) || misaligned(result_host, 2)) return QTTT_ERR_ALIGN;
+    int k = 0;
+    for (int64_t lo = 0; lo < n; lo += slice, ++k) {
+        const int64_t m = n - lo < slice ? n - lo : slice;
+        cudaStream_t st = (cudaStream_t)streams[k % n_streams];
+        cudaError_t e = cudaMemcpyAsync(in_dev + lo, action_coin_host + lo, (size_t)m, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return -(1000 + (int)e);
+        k_step_packed<<<grid_for(k_step_packed, m), kThreads, 0, st>>>(state + lo, in_dev + lo, out_dev + lo, (uint32_t)m);
+        const int rc = check_launch();
+        if (rc != QTTT_OK) return rc;
+        e = cudaMemcpyAsync(result_host + lo, out_dev + lo, (size_t)m * 2, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return -(1000 + (int)e);
     }
     return QTTT_OK;
 }

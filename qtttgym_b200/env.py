@@ -168,36 +168,34 @@ class BatchedEnv:
         return reward_host, done_host, mask_host
 
     def step_host_packed(self, action_coin_host, result_host, chunks: int = 8, n_streams: int = 4):
-        """``step_host`` with compact I/O (``qttt_step_packed``): 1 byte in and 8 bytes out per
-        env cross PCIe instead of 2 + 13.  ``action_coin_host`` uint8[N] from ``pack_actions``;
-        ``result_host`` int64[N], decoded with ``unpack_result``.  Same transition, bit for bit.
-        """
+        """``step_host`` with compact I/O (``qttt_step_packed_host``): 1 byte in and 2 bytes out
+        per env cross PCIe instead of 2 + 13.  ``action_coin_host`` uint8[N] from
+        ``pack_actions``; ``result_host`` int16[N], decoded with ``unpack_result`` (the 36-bit
+        legal mask is re-expanded on the host from the 9-bit free-square set).  Same transition,
+        bit for bit.  The slices are pipelined over side streams inside the C call."""
+        import ctypes as C
         n, dev = self.num_envs, self.device
-        for t, dt in ((action_coin_host, torch.uint8), (result_host, torch.int64)):
+        for t, dt in ((action_coin_host, torch.uint8), (result_host, torch.int16)):
             if t.dtype != dt or t.numel() != n or t.device.type != "cpu" or not t.is_contiguous():
-                raise ValueError("step_host_packed expects contiguous CPU uint8[N] / int64[N] tensors")
+                raise ValueError("step_host_packed expects contiguous CPU uint8[N] / int16[N] tensors")
         if self._host_streams is None or len(self._host_streams) != n_streams:
             self._host_streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
             self._d_act = torch.empty(n, dtype=torch.uint8, device=dev)
             self._d_coin = torch.empty(n, dtype=torch.uint8, device=dev)
+        if getattr(self, "_d_res16", None) is None:
+            self._d_res16 = torch.empty(n, dtype=torch.int16, device=dev)
+            self._stream_array = (C.c_void_p * n_streams)(*[st.cuda_stream for st in self._host_streams])
         cur = torch.cuda.current_stream(dev)
         ready = torch.cuda.Event()
         ready.record(cur)
         chunks = max(1, min(chunks, (n + 255) // 256))
         per = -(-(-(-n // chunks)) // 256) * 256
         with torch.cuda.device(dev):
-            for c in range(chunks):
-                lo, hi = c * per, min(n, (c + 1) * per)
-                if lo >= hi:
-                    break
-                st = self._host_streams[c % n_streams]
+            for st in self._host_streams:
                 st.wait_event(ready)
-                with torch.cuda.stream(st):
-                    self._d_act[lo:hi].copy_(action_coin_host[lo:hi], non_blocking=True)
-                    _lib.check(self.lib.qttt_step_packed(
-                        self.state.data_ptr() + 16 * lo, self._d_act.data_ptr() + lo,
-                        self.mask.data_ptr() + 8 * lo, hi - lo, st.cuda_stream))
-                    result_host[lo:hi].copy_(self.mask[lo:hi], non_blocking=True)
+            _lib.check(self.lib.qttt_step_packed_host(
+                self.state.data_ptr(), action_coin_host.data_ptr(), result_host.data_ptr(),
+                self._d_act.data_ptr(), self._d_res16.data_ptr(), n, per, self._stream_array, n_streams))
             for st in self._host_streams:
                 fin = torch.cuda.Event()
                 fin.record(st)
@@ -300,16 +298,35 @@ def pack_actions(actions, choices):
     return (a | ((choices & 1) << 7)).to(torch.uint8)
 
 
+_LEGAL_OF_FREE = None
+
+
+def _legal_table(device):
+    """512-entry table: free-square set -> 36-bit legal mask (mcts.py:19-27)."""
+    global _LEGAL_OF_FREE
+    if _LEGAL_OF_FREE is None:
+        tbl = []
+        for m in range(512):
+            v = 0
+            for k, (i, j) in enumerate(PAIRS):
+                if (m >> i) & 1 and (m >> j) & 1:
+                    v |= 1 << k
+            tbl.append(v)
+        _LEGAL_OF_FREE = torch.tensor(tbl, dtype=torch.int64)
+    return _LEGAL_OF_FREE.to(device)
+
+
 def unpack_result(result):
-    """int64 result words of ``step_host_packed`` -> (reward f32, terminated bool, mask int64,
+    """int16 result words of ``step_host_packed`` -> (reward f32, terminated bool, mask int64,
     status uint8), identical to what ``step`` returns."""
-    mask = result & ((1 << 36) - 1)
-    terminated = ((result >> 36) & 1).bool()
-    win = ((result >> 37) & 1).bool()
+    r = result.to(torch.int32) & 0xFFFF
+    mask = _legal_table(result.device)[(r & 0x1FF).long()]
+    terminated = ((r >> 9) & 1).bool()
+    win = ((r >> 10) & 1).bool()
     neg_one = torch.tensor(-1.0, dtype=torch.float32, device=result.device)
     neg_zero = torch.tensor(-0.0, dtype=torch.float32, device=result.device)
     reward = torch.where(win, neg_one, neg_zero)
-    status = ((result >> 38) & 3).to(torch.uint8)
+    status = ((r >> 11) & 3).to(torch.uint8)
     return reward, terminated, mask, status
 
 

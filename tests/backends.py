@@ -118,7 +118,7 @@ class EmuGames:
 
     def step_packed(self, action_coin):
         ac = np.ascontiguousarray(action_coin, dtype=np.uint8)
-        res = np.empty(self.n, np.uint64)
+        res = np.empty(self.n, np.uint16)
         self.lib.emu_step_packed(_p(self.state), _p(ac), _p(res), C.c_int64(self.n))
         return res
 
@@ -255,10 +255,10 @@ class CudaGames:
     def step_packed(self, action_coin):
         t = self.torch
         ac = t.from_numpy(np.ascontiguousarray(action_coin, np.uint8)).pin_memory()
-        res = t.empty(self.n, dtype=t.int64).pin_memory()
+        res = t.empty(self.n, dtype=t.int16).pin_memory()
         self.env.step_host_packed(ac, res, chunks=3, n_streams=2)
         t.cuda.synchronize()
-        return res.numpy().astype(np.uint64)
+        return res.numpy().view(np.uint16).copy()
 
     def step_random(self, seed, game_base=0):
         self.env.seed, self.env.game_base = seed, game_base

@@ -45,16 +45,16 @@ int emu_step(State* state, const void* action, int fmt, const uint8_t* coin, uin
     return 0;
 }
 
-int emu_step_packed(State* state, const uint8_t* action_coin, uint64_t* result, int64_t n) {
+int emu_step_packed(State* state, const uint8_t* action_coin, uint16_t* result, int64_t n) {
     const Luts L = luts();
     for (int64_t i = 0; i < n; ++i) {
         State s = state[i];
         const uint32_t ac = action_coin[i];
         const StepResult r = step_core(s, (uint32_t)L.pair[ac & 63u], ac >> 7, L);
         if (!r.illegal) state[i] = s;
-        const uint64_t win = any_line(s, r.classical, L) != 0u;
-        const uint64_t term = win | (uint64_t)(r.n > 8u);
-        result[i] = L.legal[~r.classical & M9] | (term << 36) | (win << 37) | ((uint64_t)r.illegal << 38);
+        const uint32_t win = any_line(s, r.classical, L) != 0u;
+        const uint32_t term = win | (uint32_t)(r.n > 8u);
+        result[i] = (uint16_t)((~r.classical & M9) | (term << 9) | (win << 10) | (r.illegal << 11));
     }
     return 0;
 }

@@ -350,8 +350,8 @@ def check_philox_coin(backend, n_games=3000, seed=99, game_base=1234):
 
 
 def check_packed_step(backend, n_games=5000, seed=31):
-    """qttt_step_packed: one byte in (action | coin << 7), one word out (mask | terminated << 36 |
-    line << 37 | status << 38) -- same transition as the oracle, bit for bit."""
+    """qttt_step_packed: one byte in (action | coin << 7), one 16-bit word out (free squares |
+    terminated << 9 | line << 10 | status << 11) -- same transition as the oracle, bit for bit."""
     rng = np.random.default_rng(seed)
     ref = CO.Games(n_games)
     dut = backend.games(n_games)
@@ -366,14 +366,17 @@ def check_packed_step(backend, n_games=5000, seed=31):
         pairs = np.full((n_games, 2), -1, np.int8)
         pairs[k < 36] = PAIRS[k[k < 36]]
         r = ref.step(pairs, coins)
-        res = dut.step_packed(k | (coins << 7))
+        res = dut.step_packed(k | (coins << 7)).astype(np.uint32)
         where = f"{backend.name} packed ply {ply}"
-        assert np.array_equal(res & np.uint64((1 << 36) - 1), r["mask"]), where
-        assert np.array_equal((res >> np.uint64(36)) & np.uint64(1), r["done"].astype(np.uint64)), where
-        win = (r["reward"].view(np.uint32) == 0xBF800000).astype(np.uint64)
-        assert np.array_equal((res >> np.uint64(37)) & np.uint64(1), win), where
-        assert np.array_equal((res >> np.uint64(38)) & np.uint64(3), r["status"].astype(np.uint64)), where
-        assert_same_obs(dut.observe(), ref.observe(), where)
+        robs = ref.observe()
+        free = ((robs["classical"] < 0) * (1 << np.arange(9))).sum(1).astype(np.uint32)
+        assert np.array_equal(res & 0x1FF, free), where
+        assert np.array_equal(_mask_from_obs(robs), r["mask"])               # the mask IS a function of it
+        assert np.array_equal((res >> 9) & 1, r["done"].astype(np.uint32)), where
+        win = (r["reward"].view(np.uint32) == 0xBF800000).astype(np.uint32)
+        assert np.array_equal((res >> 10) & 1, win), where
+        assert np.array_equal((res >> 11) & 3, r["status"].astype(np.uint32)), where
+        assert_same_obs(dut.observe(), robs, where)
         mask = r["mask"]
 
 

@@ -234,7 +234,7 @@ def test_pack_unpack_helpers_match_step(cuda):
     import qtttgym_b200 as Q
     n = 10_000
     gen, a, b = Q.BatchedEnv(n, seed=4), Q.BatchedEnv(n, seed=4), Q.BatchedEnv(n, seed=4)
-    res = torch.empty(n, dtype=torch.int64).pin_memory()
+    res = torch.empty(n, dtype=torch.int16).pin_memory()
     for ply in range(9):
         info = gen.step_random(record=True)[4]
         act, coin = info["action"].clone(), info["coin"].clone()
