@@ -241,7 +241,8 @@ def run_b200(args):
 
     E, K, W = args.envs, args.steps, args.warmup
     seed = 20261018
-    launches = 0
+    from qtttgym_b200 import _lib as qlib
+    launches = 0          # our kernels launched inside the timed regions (value_eager, value, e2e)
 
     # ---- synthetic workload: random-policy traces generated on the device (untimed)
     env = Q.BatchedEnv(E, device=dev, seed=seed, game_base=rank * E)
@@ -264,6 +265,7 @@ def run_b200(args):
         if it == W:
             barrier()
             sampler = ClockSampler(dev)
+            launches_before = qlib.LAUNCHES
             start.record()
         env.reset()
         for ply in range(PLIES):
@@ -275,7 +277,7 @@ def run_b200(args):
     end.record()
     barrier()
     t_ms = max_over_ranks(start.elapsed_time(end))
-    launches += K * (1 + PLIES)
+    launches += qlib.LAUNCHES - launches_before          # K x (1 reset + 9 step)
     total_steps = sum_over_ranks(float(steps_per_pass)) * K
     value = total_steps / (t_ms * 1e-3)
     # the state after the timed passes must be the state the trace generation ended in
@@ -309,7 +311,7 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop() if sampler else {}      # sampled over the eager and the graph timed regions
     graph_ms = max_over_ranks(g0.elapsed_time(g1))
-    launches += (K + W + 2) * (1 + PLIES)
+    launches += K * (1 + PLIES)                          # kernels inside the K replayed graphs
     value_graph = total_steps / (graph_ms * 1e-3)
     assert torch.equal(torch.bincount(env.winner().long(), minlength=3), final_winner)
 
@@ -324,16 +326,19 @@ def run_b200(args):
     e2e_K = max(1, min(K, args.e2e_steps))
 
     def e2e_run(step_fn):
+        nonlocal launches
         s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for it in range(2 + e2e_K):
             if it == 2:
                 barrier()
+                before = qlib.LAUNCHES
                 s2.record()
             env.reset()
             for ply in range(PLIES):
                 step_fn(ply)
         e2.record()
         barrier()
+        launches += qlib.LAUNCHES - before
         ms = max_over_ranks(s2.elapsed_time(e2))
         return sum_over_ranks(float(steps_per_pass)) * e2e_K / (ms * 1e-3), ms / e2e_K
 
@@ -342,7 +347,6 @@ def run_b200(args):
     assert int(term_chk.sum()) == E, "e2e pass did not finish every game"
     v_sep, ms_sep = e2e_run(lambda ply: env.step_host(h_act[ply], h_coin[ply], h_reward, h_done, h_mask))
     assert int(h_done.sum()) == E, "e2e pass did not finish every game"
-    launches += 2 * (2 + e2e_K) * (1 + PLIES * 8)   # 8 slices per ply
     e2e = {"value": v_packed, "unit": UNIT, "h2d_bytes_per_step": 1 * E * PLIES,
            "d2h_bytes_per_step": 2 * E * PLIES, "steps": e2e_K, "ms_per_step": ms_packed,
            "api": "BatchedEnv.reset + 9 x BatchedEnv.step_host_packed (C ABI qttt_step_packed_host; pinned host "
@@ -377,10 +381,8 @@ def run_b200(args):
         for p in range(PLIES):
             small.step(sa[p], sc[p])
     ms = timed(small_pass, 50)
-    launches += 51 * (1 + PLIES)
     graph = small.capture_episode(sa, sc)
     ms_graph = timed(graph.replay, 200)
-    launches += (201 + 2) * (1 + PLIES)
     extra["config2_4096_envs"] = {"env_steps_per_s": small_steps / (ms_graph * 1e-3) * world,
                                   "ms_per_pass_cuda_graph": ms_graph, "ms_per_pass_eager": ms,
                                   "env_steps_per_s_eager": small_steps / (ms * 1e-3) * world,
@@ -394,7 +396,6 @@ def run_b200(args):
     def sweep_pass():
         stats_box["s"] = Q.sharded_sweep(G * world, seed, dev)
     ms = timed(sweep_pass, 3)
-    launches += 4
     st = stats_box["s"].cpu().tolist()
     extra["config5_sweep"] = {
         "env_steps_per_s": st[3] / (ms * 1e-3), "games": st[5], "env_steps": st[3], "ms": ms,
@@ -410,7 +411,6 @@ def run_b200(args):
         qenv.step(actions[p, :nb], coins[p, :nb])
     qa = torch.where(qa < 36, qa, torch.zeros_like(qa))
     ms = timed(lambda: Q.qeval_both(qenv.state, qa, want_states=False, want_probs=False), 20)
-    launches += 21
     extra["config3_qeval_1M_boards"] = {
         "boards_per_s": nb / (ms * 1e-3) * world, "ms": ms,
         "hbm_frac_at_33B": nb / (ms * 1e-3) * BYTES_PER_BOARD_QEVAL / 1e9 / peak}
@@ -422,7 +422,6 @@ def run_b200(args):
     def roll():
         box["r"] = Q.rollout_eval(roots, 256, seed)
     ms = timed(roll, 20)
-    launches += 21
     rsteps = int(box["r"][2].item())
     extra["config4_rollout_1024x256"] = {"playouts_per_s": 1024 * 256 / (ms * 1e-3) * world,
                                          "env_steps_per_s": rsteps / (ms * 1e-3) * world, "ms": ms}
@@ -435,7 +434,7 @@ def run_b200(args):
             mc.reset(roots, total_rollouts=n_roll)
             mc.contemplate(n_roll)
         ms = timed(search, 3)
-        launches += 4 * 2
+
         assert int(mc.errors().max().item()) == 0
         extra[name] = {"ms": ms, "rollouts_per_s": 1024 * n_roll / (ms * 1e-3) * world,
                        "playouts_per_s": 1024 * n_roll * n_sim / (ms * 1e-3) * world,
@@ -444,13 +443,11 @@ def run_b200(args):
 
     # a9 observation decode (env.py:68-85 + extras) and the to_vector feature encoder
     ms = timed(lambda: env.observation(extras=True), 5)
-    launches += 6
     extra["observe_all_outputs"] = {"ms": ms, "envs": E, "bytes_per_env": 16 + 90,
                                     "gb_per_s": E * (16 + 90) / (ms * 1e-3) / 1e9,
                                     "note": "qttt_observe, every output (classical, moves, n_moves, q lists, turn, "
                                             "rounds, reward_p1, winner, bool mask); includes torch.empty of the outputs"}
     ms = timed(lambda: Q.to_vector(qenv.state), 20)
-    launches += 21
     extra["to_vector_1M_states"] = {"ms": ms, "states_per_s": nb / (ms * 1e-3) * world,
                                     "gb_per_s": nb * 736 / (ms * 1e-3) / 1e9}
     if cpu_c:

@@ -65,9 +65,16 @@ def lib():
     return _lib
 
 
-def check(rc: int) -> None:
+#: number of kernel launches issued through this binding (one per C call unless the caller
+#: says otherwise); bench.py reads it to report how many of our kernels ran in a timed region
+LAUNCHES = 0
+
+
+def check(rc: int, launches: int = 1) -> None:
+    global LAUNCHES
     if rc != 0:
         raise RuntimeError(lib().qttt_strerror(rc).decode())
+    LAUNCHES += launches
 
 
 def ptr(t):

@@ -195,7 +195,8 @@ class BatchedEnv:
                 st.wait_event(ready)
             _lib.check(self.lib.qttt_step_packed_host(
                 self.state.data_ptr(), action_coin_host.data_ptr(), result_host.data_ptr(),
-                self._d_act.data_ptr(), self._d_res16.data_ptr(), n, per, self._stream_array, n_streams))
+                self._d_act.data_ptr(), self._d_res16.data_ptr(), n, per, self._stream_array, n_streams),
+                launches=-(-n // per))
             for st in self._host_streams:
                 fin = torch.cuda.Event()
                 fin.record(st)
