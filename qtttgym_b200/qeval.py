@@ -17,7 +17,7 @@ from .env import _stream_ptr, pack_states
 
 
 def qeval_both(state, actions, *, want_states=True, want_boards=True, want_squares=False,
-               want_probs=True):
+               want_probs=True, out=None):
     """Both collapse outcomes of ``actions`` (uint8[N], 0..35) applied to packed ``state``
     (int32[N,4]).  Returns a dict with
 
@@ -26,11 +26,22 @@ def qeval_both(state, actions, *, want_states=True, want_boards=True, want_squar
     sq0/sq1      int8[N,9]  square each move index collapses into (-1: not in the measurement)
     closes       uint8[N]   1 when the action closes a cycle
     result_prob  f32[N,3]   P(X wins), P(O wins), P(neither) over the two equiprobable outcomes
+
+    ``out``: a dict returned by an earlier call with the same shapes; its tensors are reused
+    (no allocation, so the call can be captured in a CUDA graph).
     """
     lib = _lib.lib()
     dev, n = state.device, state.shape[0]
     actions = actions.to(torch.uint8).contiguous()
     assert actions.device == dev and actions.shape == (n,)
+    if out is not None:
+        g = lambda k: _lib.ptr(out.get(k))   # noqa: E731
+        with torch.cuda.device(dev):
+            _lib.check(lib.qttt_qeval_both(state.data_ptr(), actions.data_ptr(), g("next0"), g("next1"),
+                                           g("board0"), g("board1"), g("sq0"), g("sq1"),
+                                           out["closes"].data_ptr(), g("result_prob"), n,
+                                           _stream_ptr(dev)))
+        return out
     out = {"closes": torch.empty(n, dtype=torch.uint8, device=dev)}
     if want_states:
         out["next0"] = torch.empty_like(state)
