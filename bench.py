@@ -432,6 +432,27 @@ def run_b200(args):
     rsteps = int(box["r"][2].item())
     extra["config4_rollout_1024x256"] = {"playouts_per_s": 1024 * 256 / (ms * 1e-3) * world,
                                          "env_steps_per_s": rsteps / (ms * 1e-3) * world, "ms": ms}
+    # config 1 through the drop-in single-env adapter (qtttgym_b200.Env): the reference's own loop
+    if rank == 0:
+        import random as _random
+        single = Q.Env(device=dev, seed=seed)
+        prng = _random.Random(1)
+        t0 = time.perf_counter()
+        n_single = 0
+        for _ in range(300):
+            obs, _ = single.reset()
+            term = False
+            while not term:
+                board = obs["classical"]
+                legal = [p for p in Q.PAIRS if board[p[0]] == -1 and board[p[1]] == -1]
+                obs, _, term, _, _ = single.step(prng.choice(legal))
+                n_single += 1
+        dt = time.perf_counter() - t0
+        extra["config1_single_env_adapter"] = {
+            "env_steps_per_s": n_single / dt, "us_per_step": 1e6 * dt / n_single,
+            "note": "one env, one step per call through qtttgym_b200.Env (2 launches + 1 device->host copy + "
+                    "1 sync per step): latency-bound by construction, listed for completeness"}
+
     # MCTS search around the leaf evaluator (next row #1): 1024 mid-game roots, the reference's
     # default num_simulations=10, 500 rollouts per root; and the config-4 shape (256 playouts per leaf)
     for name, n_roll, n_sim in (("mcts_1024_roots_500x10", 500, 10), ("mcts_1024_roots_100x256", 100, 256)):
@@ -503,6 +524,15 @@ def main():
                     help="dram bytes per k_step launch from the committed ncu capture (profiles/)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl == "b200":
+        # launched directly with --gpus N: re-launch as one rank per GPU (what the driver does itself)
+        import socket
+        with socket.socket() as sock:
+            sock.bind(("127.0.0.1", 0))
+            port = sock.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference(args)
     else:

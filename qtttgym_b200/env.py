@@ -416,59 +416,130 @@ class Env:
     """Single-env adapter with the reference's exact return types (qtttgym/env.py:15-66):
     Python lists / tuples in ``obs``, a Python float reward (``-0.0`` / ``-1.0``), bools.
 
+    One ``step`` is two kernel launches (``qttt_step`` + ``qttt_observe``, all outputs written
+    into ONE 128-byte device record) and one device->host copy of that record: a single env
+    is latency-bound by construction (tens of microseconds per call); throughput comes from
+    ``BatchedEnv``.
+
     Deviations, all documented in DESIGN.md: ``obs["classical"]`` is a snapshot list, not an
     alias of live state (Q5); the collapse coin comes from Philox ``(seed, 0, len(moves))``
     unless ``coin`` is passed to ``step``; gymnasium spaces are not constructed (the reference's
     ``observation_space`` is wrong anyway, Q6)."""
 
-    def __init__(self, device="cuda", seed: int = 0):
-        self._batched = BatchedEnv(1, device=device, seed=seed)
-        self._device = self._batched.device
+    # byte offsets inside the record (state first: 16-byte aligned)
+    _STATE, _MASK, _REWARD, _DONE, _STATUS, _TURN, _NMOVES = 0, 16, 24, 28, 29, 30, 31
+    _CLASSICAL, _Q1, _Q2, _ROUNDS, _WINNER, _REWARD_P1, _MOVES = 32, 48, 58, 66, 68, 72, 80
+    _BYTES = 128
 
+    def __init__(self, device="cuda", seed: int = 0):
+        self.lib = _lib.lib()
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("qtttgym_b200 runs on CUDA devices only (no CPU fallback)")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self._device = dev
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._rec = torch.zeros(self._BYTES, dtype=torch.uint8, device=dev)
+        self._host = torch.zeros(self._BYTES, dtype=torch.uint8).pin_memory()
+        self._np = self._host.numpy()
+        self._d_act = torch.zeros(4, dtype=torch.int8, device=dev)       # (a, b) and the coin byte
+        self._h_act = torch.zeros(4, dtype=torch.int8).pin_memory()
+        self._h_act_np = self._h_act.numpy()
+        self._last_status = 0
+        self.reset()
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _p(self, off):
+        return self._rec.data_ptr() + off
+
+    def _refresh(self):
+        """qttt_observe into the record, one copy to the host, one synchronisation."""
+        st = _stream_ptr(self._device)
+        with torch.cuda.device(self._device):
+            _lib.check(self.lib.qttt_observe(self._p(self._STATE), self._p(self._CLASSICAL), self._p(self._MOVES),
+                                             self._p(self._NMOVES), self._p(self._Q1), self._p(self._Q2),
+                                             self._p(self._TURN), self._p(self._ROUNDS), self._p(self._REWARD_P1),
+                                             self._p(self._WINNER), None, 1, st))
+            self._host.copy_(self._rec, non_blocking=True)
+            torch.cuda.current_stream(self._device).synchronize()
+
+    def _observation(self):
+        r = self._np
+        i8 = r.view("int8")
+        q1 = i8[self._Q1:self._Q1 + 10].reshape(5, 2).tolist()
+        q2 = i8[self._Q2:self._Q2 + 8].reshape(4, 2).tolist()
+        return {"q_states_p1": [tuple(p) for p in q1 if p[0] >= 0],
+                "q_states_p2": [tuple(p) for p in q2 if p[0] >= 0],
+                "classical": i8[self._CLASSICAL:self._CLASSICAL + 9].tolist(),
+                "turn": int(r[self._TURN])}
+
+    # -- the reference API ------------------------------------------------------------------
     def reset(self, *, seed=None, options=None):
-        self._batched.reset()
+        """env.py:55-57 (seed / options ignored, Q4)."""
+        with torch.cuda.device(self._device):
+            _lib.check(self.lib.qttt_reset(self._p(self._STATE), self._p(self._MASK), 1,
+                                           _stream_ptr(self._device)))
+        self._refresh()
         return self._observation(), {}
 
     def step(self, action, verbose=False, coin=None):
+        """env.py:34-53."""
         try:
             a, b = int(action[0]), int(action[1])
         except Exception as e:              # env.py:41: anything raised becomes a no-op
             if verbose:
                 print("noop (i.e. invalid) move...", e)
             a = b = -1
-        a = a if -1 <= a <= 127 else -1
-        b = b if -1 <= b <= 127 else -1
-        act = torch.tensor([[a, b]], dtype=torch.int8, device=self._device)
-        ch = None if coin is None else torch.tensor([int(coin) & 1], dtype=torch.uint8,
-                                                    device=self._device)
-        _, reward, term, _, info = self._batched.step(act, ch)
-        if verbose and int(info["status"][0]) == 1:
+        self._h_act_np[0] = a if -1 <= a <= 127 else -1
+        self._h_act_np[1] = b if -1 <= b <= 127 else -1
+        self._h_act_np[2] = 0 if coin is None else int(coin) & 1
+        with torch.cuda.device(self._device):
+            self._d_act.copy_(self._h_act, non_blocking=True)
+            coin_ptr = None if coin is None else self._d_act.data_ptr() + 2
+            _lib.check(self.lib.qttt_step(self._p(self._STATE), self._d_act.data_ptr(), _lib.ACT_PAIR, coin_ptr,
+                                          self.seed, 0, self._p(self._REWARD), self._p(self._DONE),
+                                          self._p(self._MASK), self._p(self._STATUS), 1,
+                                          _stream_ptr(self._device)))
+        self._refresh()
+        r = self._np
+        self._last_status = int(r[self._STATUS])
+        if verbose and self._last_status == 1:
             print("noop (i.e. invalid) move...")
-        return self._observation(), float(reward[0].item()), bool(term[0].item()), False, {}
+        reward = float(r[self._REWARD:self._REWARD + 4].view("float32")[0])
+        return self._observation(), reward, bool(r[self._DONE]), False, {}
 
     def observ(self):
         return self._observation()
 
     def turn(self):
-        return int(self._batched.turn()[0].item())
+        """env.py:65-66."""
+        return int(self._np[self._NMOVES])
 
     def action_mask(self):
-        return self._batched.action_mask()[0].cpu().numpy()
+        """mcts.py:87-91: bool[36]."""
+        m = int(self._np[self._MASK:self._MASK + 8].view("uint64")[0])
+        import numpy as np
+        return np.array([(m >> k) & 1 for k in range(36)], dtype=bool)
 
     def render(self):
         """env.py:59-60 -> displayBoard (display.py:4-32)."""
-        o = self._batched.observation(extras=True)
-        print(render_text(o["classical"][0].tolist(), o["moves"][0].tolist(), int(o["n_moves"][0])))
-
-    def _observation(self):
-        o = self._batched.observation()
-        unpad = lambda t: [tuple(p) for p in t[0].tolist() if p[0] >= 0]   # noqa: E731
-        return {"q_states_p1": unpad(o["q_states_p1"]), "q_states_p2": unpad(o["q_states_p2"]),
-                "classical": o["classical"][0].tolist(), "turn": int(o["turn"][0].item())}
+        i8 = self._np.view("int8")
+        print(render_text(i8[self._CLASSICAL:self._CLASSICAL + 9].tolist(),
+                          i8[self._MOVES:self._MOVES + 18].reshape(9, 2).tolist(), self.turn()))
 
     def _reward(self):
         """env.py:87-112."""
-        return float(self._batched.observation(extras=True)["reward_p1"][0].item())
+        return float(self._np[self._REWARD_P1:self._REWARD_P1 + 4].view("float32")[0])
+
+    def winner(self):
+        """0 none / draw, 1 X, 2 O (mcts.py:52-65)."""
+        return int(self._np[self._WINNER])
+
+    @property
+    def state(self):
+        """the packed state as an int32[1,4] device tensor (a view of the record)"""
+        return self._rec[:16].view(torch.int32).view(1, 4)
 
 
 __all__ = ["BatchedEnv", "Env", "observe_states", "pack_states", "pack_actions", "unpack_result",
