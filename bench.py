@@ -422,6 +422,17 @@ def run_b200(args):
         "hbm_frac_at_33B": nb / (ms * 1e-3) * BYTES_PER_BOARD_QEVAL / 1e9 / peak,
         "note": "device time per launch (10 launches per CUDA-graph replay); a bare Python call costs ms_per_python_call"}
 
+    # the same kernel at a size that fills the GPU (2^24 boards: the trace's ply-4 positions)
+    qa_big = torch.where(actions[4] < 36, actions[4], torch.zeros_like(actions[4]))
+    big = Q.BatchedEnv(E, device=dev, seed=seed, game_base=rank * E)
+    for p in range(4):
+        big.step(actions[p], coins[p])
+    qout_big = Q.qeval_both(big.state, qa_big, want_states=False, want_probs=False)
+    ms = timed(lambda: Q.qeval_both(big.state, qa_big, out=qout_big), 10)
+    extra["qeval_16M_boards"] = {"boards_per_s": E / (ms * 1e-3) * world, "ms": ms,
+                                 "hbm_frac_at_33B": E / (ms * 1e-3) * BYTES_PER_BOARD_QEVAL / 1e9 / peak}
+    del qout_big
+
     # config 4: 1024 roots x 256 rollouts
     roots = qenv.state[:1024].clone()
     box = {}
@@ -478,6 +489,12 @@ def run_b200(args):
     ms = timed(lambda: Q.to_vector(qenv.state), 20)
     extra["to_vector_1M_states"] = {"ms": ms, "states_per_s": nb / (ms * 1e-3) * world,
                                     "gb_per_s": nb * 736 / (ms * 1e-3) / 1e9}
+    # the rollout kernel at a size that fills the GPU: 65,536 roots x 256 playouts
+    big_roots = big.state[:65536].clone()
+    ms = timed(lambda: box.__setitem__("rb", Q.rollout_eval(big_roots, 256, seed)), 5)
+    extra["rollout_65536x256"] = {"playouts_per_s": 65536 * 256 / (ms * 1e-3) * world,
+                                  "env_steps_per_s": int(box["rb"][2].item()) / (ms * 1e-3) * world, "ms": ms}
+    del big
     if cpu_c:
         extra["cpu_c_oracle"] = cpu_c
     if affinity is not None:
@@ -518,7 +535,7 @@ def main():
     ap.add_argument("--sweep-games", type=int, default=125_000_000, help="config-5 games per GPU")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=3.0, help="CPU baseline wall seconds per core")
-    ap.add_argument("--ref-games", type=int, default=1500, help="--impl reference: games per process per step")
+    ap.add_argument("--ref-games", type=int, default=4000, help="--impl reference: games per process per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per k_step launch from the committed ncu capture (profiles/)")
