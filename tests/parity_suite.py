@@ -467,3 +467,31 @@ def check_mcts_batch_vs_oracle(backend, n_roots=24, rollouts=80, sims=8, seed=42
         want = m.choose()
         assert int(ch[i]) == (255 if want is None else want)
     assert (s.errors() == 0).all()
+
+
+def check_rollout_frequencies_vs_reference_simulate(backend, n_rollouts=4096, seed=5):
+    """config 4, statistical bridge: per-root X / O / draw frequencies of the Philox-driven
+    rollouts vs counts recorded from the UNMODIFIED reference's MCTS._simulate with its own
+    randomness (tests/golden/simulate_freq_v1.json), 4.5 sigma per cell."""
+    cases = load_golden("simulate_freq_v1.json")
+    games = []
+    for case in cases:
+        g = O.Game()
+        for a, b, c in case["prefix"]:
+            g.place(a, b, lambda: c)
+        games.append(g)
+    n = len(games)
+    classical = np.array([g.board for g in games], np.int8)
+    moves = np.full((n, 9, 2), -1, np.int8)
+    nm = np.array([len(g.moves) for g in games], np.uint8)
+    for i, g in enumerate(games):
+        for a, b, idx in g.moves:
+            moves[i, idx] = (a, b)
+    tallies, _, _ = backend.games(n).load(classical, moves, nm).rollout(n_rollouts, seed)
+    for i, case in enumerate(cases):
+        m = case["playouts"]
+        for k, key in enumerate(("x", "o", "draw")):
+            p, q = tallies[i, k] / n_rollouts, case[key] / m
+            pooled = (tallies[i, k] + case[key]) / (n_rollouts + m)
+            sigma = max((pooled * (1 - pooled) * (1 / n_rollouts + 1 / m)) ** 0.5, 1e-9)
+            assert abs(p - q) < 4.5 * sigma or abs(p - q) < 1e-12, (i, key, p, q)

@@ -366,3 +366,7 @@ def test_mcts_player_beats_random(cuda):
     res = Q.eval_strats(Q.MCTSStrategy(rollouts=150, num_simulations=8, seed=5), Q.RandomStrategy(3),
                         num_games=1024, seed=11)
     assert res["strat1_wins"] > 0.72 * res["games"], res     # random-vs-random: X wins 58 %, O 29 %
+
+
+def test_rollout_frequencies_vs_reference_simulate(cuda):
+    S.check_rollout_frequencies_vs_reference_simulate(cuda, n_rollouts=65536)

@@ -83,3 +83,7 @@ def test_golden_mcts_search(emu):
 
 def test_mcts_batch_vs_oracle(emu):
     S.check_mcts_batch_vs_oracle(emu)
+
+
+def test_rollout_frequencies_vs_reference_simulate(emu):
+    S.check_rollout_frequencies_vs_reference_simulate(emu, n_rollouts=2048)

@@ -175,3 +175,28 @@ def test_population_statistics_match_reference():
     assert abs(stats[3] / n - ref["steps"] / m) < 0.03
     assert abs(stats[4] / n - ref["collapses"] / m) < 0.03
     assert hist[:5].sum() == 0 and hist.sum() == n
+
+
+def test_c_oracle_rollout_frequencies_vs_reference_simulate():
+    """The oracle's Philox playouts against counts from the reference's own MCTS._simulate."""
+    import parity_suite as S
+
+    class _Oracle:
+        name = "c-oracle"
+
+        class _G:
+            def __init__(self, n):
+                self.n = n
+
+            def load(self, classical, moves, n_moves):
+                self.g = CO.Games.from_arrays(classical, moves, n_moves)
+                return self
+
+            def rollout(self, n_rollouts, seed):
+                t, steps = self.g.rollout(n_rollouts, seed)
+                return t, None, steps
+
+        def games(self, n):
+            return self._G(n)
+
+    S.check_rollout_frequencies_vs_reference_simulate(_Oracle(), n_rollouts=8192)
