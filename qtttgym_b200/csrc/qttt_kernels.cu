@@ -506,13 +506,17 @@ k_mcts_sync(MctsNode* __restrict__ pool, int64_t capacity, int32_t* __restrict__
 // this kernel), so the grid-stride loops finish in one balanced wave.
 template <class Kernel>
 static int grid_for(Kernel kernel, int64_t n) {
-    int dev = 0, sms = 148, per_sm = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1)
-        per_sm = 4;
+    // resident blocks of this kernel on this kind of device: queried once per kernel (all
+    // devices of a box are the same part), so a launch costs no extra driver calls
+    static const int resident = [kernel]() {
+        int dev = 0, sms = 148, per_sm = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 4;
+        return sms * per_sm;
+    }();
     const int64_t want = (n + kThreads - 1) / kThreads;
-    const int64_t cap = (int64_t)sms * per_sm;
-    return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    return (int)(want < resident ? (want < 1 ? 1 : want) : resident);
 }
 static int check_launch() {
     const cudaError_t e = cudaGetLastError();
