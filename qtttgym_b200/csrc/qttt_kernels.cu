@@ -198,37 +198,66 @@ k_pack(qttt_state* __restrict__ state, const int8_t* __restrict__ classical_in,
 }
 
 // ------------------------------------------------------------------------------ features
-// GameState.to_vector for n games -> float[n][18][10].  720 B per game are written, so the
-// kernel is store-bound: a warp owns 32 consecutive games (23 KB of contiguous output) and
-// writes it as float4 vectors, lane-contiguous, fetching the owning game's state by shuffle.
-__global__ void __launch_bounds__(kThreads)
+// GameState.to_vector for n games -> float[n][18][10].  720 B per game are written and only
+// ~30 of the 180 values are non-zero, so: every lane zero-fills its own game's slot in shared
+// memory, scatters the non-zeros (one-hot of the board, 1/sqrt(9) marks of every move, the
+// "no live mark" column), and the warp then streams its 32 games (23 KB, contiguous in the
+// output) to HBM as lane-contiguous float4 vectors.
+constexpr int kFeatThreads = 64;            // 2 warps x 32 games x 188 floats = 48,128 B of shared memory
+constexpr int kFeatStride = 188;            // floats per game slot: 180 used; 188 = 4 (mod 32) x 7 keeps float4 accesses of 8 lanes on distinct banks
+
+template <int T>
+__device__ __forceinline__ void feature_move(float* slot, const State& s, uint32_t nm) {
+    if ((uint32_t)T < nm) {
+        const uint32_t E = edge<T>(s);
+        if (E) {
+            slot[(9 + ctz32(E)) * 10 + T] = 1.0f / 3.0f;
+            slot[(9 + flo32(E)) * 10 + T] = 1.0f / 3.0f;    // the same cell for the autofill entry (s, s, t)
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFeatThreads)
 k_features(const qttt_state* __restrict__ state, float* __restrict__ out, int64_t n) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * kThreads) >> 5;
+    __shared__ __align__(16) float buf[kFeatThreads / 32][32 * kFeatStride];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* mine = buf[warp] + lane * kFeatStride;
+    const int64_t warp0 = ((int64_t)blockIdx.x * kFeatThreads + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * kFeatThreads) >> 5;
     for (int64_t base = warp0 * 32; base < n; base += n_warps * 32) {
         const int64_t g = base + lane;
-        State s = empty_state();
-        if (g < n) s = load_state(state, g);
-        const uint32_t live = live_squares(s);
         const int games_here = (int)((n - base) < 32 ? (n - base) : 32);
-        float4* dst = reinterpret_cast<float4*>(out + base * 180);
-        for (int q0 = 0; q0 < games_here * 45; q0 += 32) {     // warp-uniform trip count (shuffles inside)
-            const int q = q0 + lane;
-            const bool valid = q < games_here * 45;
-            const int owner = valid ? q / 45 : 0, e0 = (q - owner * 45) * 4;
-            State t;
-            t.x = __shfl_sync(0xFFFFFFFFu, s.x, owner); t.y = __shfl_sync(0xFFFFFFFFu, s.y, owner);
-            t.z = __shfl_sync(0xFFFFFFFFu, s.z, owner); t.w = __shfl_sync(0xFFFFFFFFu, s.w, owner);
-            const uint32_t lv = __shfl_sync(0xFFFFFFFFu, live, owner);
-            float v[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t e = valid ? (uint32_t)(e0 + k) : 0u;
-                v[k] = feature_element(t, lv, e / 10u, e % 10u);
+        for (int k = 0; k < 45; ++k) reinterpret_cast<float4*>(mine)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g < n) {
+            const State s = load_state(state, g);
+            const uint32_t P0 = plane0(s), P1 = plane1(s), P2 = plane2(s), P3 = plane3(s);
+            const uint32_t C = P0 | P1 | P2 | P3, nm = n_moves(s);
+#pragma unroll
+            for (int sq = 0; sq < 9; ++sq) {                       // rows 0..8: one-hot of board[sq]
+                const int b = board_value(P0, P1, P2, P3, sq);
+                mine[sq * 10 + (b < 0 ? 9 : b)] = 1.0f;
             }
-            if (valid) dst[q] = make_float4(v[0], v[1], v[2], v[3]);
+            feature_move<0>(mine, s, nm); feature_move<1>(mine, s, nm); feature_move<2>(mine, s, nm);
+            feature_move<3>(mine, s, nm); feature_move<4>(mine, s, nm); feature_move<5>(mine, s, nm);
+            feature_move<6>(mine, s, nm); feature_move<7>(mine, s, nm); feature_move<8>(mine, s, nm);
+            uint32_t live = 0u;                                    // squares with an uncollapsed mark
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const uint32_t E = edge_dyn(s, (uint32_t)t);
+                live |= ((uint32_t)t < nm && !(E & C)) ? E : 0u;
+            }
+#pragma unroll
+            for (int sq = 0; sq < 9; ++sq)
+                if (!(live >> sq & 1u)) mine[(9 + sq) * 10 + 9] = 1.0f;
         }
+        __syncwarp();
+        float4* dst = reinterpret_cast<float4*>(out + base * 180);
+        for (int q = lane; q < games_here * 45; q += 32) {
+            const int owner = q / 45, r = q - owner * 45;
+            dst[q] = reinterpret_cast<const float4*>(buf[warp] + owner * kFeatStride)[r];
+        }
+        __syncwarp();
     }
 }
 
@@ -664,7 +693,13 @@ int qttt_features(const qttt_state* state, float* features, int64_t n, void* str
     if (n == 0) return QTTT_OK;
     if (!state || !features || n < 0) return QTTT_ERR_ARG;
     if (misaligned(state, 16) || misaligned(features, 16)) return QTTT_ERR_ALIGN;
-    k_features<<<grid_for(k_features, n), kThreads, 0, (cudaStream_t)stream>>>(state, features, n);
+    {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int64_t want = (n + kFeatThreads - 1) / kFeatThreads;
+        const int64_t cap = (int64_t)sms * 4;                     // 4 blocks of 47 KB fit one SM
+        k_features<<<(int)(want < cap ? want : cap), kFeatThreads, 0, (cudaStream_t)stream>>>(state, features, n);
+    }
     return check_launch();
 }
 
