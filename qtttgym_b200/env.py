@@ -223,6 +223,23 @@ class BatchedEnv:
                 self.step(actions[t], choices[t])
         return graph
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self):
+        """Everything needed to resume: the packed states plus the RNG keying.  (The reference
+        has no checkpointing of games; here the whole batch is one tensor.)"""
+        return {"state": self.state.clone(), "seed": self.seed, "game_base": self.game_base,
+                "num_envs": self.num_envs}
+
+    def load_state_dict(self, sd):
+        if int(sd["num_envs"]) != self.num_envs:
+            raise ValueError("checkpoint holds a different number of envs")
+        self.state.copy_(sd["state"].to(self.device))
+        self.seed, self.game_base = int(sd["seed"]), int(sd["game_base"])
+        # reward / done / mask are functions of the state: recompute them with a no-op step
+        noop = torch.full((self.num_envs,), 255, dtype=torch.uint8, device=self.device)
+        self.step(noop)
+        return self
+
     def turn(self):
         """env.py:65-66: len(moves) per env (uint8[N])."""
         return ((self.state[:, 0] >> 27) & 15).to(torch.uint8)

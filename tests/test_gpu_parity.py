@@ -370,3 +370,23 @@ def test_mcts_player_beats_random(cuda):
 
 def test_rollout_frequencies_vs_reference_simulate(cuda):
     S.check_rollout_frequencies_vs_reference_simulate(cuda, n_rollouts=65536)
+
+
+def test_checkpoint_resume(cuda, tmp_path):
+    """A batch saved mid-game and restored into a fresh env continues bit-identically
+    (Philox coins are keyed on (seed, game, ply), so no RNG state needs saving)."""
+    import torch
+    import qtttgym_b200 as Q
+    n = 5000
+    a = Q.BatchedEnv(n, seed=77, game_base=1000)
+    for _ in range(4):
+        a.step_random()
+    torch.save(a.state_dict(), tmp_path / "ckpt.pt")
+    b = Q.BatchedEnv(n, seed=0)
+    b.load_state_dict(torch.load(tmp_path / "ckpt.pt"))
+    assert torch.equal(a.done, b.done) and torch.equal(a.mask, b.mask)
+    assert torch.equal(a.reward.view(torch.int32), b.reward.view(torch.int32))
+    for _ in range(5):
+        a.step_random()
+        b.step_random()
+        assert torch.equal(a.state, b.state)
