@@ -390,3 +390,29 @@ def test_checkpoint_resume(cuda, tmp_path):
         a.step_random()
         b.step_random()
         assert torch.equal(a.state, b.state)
+
+
+def test_batched_env_api_surface(cuda):
+    """reset / step argument forms, obs modes, turn(), action_mask(), invalid()."""
+    import torch
+    import qtttgym_b200 as Q
+    env = Q.BatchedEnv(6, obs_mode="full", seed=1)
+    obs, info = env.reset(seed=99, options={"ignored": True})            # Q4: accepted and ignored
+    assert set(obs) == {"classical", "q_states_p1", "q_states_p2", "turn"}
+    assert bool((obs["classical"] == -1).all()) and int(info["action_mask"][0]) == (1 << 36) - 1
+    # python lists of pairs (any order), an illegal one, and an off-board one
+    obs, r, term, trunc, info = env.step([[0, 1], [1, 0], [3, 3], [8, 2], [9, 1], [-1, 4]])
+    assert env.invalid().tolist() == [False, False, True, False, True, True]
+    assert env.turn().tolist() == [1, 1, 0, 1, 0, 0] and obs["turn"].tolist() == [1, 1, 0, 1, 0, 0]
+    assert obs["q_states_p1"][0, 0].tolist() == [0, 1] and obs["q_states_p1"][1, 0].tolist() == [0, 1]
+    assert obs["q_states_p1"][3, 0].tolist() == [2, 8]
+    assert not bool(term.any()) and not bool(trunc.any())
+    assert r.view(torch.int32).tolist() == [-2147483648] * 6               # -0.0 everywhere (Q1)
+    assert env.action_mask().shape == (6, 36) and bool(env.action_mask().all())
+    # index form with wrong batch size / wrong device is refused
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(5, dtype=torch.uint8, device="cuda"))
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(6, dtype=torch.uint8))
+    packed = Q.BatchedEnv(6).reset()[0]
+    assert set(packed) == {"packed"} and packed["packed"].shape == (6, 4)
