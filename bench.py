@@ -481,11 +481,13 @@ def run_b200(args):
         del mc
 
     # a9 observation decode (env.py:68-85 + extras) and the to_vector feature encoder
-    ms = timed(lambda: env.observation(extras=True), 5)
+    obs_buf = env.observation(extras=True)
+    ms = timed(lambda: env.observation(extras=True, out=obs_buf), 10)
     extra["observe_all_outputs"] = {"ms": ms, "envs": E, "bytes_per_env": 16 + 90,
                                     "gb_per_s": E * (16 + 90) / (ms * 1e-3) / 1e9,
                                     "note": "qttt_observe, every output (classical, moves, n_moves, q lists, turn, "
-                                            "rounds, reward_p1, winner, bool mask); includes torch.empty of the outputs"}
+                                            "rounds, reward_p1, winner, bool mask) into preallocated tensors"}
+    del obs_buf
     ms = timed(lambda: Q.to_vector(qenv.state), 20)
     extra["to_vector_1M_states"] = {"ms": ms, "states_per_s": nb / (ms * 1e-3) * world,
                                     "gb_per_s": nb * 736 / (ms * 1e-3) / 1e9}

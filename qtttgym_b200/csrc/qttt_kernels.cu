@@ -141,6 +141,68 @@ __device__ __forceinline__ void copy_out(const uint8_t* sm, void* dst, int64_t b
     }
 }
 
+// One move slot of the observation: Board.moves[T] and, when the move is uncollapsed, its entry
+// in q_states_p1 / q_states_p2 (env.py:73-78).  T is a compile-time slot.
+template <int T>
+__device__ __forceinline__ void observe_move(const State& s, uint32_t nm, uint32_t C, int8_t* moves,
+                                             int8_t* q1, int8_t* q2, int& c1, int& c2) {
+    const uint32_t E = edge<T>(s);
+    const bool present = ((uint32_t)T < nm) & (E != 0u);
+    const int a = present ? ctz32(E) : -1, b = present ? flo32(E) : -1;
+    if (moves) { moves[2 * T] = (int8_t)a; moves[2 * T + 1] = (int8_t)b; }
+    if (present && !(E & C)) {
+        if (T & 1) { if (q2 && c2 < 4) { q2[2 * c2] = (int8_t)a; q2[2 * c2 + 1] = (int8_t)b; } ++c2; }
+        else       { if (q1 && c1 < 5) { q1[2 * c1] = (int8_t)a; q1[2 * c1 + 1] = (int8_t)b; } ++c1; }
+    }
+}
+
+// Device form of observe_game (qttt_core.cuh) writing one game's rows of the staging buffers:
+// same values, with compile-time move slots, word stores for the bool mask and the q-list
+// padding.  (The host emulation keeps the plain form; GPU tests diff this one against the
+// oracle on every output after every ply.)
+__device__ __forceinline__ void observe_row(const State& s, const Luts& L, int8_t* cl, int8_t* moves,
+                                            uint8_t* nmoves, int8_t* q1, int8_t* q2, uint8_t* turn,
+                                            int8_t* rounds, float* reward_p1, uint8_t* winner,
+                                            uint8_t* mask_bool) {
+    const uint32_t P0 = plane0(s), P1 = plane1(s), P2 = plane2(s), P3 = plane3(s);
+    const uint32_t C = P0 | P1 | P2 | P3;
+    const uint32_t nm = n_moves(s);
+    if (cl) {
+#pragma unroll
+        for (int sq = 0; sq < 9; ++sq) cl[sq] = (int8_t)board_value(P0, P1, P2, P3, sq);
+    }
+    if (nmoves) *nmoves = (uint8_t)nm;
+    if (turn) *turn = (uint8_t)(nm & 1u);                                     // env.py:83
+    if (q1) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) reinterpret_cast<uint16_t*>(q1)[k] = 0xFFFFu;   // (-1, -1) padding
+    }
+    if (q2) *reinterpret_cast<uint2*>(q2) = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+    int c1 = 0, c2 = 0;
+    observe_move<0>(s, nm, C, moves, q1, q2, c1, c2); observe_move<1>(s, nm, C, moves, q1, q2, c1, c2);
+    observe_move<2>(s, nm, C, moves, q1, q2, c1, c2); observe_move<3>(s, nm, C, moves, q1, q2, c1, c2);
+    observe_move<4>(s, nm, C, moves, q1, q2, c1, c2); observe_move<5>(s, nm, C, moves, q1, q2, c1, c2);
+    observe_move<6>(s, nm, C, moves, q1, q2, c1, c2); observe_move<7>(s, nm, C, moves, q1, q2, c1, c2);
+    observe_move<8>(s, nm, C, moves, q1, q2, c1, c2);
+    if (rounds || reward_p1 || winner) {
+        int px, po;
+        win_rounds(s, L, px, po);
+        if (rounds) { rounds[0] = (int8_t)px; rounds[1] = (int8_t)po; }
+        if (reward_p1) {                                                      // env.py:87-112
+            const int a = px < 0 ? 10 : px, b = po < 0 ? 10 : po;
+            *reward_p1 = a < b ? 1.0f : (b < a ? -1.0f : 0.0f);
+        }
+        if (winner) *winner = (uint8_t)winner_of(px, po);                     // mcts.py:52-65
+    }
+    if (mask_bool) {                                                          // mcts.py:87-91
+        const uint64_t lm = L.legal[~C & M9];
+        uint32_t* w = reinterpret_cast<uint32_t*>(mask_bool);
+#pragma unroll
+        for (int k = 0; k < 9; ++k)       // 4 mask bits -> 4 bool bytes: (bits * 0x204081) & 0x01010101
+            w[k] = (((uint32_t)(lm >> (4 * k)) & 15u) * 0x00204081u) & 0x01010101u;
+    }
+}
+
 // Env._observation & co. for n games.  Every output is a few BYTES per game at an odd stride
 // (9, 18, 10, 8, 36 ...), so each block of 256 games is decoded into shared memory first and
 // then written out with coalesced 16-byte stores.
@@ -166,14 +228,16 @@ k_observe(const qttt_state* __restrict__ state, int8_t* __restrict__ classical_o
         const int valid = (int)((n - block_start) < kThreads ? (n - block_start) : kThreads);
         const int t = threadIdx.x;
         if (t < valid)
-            observe_game(load_state(state, block_start + t), L,
-                         classical_out ? reinterpret_cast<int8_t*>(st_classical) : nullptr,
-                         moves ? reinterpret_cast<int8_t*>(st_moves) : nullptr, nmoves ? st_n : nullptr,
-                         q1 ? reinterpret_cast<int8_t*>(st_q1) : nullptr,
-                         q2 ? reinterpret_cast<int8_t*>(st_q2) : nullptr, turn ? st_turn : nullptr,
-                         rounds ? reinterpret_cast<int8_t*>(st_rounds) : nullptr,
-                         reward_p1 ? st_reward : nullptr, winner ? st_winner : nullptr,
-                         mask_bool ? st_mask : nullptr, t);
+            observe_row(load_state(state, block_start + t), L,
+                        classical_out ? reinterpret_cast<int8_t*>(st_classical) + 9 * t : nullptr,
+                        moves ? reinterpret_cast<int8_t*>(st_moves) + 18 * t : nullptr,
+                        nmoves ? st_n + t : nullptr,
+                        q1 ? reinterpret_cast<int8_t*>(st_q1) + 10 * t : nullptr,
+                        q2 ? reinterpret_cast<int8_t*>(st_q2) + 8 * t : nullptr,
+                        turn ? st_turn + t : nullptr,
+                        rounds ? reinterpret_cast<int8_t*>(st_rounds) + 2 * t : nullptr,
+                        reward_p1 ? st_reward + t : nullptr, winner ? st_winner + t : nullptr,
+                        mask_bool ? st_mask + 36 * t : nullptr);
         __syncthreads();
         copy_out<9>(st_classical, classical_out, block_start, valid);
         copy_out<18>(st_moves, moves, block_start, valid);

@@ -247,12 +247,12 @@ class BatchedEnv:
     def observ(self):
         return self.observation()
 
-    def observation(self, extras: bool = False):
+    def observation(self, extras: bool = False, out=None):
         """env.py:68-85 as tensors: ``classical`` int8[N,9], ``q_states_p1`` int8[N,5,2],
         ``q_states_p2`` int8[N,4,2] (padded with -1), ``turn`` uint8[N]; with ``extras`` also
         ``moves`` int8[N,9,2], ``n_moves``, ``rounds`` (check_win), ``reward_p1`` (Env._reward),
         ``winner`` (0 none, 1 X, 2 O) and ``action_mask`` bool[N,36]."""
-        return observe_states(self.state, extras=extras)
+        return observe_states(self.state, extras=extras, out=out)
 
     def winner(self):
         """mcts.py:52-65 / strat_eval.py:21-32 per env: uint8[N], 0 none or draw, 1 X, 2 O."""
@@ -348,9 +348,20 @@ def unpack_result(result):
     return reward, terminated, mask, status
 
 
-def observe_states(state, extras: bool = False):
+def observe_states(state, extras: bool = False, out=None):
+    """``out``: the dict returned by an earlier call with the same shapes and ``extras`` -- its
+    tensors are overwritten instead of allocating new ones."""
     lib = _lib.lib()
     n, dev = state.shape[0], state.device
+    if out is not None:
+        mask_u8 = out["action_mask"].view(torch.uint8) if "action_mask" in out else None
+        with torch.cuda.device(dev):
+            _lib.check(lib.qttt_observe(
+                state.data_ptr(), out["classical"].data_ptr(), _lib.ptr(out.get("moves")),
+                _lib.ptr(out.get("n_moves")), out["q_states_p1"].data_ptr(), out["q_states_p2"].data_ptr(),
+                out["turn"].data_ptr(), _lib.ptr(out.get("rounds")), _lib.ptr(out.get("reward_p1")),
+                _lib.ptr(out.get("winner")), _lib.ptr(mask_u8), n, _stream_ptr(dev)))
+        return out
     e8 = lambda *shape: torch.empty(shape, dtype=torch.int8, device=dev)   # noqa: E731
     out = {"classical": e8(n, 9), "q_states_p1": e8(n, 5, 2), "q_states_p2": e8(n, 4, 2),
            "turn": torch.empty(n, dtype=torch.uint8, device=dev)}
