@@ -1,5 +1,4 @@
 """CPU: the C-ABI library loads and exports every symbol include/*.h declares (no compute)."""
-import ctypes as C
 import glob
 import os
 import re

@@ -185,7 +185,6 @@ def test_square_probabilities(cuda):
 
 
 def test_error_codes(cuda):
-    import ctypes as C
     import torch
     import qtttgym_b200._lib as L
     lib = L.lib()
