@@ -437,9 +437,11 @@ def run_b200(args):
     roots = qenv.state[:1024].clone()
     box = {}
 
+    box["r"] = Q.rollout_eval(roots, 256, seed)
+
     def roll():
-        box["r"] = Q.rollout_eval(roots, 256, seed)
-    ms = timed(roll, 20)
+        Q.rollout_eval(roots, 256, seed, out=box["r"])
+    ms = timed(roll, 50)
     rsteps = int(box["r"][2].item())
     extra["config4_rollout_1024x256"] = {"playouts_per_s": 1024 * 256 / (ms * 1e-3) * world,
                                          "env_steps_per_s": rsteps / (ms * 1e-3) * world, "ms": ms}
@@ -493,7 +495,8 @@ def run_b200(args):
                                     "gb_per_s": nb * 736 / (ms * 1e-3) / 1e9}
     # the rollout kernel at a size that fills the GPU: 65,536 roots x 256 playouts
     big_roots = big.state[:65536].clone()
-    ms = timed(lambda: box.__setitem__("rb", Q.rollout_eval(big_roots, 256, seed)), 5)
+    box["rb"] = Q.rollout_eval(big_roots, 256, seed)
+    ms = timed(lambda: Q.rollout_eval(big_roots, 256, seed, out=box["rb"]), 20)
     extra["rollout_65536x256"] = {"playouts_per_s": 65536 * 256 / (ms * 1e-3) * world,
                                   "env_steps_per_s": int(box["rb"][2].item()) / (ms * 1e-3) * world, "ms": ms}
     del big

@@ -8,8 +8,9 @@ Random choices of the reference and their keyed replacements (Philox4x32-10, key
       counter (id_lo, id_hi, depth, 2), id = root * 2^32 + rollout;  index = x1 & 1 (two children)
   * _simulate: np.random.choice(node.actions, p=uniform)     mcts.py:193, 287-292
                np.random.choice(nodes)                       mcts.py:195
-      counter (id_lo, id_hi, len(node.moves), 3), id = (root * 2^32 + rollout) * 4096 + sim;
-      action = floor(x0 * m / 2^32)-th legal action, child index = x1 & 1
+      the per-ply draw of oracle/qttt_oracle.py policy_draw(seed, id, len(node.moves), 3) with
+      id = (root * 2^32 + rollout) * 4096 + sim (one Philox block per two plies):
+      action = floor(word * m / 2^32)-th legal action, child index = coin word & 1
   * QEvalClassic.eval's stdlib coin inside MCTS._step (mcts.py:242, 259): forced to 0 then 1,
     so children[a] == [coin-0 outcome, coin-1 outcome].
 """
@@ -104,7 +105,7 @@ class MCTS:
                 leaf.P = {a: 1 / len(leaf.actions) for a in leaf.actions}   # mcts.py:189-191, 287-289
             g = leaf.game.clone()
             while True:
-                x = _draw(self.seed, ident, len(g.moves), DOMAIN_SIM)
+                x = O.policy_draw(self.seed, ident, len(g.moves), DOMAIN_SIM)
                 act = O.policy_action(g.legal_mask(), x[0])
                 a, b = O.PAIRS[act]
                 bit = x[1] & 1
@@ -196,7 +197,7 @@ class KeyedNumpy:
             self.depth += 1
             return seq[x[1] & 1] if len(seq) == 2 else seq[0]
         if p is not None:                                          # sample_action, mcts.py:291-292
-            x = _draw(self.seed, base * MAX_SIMS + self.sim, self.sim_len, DOMAIN_SIM)
+            x = O.policy_draw(self.seed, base * MAX_SIMS + self.sim, self.sim_len, DOMAIN_SIM)
             self.pending = x
             return seq[(x[0] * len(seq)) >> 32]                    # seq = node.actions, ascending
         x = self.pending                                           # child choice of the same ply

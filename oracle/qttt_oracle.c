@@ -298,8 +298,18 @@ static inline int nth_set(uint64_t m, int k) {
     return -1;
 }
 
-/* mcts.py:185-208 (_simulate) with the Philox policy: action = floor(x0*m/2^32)-th legal
- * action, coin = x1 & 1, counter (game_lo, game_hi, ply, domain), key = seed.
+/* The random draw of one ply: one Philox block, counter (game_lo, game_hi, ply >> 1, domain),
+ * key = seed, serves two consecutive plies: even ply -> (x0, x1 & 1), odd ply -> (x2, x3 & 1). */
+static inline void ply_draw(uint64_t seed, uint64_t gid, uint32_t ply, uint32_t domain,
+                            uint32_t *word, uint32_t *coin) {
+    uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), ply >> 1, domain};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    *word = (ply & 1u) ? c[2] : c[0];
+    *coin = ((ply & 1u) ? c[3] : c[1]) & 1u;
+}
+
+/* mcts.py:185-208 (_simulate) with the Philox policy: action = floor(word*m/2^32)-th legal
+ * action and the coin from ply_draw(seed, game, len(moves), domain).
  * Terminal per mcts.py:52-65.  Returns winner; *steps / *cols incremented. */
 static int playout(orc_game *g, uint64_t seed, uint64_t gid, uint32_t domain,
                    int64_t *steps, int64_t *cols) {
@@ -307,13 +317,13 @@ static int playout(orc_game *g, uint64_t seed, uint64_t gid, uint32_t domain,
     for (;;) {
         int w = orc_winner(g);
         if (w != 0 || g->n_moves == 9) return w;
-        uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)g->n_moves, domain};
-        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        uint32_t word, coin;
+        ply_draw(seed, gid, (uint32_t)g->n_moves, domain, &word, &coin);
         uint64_t mask = orc_legal_mask(g);
         int m = __builtin_popcountll(mask);
-        int act = nth_set(mask, (int)(((uint64_t)c[0] * (uint64_t)m) >> 32));
+        int act = nth_set(mask, (int)(((uint64_t)word * (uint64_t)m) >> 32));
         int col = 0;
-        orc_place(g, PAIR[act][0], PAIR[act][1], (int)(c[1] & 1), &col);
+        orc_place(g, PAIR[act][0], PAIR[act][1], (int)coin, &col);
         ++*steps; *cols += col;
     }
 }
@@ -368,13 +378,13 @@ int orc_playout_trace(orc_game *g, uint64_t seed, uint64_t gid, uint32_t domain,
     for (;;) {
         int w = orc_winner(g);
         if (w != 0 || g->n_moves == 9) { *n_out = n; return w; }
-        uint32_t c[4] = {(uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)g->n_moves, domain};
-        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        uint32_t word, coin;
+        ply_draw(seed, gid, (uint32_t)g->n_moves, domain, &word, &coin);
         uint64_t mask = orc_legal_mask(g);
         int m = __builtin_popcountll(mask);
-        int act = nth_set(mask, (int)(((uint64_t)c[0] * (uint64_t)m) >> 32));
-        acts[n] = (uint8_t)act; coins[n] = (uint8_t)(c[1] & 1); ++n;
-        orc_place(g, PAIR[act][0], PAIR[act][1], (int)(c[1] & 1), 0);
+        int act = nth_set(mask, (int)(((uint64_t)word * (uint64_t)m) >> 32));
+        acts[n] = (uint8_t)act; coins[n] = (uint8_t)coin; ++n;
+        orc_place(g, PAIR[act][0], PAIR[act][1], (int)coin, 0);
     }
 }
 

@@ -301,10 +301,12 @@ DOMAIN_ROLLOUT = 1   # rollout leaf evaluation
 
 
 def policy_draw(seed: int, game_id: int, ply: int, domain: int) -> tuple[int, int]:
-    """(x0, x1) of Philox4x32-10 with counter (game_lo, game_hi, ply, domain), key = seed."""
-    x = philox4x32((game_id & _U32, (game_id >> 32) & _U32, ply, domain),
+    """The random draw of one ply, (action word, coin word): one Philox4x32-10 block with
+    counter (game_lo, game_hi, ply >> 1, domain) and key = seed serves two consecutive plies --
+    the even ply takes (x0, x1), the odd ply (x2, x3).  Bit 0 of the coin word is the coin."""
+    x = philox4x32((game_id & _U32, (game_id >> 32) & _U32, ply >> 1, domain),
                    (seed & _U32, (seed >> 32) & _U32))
-    return x[0], x[1]
+    return (x[2], x[3]) if ply & 1 else (x[0], x[1])
 
 
 def nth_set_bit(mask: int, k: int) -> int:

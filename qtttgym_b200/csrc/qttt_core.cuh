@@ -461,14 +461,49 @@ QTTT_HD uint32_t policy_edge(uint32_t free_set, uint32_t x0, const Luts& L) {
     return m ? e : 0u;
 }
 
+// The random draw of one ply: (action word, coin bit) = f(seed, game, ply, domain).  One
+// Philox4x32-10 block, counter (game_lo, game_hi, ply >> 1, domain), serves TWO consecutive
+// plies: the even ply takes (x0, x1 & 1), the odd ply (x2, x3 & 1).
+QTTT_HD void ply_draw(uint64_t seed, uint64_t game, uint32_t ply, uint32_t domain,
+                      uint32_t& action_word, uint32_t& coin) {
+    uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = ply >> 1, c3 = domain;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    action_word = (ply & 1u) ? c2 : c0;
+    coin = ((ply & 1u) ? c3 : c1) & 1u;
+}
+
+// The same draw for code that walks the plies of one game in order (playouts): the block
+// computed at an even ply is kept for the odd ply that follows.
+struct DrawCache { uint32_t word, coin, ply; };
+QTTT_HD DrawCache empty_draw_cache() { return DrawCache{0u, 0u, 0xFFFFFFFFu}; }
+QTTT_HD void ply_draw_cached(uint64_t seed, uint64_t game, uint32_t ply, uint32_t domain, DrawCache& cache,
+                             uint32_t& action_word, uint32_t& coin) {
+    if (cache.ply == ply) {
+        action_word = cache.word;
+        coin = cache.coin;
+        return;
+    }
+    uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = ply >> 1, c3 = domain;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    if (ply & 1u) {
+        action_word = c2;
+        coin = c3 & 1u;
+    } else {
+        action_word = c0;
+        coin = c1 & 1u;
+        cache.word = c2;
+        cache.coin = c3 & 1u;
+        cache.ply = ply + 1u;
+    }
+}
+
 // uniform-random legal action + coin for (seed, game, ply, domain)
 QTTT_HD void policy_draw(uint64_t seed, uint64_t game, uint32_t ply, uint32_t domain,
                          uint64_t legal_mask, uint32_t& action, uint32_t& coin) {
-    uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = ply, c3 = domain;
-    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint32_t word;
+    ply_draw(seed, game, ply, domain, word, coin);
     const uint32_t m = (uint32_t)popc32((uint32_t)legal_mask) + (uint32_t)popc32((uint32_t)(legal_mask >> 32));
-    action = m ? nth_set_bit36(legal_mask, mulhi32(c0, m)) : 255u;
-    coin = c1 & 1u;
+    action = m ? nth_set_bit36(legal_mask, mulhi32(word, m)) : 255u;
 }
 
 
@@ -508,10 +543,10 @@ QTTT_HD uint32_t finished_winner(const State& s, const Luts& L, bool& terminal) 
 // One ply of MCTS._simulate (mcts.py:188-196): action ~ U(legal), coin ~ U{0,1}.
 // Needs the policy tables (kLutPolicyBytes staged).
 QTTT_HD StepResult playout_ply(State& s, uint32_t C, uint64_t seed, uint64_t game, uint32_t domain,
-                               const Luts& L) {
-    uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = n_moves(s), c3 = domain;
-    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
-    return step_core(s, policy_edge(~C & M9, c0, L), c1 & 1u, L);
+                               const Luts& L, DrawCache& cache) {
+    uint32_t word, coin;
+    ply_draw_cached(seed, game, n_moves(s), domain, cache, word, coin);
+    return step_core(s, policy_edge(~C & M9, word, L), coin, L);
 }
 
 QTTT_HD int board_value(uint32_t P0, uint32_t P1, uint32_t P2, uint32_t P3, int sq) {
@@ -663,8 +698,9 @@ QTTT_HD uint32_t playout_game(State s, uint64_t seed, uint64_t game, uint32_t do
                               uint32_t& steps, uint32_t& collapses) {
     uint32_t C = classical(s);
     bool terminal = (any_line(s, C, L) != 0u) | (n_moves(s) >= 9u);          // mcts.py:52-65
+    DrawCache cache = empty_draw_cache();
     while (!terminal) {
-        const StepResult r = playout_ply(s, C, seed, game, domain, L);
+        const StepResult r = playout_ply(s, C, seed, game, domain, L, cache);
         C = r.classical;
         ++steps;
         collapses += r.collapsed;

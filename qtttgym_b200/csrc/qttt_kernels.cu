@@ -86,10 +86,8 @@ k_step(qttt_state* __restrict__ state, const uint8_t* __restrict__ action,
             if (coin) {
                 c = *elem(coin, i) & 1u;
             } else {
-                const uint64_t game = game_base + (uint64_t)i;
-                uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = n_moves(s), c3 = 0u;
-                philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
-                c = c1 & 1u;
+                uint32_t word;
+                ply_draw(seed, game_base + (uint64_t)i, n_moves(s), 0u, word, c);
             }
         }
         const StepResult r = step_core(s, enew, c, L);
@@ -343,9 +341,9 @@ k_qeval_both(const qttt_state* __restrict__ state, const uint8_t* __restrict__ a
 }
 
 // ------------------------------------------------------------------------------ playouts
-// K4: block per root, rollouts strided over the block's threads.
+// K4: a block works on one root at a time (rollouts strided over its threads).
 __global__ void __launch_bounds__(kThreads)
-k_rollout(const qttt_state* __restrict__ roots, int32_t n_rollouts, uint64_t seed,
+k_rollout(const qttt_state* __restrict__ roots, int64_t n_roots, int32_t n_rollouts, uint64_t seed,
           int32_t* __restrict__ tallies, float* __restrict__ value,
           unsigned long long* __restrict__ steps_total) {
     __shared__ __align__(16) uint8_t smem[kLutPolicyBytes];
@@ -353,37 +351,41 @@ k_rollout(const qttt_state* __restrict__ roots, int32_t n_rollouts, uint64_t see
     __shared__ unsigned long long sh_steps;
     stage_luts(smem, kLutPolicyBytes);
     const Luts L = luts_from_image(smem);
-    if (threadIdx.x < 3) sh_tally[threadIdx.x] = 0;
-    if (threadIdx.x == 0) sh_steps = 0ull;
-    __syncthreads();
-
-    const int64_t root = blockIdx.x;
-    const State s0 = load_state(roots, root);
-    int xw = 0, ow = 0, dr = 0;
-    uint32_t steps = 0, cols = 0;
-    for (int32_t j = threadIdx.x; j < n_rollouts; j += kThreads) {
-        const uint64_t game = (uint64_t)root * (uint64_t)n_rollouts + (uint64_t)j;
-        const uint32_t w = playout_game(s0, seed, game, 1u, L, steps, cols);
-        xw += w == 1u; ow += w == 2u; dr += w == 0u;
-    }
-    xw = __reduce_add_sync(0xFFFFFFFFu, xw);
-    ow = __reduce_add_sync(0xFFFFFFFFu, ow);
-    dr = __reduce_add_sync(0xFFFFFFFFu, dr);
-    steps = __reduce_add_sync(0xFFFFFFFFu, steps);
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&sh_tally[0], xw); atomicAdd(&sh_tally[1], ow); atomicAdd(&sh_tally[2], dr);
-        atomicAdd(&sh_steps, (unsigned long long)steps);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (tallies) { tallies[3 * root] = sh_tally[0]; tallies[3 * root + 1] = sh_tally[1]; tallies[3 * root + 2] = sh_tally[2]; }
-        if (value) {
-            // mcts.py:171,173: sum(r if leaf.turn else -r) / num_simulations
-            const float r = (float)(sh_tally[0] - sh_tally[1]) / (float)n_rollouts;
-            value[root] = (plies_of(s0) & 1u) ? -r : r;
+    unsigned long long block_steps = 0ull;
+    // persistent blocks: the tables are staged once per block, roots are taken grid-stride
+    for (int64_t root = blockIdx.x; root < n_roots; root += gridDim.x) {
+        if (threadIdx.x < 3) sh_tally[threadIdx.x] = 0;
+        if (threadIdx.x == 0) sh_steps = 0ull;
+        __syncthreads();
+        const State s0 = load_state(roots, root);
+        int xw = 0, ow = 0, dr = 0;
+        uint32_t steps = 0, cols = 0;
+        for (int32_t j = threadIdx.x; j < n_rollouts; j += kThreads) {
+            const uint64_t game = (uint64_t)root * (uint64_t)n_rollouts + (uint64_t)j;
+            const uint32_t w = playout_game(s0, seed, game, 1u, L, steps, cols);
+            xw += w == 1u; ow += w == 2u; dr += w == 0u;
         }
-        if (steps_total) atomicAdd(steps_total, sh_steps);
+        xw = __reduce_add_sync(0xFFFFFFFFu, xw);
+        ow = __reduce_add_sync(0xFFFFFFFFu, ow);
+        dr = __reduce_add_sync(0xFFFFFFFFu, dr);
+        steps = __reduce_add_sync(0xFFFFFFFFu, steps);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&sh_tally[0], xw); atomicAdd(&sh_tally[1], ow); atomicAdd(&sh_tally[2], dr);
+            atomicAdd(&sh_steps, (unsigned long long)steps);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (tallies) { tallies[3 * root] = sh_tally[0]; tallies[3 * root + 1] = sh_tally[1]; tallies[3 * root + 2] = sh_tally[2]; }
+            if (value) {
+                // mcts.py:171,173: sum(r if leaf.turn else -r) / num_simulations
+                const float r = (float)(sh_tally[0] - sh_tally[1]) / (float)n_rollouts;
+                value[root] = (plies_of(s0) & 1u) ? -r : r;
+            }
+            block_steps += sh_steps;
+        }
+        __syncthreads();
     }
+    if (threadIdx.x == 0 && steps_total && block_steps) atomicAdd(steps_total, block_steps);
 }
 
 // K5: self-play sweep from the empty board, entirely in registers.  The 32 games of a warp are
@@ -407,13 +409,14 @@ k_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, unsigned long long* __r
         if (!__any_sync(0xFFFFFFFFu, active)) break;
         State s = empty_state();
         uint32_t C = 0u, len = 0u;
+        DrawCache cache = empty_draw_cache();
         const bool mine = active;
         games += active;
 #pragma unroll 1
         for (uint32_t ply = 0; ply < 9u; ++ply) {
             if (!__any_sync(0xFFFFFFFFu, active)) break;
             if (active) {
-                const StepResult r = playout_ply(s, C, seed, (uint64_t)g, 0u, L);
+                const StepResult r = playout_ply(s, C, seed, (uint64_t)g, 0u, L, cache);
                 C = r.classical;
                 co += r.collapsed;
                 len = ply + 1u;
@@ -800,8 +803,8 @@ int qttt_rollout(const qttt_state* roots, int64_t n_roots, int32_t n_rollouts, u
     if (misaligned(roots, 16) || misaligned(tallies, 4) || misaligned(value, 4) || misaligned(steps_total, 8))
         return QTTT_ERR_ALIGN;
     if (n_roots == 0) return QTTT_OK;
-    k_rollout<<<(int)n_roots, kThreads, 0, (cudaStream_t)stream>>>(
-        roots, n_rollouts, seed, tallies, value, reinterpret_cast<unsigned long long*>(steps_total));
+    k_rollout<<<grid_for(k_rollout, n_roots * kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        roots, n_roots, n_rollouts, seed, tallies, value, reinterpret_cast<unsigned long long*>(steps_total));
     return check_launch();
 }
 

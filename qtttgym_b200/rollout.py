@@ -11,19 +11,24 @@ from .env import _stream_ptr
 STAT_NAMES = ("x_wins", "o_wins", "draws", "env_steps", "collapses", "games")
 
 
-def rollout_eval(roots, n_rollouts: int, seed: int = 0):
+def rollout_eval(roots, n_rollouts: int, seed: int = 0, out=None):
     """``n_rollouts`` uniform-random playouts from every packed root (int32[R,4]).
 
     Returns ``(tallies int32[R,3] = (X wins, O wins, draws), value f32[R], env_steps int)``;
     ``value`` is the mean playout reward from the root's side to move, exactly the quantity
     ``MCTS._rollout`` backs up (mcts.py:168-173).  Playout j of root r draws from Philox with
-    game id ``r * n_rollouts + j`` in domain 1.
+    game id ``r * n_rollouts + j`` in domain 1.  ``out``: a tuple returned by an earlier call
+    with the same number of roots, reused instead of allocating (``env_steps`` is zeroed).
     """
     lib = _lib.lib()
     dev, r = roots.device, roots.shape[0]
-    tallies = torch.empty((r, 3), dtype=torch.int32, device=dev)
-    value = torch.empty(r, dtype=torch.float32, device=dev)
-    steps = torch.zeros(1, dtype=torch.int64, device=dev)
+    if out is not None:
+        tallies, value, steps = out
+        steps.zero_()
+    else:
+        tallies = torch.empty((r, 3), dtype=torch.int32, device=dev)
+        value = torch.empty(r, dtype=torch.float32, device=dev)
+        steps = torch.zeros(1, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.qttt_rollout(roots.data_ptr(), r, int(n_rollouts),
                                     int(seed) & 0xFFFFFFFFFFFFFFFF, tallies.data_ptr(),

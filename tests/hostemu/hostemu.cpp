@@ -33,10 +33,8 @@ int emu_step(State* state, const void* action, int fmt, const uint8_t* coin, uin
         else enew = pair_to_edge(act[2 * i], act[2 * i + 1]);
         if (coin) c = coin[i] & 1u;
         else {
-            const uint64_t game = game_base + (uint64_t)i;
-            uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = n_moves(s), c3 = 0u;
-            philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
-            c = c1 & 1u;
+            uint32_t word;
+            ply_draw(seed, game_base + (uint64_t)i, n_moves(s), 0u, word, c);
         }
         const StepResult r = step_core(s, enew, c, L);
         state[i] = s;
