@@ -293,12 +293,16 @@ QTTT_HD void sweep(uint32_t x, uint32_t y, uint32_t z, uint32_t& R, uint32_t& W,
 // of the step kernel, so (a) the sweep touches only the n move slots that exist -- n is
 // uniform across a warp when a batch is stepped in lock-step, so the switch does not diverge
 // -- and (b) bit placement is written as multiply-add by table constants (IMAD pipe).
-template <bool kTargets = false>
-QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, const Luts& L, uint32_t* tgt = nullptr) {
+//
+// kKnownC: the caller already holds the classical set of `s` (playouts carry it from the
+// previous step's result) and passes it as `known_c`.
+template <bool kTargets = false, bool kKnownC = false>
+QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, const Luts& L, uint32_t* tgt = nullptr,
+                             uint32_t known_c = 0u) {
     const uint32_t x = s.x, y = s.y, z = s.z, w = s.w;
     const uint32_t n = (x >> 27) & 15u;
     const NRow row = L.nrow[n];
-    const uint32_t C = classical(s);
+    const uint32_t C = kKnownC ? known_c : classical(s);
     const bool legal = (enew != 0u) & ((enew & C) == 0u) & (n < 9u);   // board.py:10-15
     enew = legal ? enew : 0u;
 
@@ -546,7 +550,7 @@ QTTT_HD StepResult playout_ply(State& s, uint32_t C, uint64_t seed, uint64_t gam
                                const Luts& L, DrawCache& cache) {
     uint32_t word, coin;
     ply_draw_cached(seed, game, n_moves(s), domain, cache, word, coin);
-    return step_core(s, policy_edge(~C & M9, word, L), coin, L);
+    return step_core<false, true>(s, policy_edge(~C & M9, word, L), coin, L, nullptr, C);
 }
 
 QTTT_HD int board_value(uint32_t P0, uint32_t P1, uint32_t P2, uint32_t P3, int sq) {
