@@ -85,6 +85,13 @@ QTTT_API int qttt_step(qttt_state* state, const void* action, int action_format,
               uint64_t seed, uint64_t game_base, float* reward, uint8_t* done, uint64_t* mask,
               uint8_t* status, int64_t n, void* stream);
 
+/* Env.reset followed by the first Env.step (env.py:55-57 then 34-53) in one launch: the games
+ * start from the empty board, so the state is written but not read.  Same arguments and
+ * outputs as qttt_step. */
+QTTT_API int qttt_reset_step(qttt_state* state, const void* action, int action_format,
+                             const uint8_t* coin, uint64_t seed, uint64_t game_base, float* reward,
+                             uint8_t* done, uint64_t* mask, uint8_t* status, int64_t n, void* stream);
+
 /* qttt_step with compact I/O, for callers whose buffers live in HOST memory (there the PCIe
  * link, not HBM, is the bound: 3 bytes per game cross it instead of 15).
  *   action_coin uint8[n]  : bits 0..5 action index (QTTT_ACT_INDEX; 36..63 = illegal),

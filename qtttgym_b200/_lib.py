@@ -20,6 +20,7 @@ _SIGNATURES = {
     "qttt_strerror": ([_int], C.c_char_p),
     "qttt_reset": ([_vp, _vp, _i64, _vp], _int),
     "qttt_step": ([_vp, _vp, _int, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _i64, _vp], _int),
+    "qttt_reset_step": ([_vp, _vp, _int, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _i64, _vp], _int),
     "qttt_step_packed": ([_vp, _vp, _vp, _i64, _vp], _int),
     "qttt_step_packed_host": ([_vp, _vp, _vp, _vp, _vp, _i64, _i64, C.POINTER(C.c_void_p), _int], _int),
     "qttt_step_random": ([_vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp], _int),

@@ -529,7 +529,7 @@ QTTT_HD void emit_step_outputs(const State& s, const StepResult& r, uint32_t sta
                                float* reward, uint8_t* done, uint64_t* mask, uint8_t* status_out,
                                int64_t i) {
     const uint32_t win = any_line(s, r.classical, L);
-    if (reward) reward[i] = bits_to_float(reward_bits(win));                 // env.py:49
+    if (reward) reinterpret_cast<uint32_t*>(reward)[i] = reward_bits(win);   // env.py:49 (bit pattern, see k_step)
     if (done) done[i] = (uint8_t)((win != 0u) | (r.n > 8u));                  // env.py:51
     if (mask) mask[i] = L.legal[~r.classical & M9];                           // mcts.py:87-91
     if (status_out) status_out[i] = (uint8_t)status;

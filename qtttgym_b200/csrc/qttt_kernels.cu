@@ -49,7 +49,8 @@ __device__ __forceinline__ T* elem(T* base, uint32_t i) { return base + i; }
 // kFmt: QTTT_ACT_INDEX / QTTT_ACT_PAIR; kRandom: Philox policy instead of given actions;
 // kFull: reward, done, mask and status are all requested (no per-game NULL tests).
 // Launched with n <= 2^31 so that game indices fit 32 bits.
-template <int kFmt, bool kRandom, bool kFull>
+// kFresh: the games start from the empty board (Env.reset fused in): the state is not read.
+template <int kFmt, bool kRandom, bool kFull, bool kFresh = false>
 __global__ void __launch_bounds__(kThreads)
 k_step(qttt_state* __restrict__ state, const uint8_t* __restrict__ action,
        const uint8_t* __restrict__ coin, uint64_t seed, uint64_t game_base,
@@ -63,8 +64,11 @@ k_step(qttt_state* __restrict__ state, const uint8_t* __restrict__ action,
     const uint32_t stride = gridDim.x * kThreads;
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
         uint4* sp = reinterpret_cast<uint4*>(elem(state, i));
-        const uint4 sv = *sp;
-        State s{sv.x, sv.y, sv.z, sv.w};
+        State s = empty_state();
+        if (!kFresh) {
+            const uint4 sv = *sp;
+            s = State{sv.x, sv.y, sv.z, sv.w};
+        }
         uint32_t enew, c, st_extra = 0u;
         if (kRandom) {
             const uint32_t C = classical(s);
@@ -91,10 +95,13 @@ k_step(qttt_state* __restrict__ state, const uint8_t* __restrict__ action,
             }
         }
         const StepResult r = step_core(s, enew, c, L);
-        if (!r.illegal) *sp = make_uint4(s.x, s.y, s.z, s.w);     // a no-op leaves the state as it is
+        if (kFresh || !r.illegal) *sp = make_uint4(s.x, s.y, s.z, s.w);     // a no-op leaves the state as it is
         const uint32_t win = any_line(s, r.classical, L);
         const uint32_t st = st_extra ? st_extra : r.illegal;
-        if (kFull || reward) *elem(reward, i) = bits_to_float(reward_bits(win));             // env.py:49
+        // the reward is stored through an integer pointer: its two values differ only in bit
+        // patterns (-0.0f / -1.0f), and a float-typed select gets "simplified" by the compiler
+        // into an int->float conversion that loses the sign of zero
+        if (kFull || reward) *reinterpret_cast<uint32_t*>(elem(reward, i)) = reward_bits(win);   // env.py:49
         if (kFull || done) *elem(done, i) = (uint8_t)((win != 0u) | (r.n > 8u));              // env.py:51
         if (kFull || mask) *elem(mask, i) = L.legal[~r.classical & M9];  // mcts.py:87-91
         if (kFull || status) *elem(status, i) = (uint8_t)st;
@@ -651,7 +658,7 @@ int qttt_reset(qttt_state* state, uint64_t* mask, int64_t n, void* stream) {
 }  // extern "C"
 
 // Launches k_step over [0, n) in slices of at most 2^31 games (32-bit indices in the kernel).
-template <int kFmt, bool kRandom>
+template <int kFmt, bool kRandom, bool kFresh = false>
 static int launch_step(qttt_state* state, const uint8_t* action, const uint8_t* coin, uint64_t seed,
                        uint64_t game_base, float* reward, uint8_t* done, uint64_t* mask,
                        uint8_t* status, uint8_t* action_out, uint8_t* coin_out, int64_t n,
@@ -671,9 +678,9 @@ static int launch_step(qttt_state* state, const uint8_t* action, const uint8_t* 
         uint8_t* ao = action_out ? action_out + lo : nullptr;
         uint8_t* co = coin_out ? coin_out + lo : nullptr;
         if (full)
-            k_step<kFmt, kRandom, true><<<grid_for(k_step<kFmt, kRandom, true>, m), kThreads, 0, st>>>(s_, a_, c_, seed, game_base + (uint64_t)lo, r_, d_, m_, t_, ao, co, (uint32_t)m);
+            k_step<kFmt, kRandom, true, kFresh><<<grid_for(k_step<kFmt, kRandom, true, kFresh>, m), kThreads, 0, st>>>(s_, a_, c_, seed, game_base + (uint64_t)lo, r_, d_, m_, t_, ao, co, (uint32_t)m);
         else
-            k_step<kFmt, kRandom, false><<<grid_for(k_step<kFmt, kRandom, false>, m), kThreads, 0, st>>>(s_, a_, c_, seed, game_base + (uint64_t)lo, r_, d_, m_, t_, ao, co, (uint32_t)m);
+            k_step<kFmt, kRandom, false, kFresh><<<grid_for(k_step<kFmt, kRandom, false, kFresh>, m), kThreads, 0, st>>>(s_, a_, c_, seed, game_base + (uint64_t)lo, r_, d_, m_, t_, ao, co, (uint32_t)m);
         const int rc = check_launch();
         if (rc != QTTT_OK) return rc;
     }
@@ -695,6 +702,21 @@ int qttt_step(qttt_state* state, const void* action, int action_format, const ui
     if (action_format == QTTT_ACT_INDEX)
         return launch_step<QTTT_ACT_INDEX, false>(state, act, coin, seed, game_base, reward, done, mask, status, nullptr, nullptr, n, st);
     return launch_step<QTTT_ACT_PAIR, false>(state, act, coin, seed, game_base, reward, done, mask, status, nullptr, nullptr, n, st);
+}
+
+int qttt_reset_step(qttt_state* state, const void* action, int action_format, const uint8_t* coin,
+                    uint64_t seed, uint64_t game_base, float* reward, uint8_t* done, uint64_t* mask,
+                    uint8_t* status, int64_t n, void* stream) {
+    if (action_format != QTTT_ACT_INDEX && action_format != QTTT_ACT_PAIR) return QTTT_ERR_ARG;
+    if (n == 0) return QTTT_OK;
+    if (!state || !action || n < 0) return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(mask, 8) || misaligned(reward, 4)) return QTTT_ERR_ALIGN;
+    if (action_format == QTTT_ACT_PAIR && misaligned(action, 2)) return QTTT_ERR_ALIGN;
+    const uint8_t* act = static_cast<const uint8_t*>(action);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (action_format == QTTT_ACT_INDEX)
+        return launch_step<QTTT_ACT_INDEX, false, true>(state, act, coin, seed, game_base, reward, done, mask, status, nullptr, nullptr, n, st);
+    return launch_step<QTTT_ACT_PAIR, false, true>(state, act, coin, seed, game_base, reward, done, mask, status, nullptr, nullptr, n, st);
 }
 
 int qttt_step_packed(qttt_state* state, const uint8_t* action_coin, uint16_t* result, int64_t n,

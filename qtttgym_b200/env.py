@@ -96,6 +96,25 @@ class BatchedEnv:
                 _stream_ptr(self.device)))
         return self._result()
 
+    def reset_step(self, actions, choices=None):
+        """``reset()`` followed by ``step(actions, choices)`` as ONE kernel launch
+        (``qttt_reset_step``): the games restart from the empty board, so the packed state is
+        written but never read.  Returns what ``step`` returns."""
+        act, fmt = self._check_actions(actions)
+        coin = None
+        if choices is not None:
+            coin = choices if choices.dtype == torch.uint8 else choices.to(torch.uint8)
+            coin = coin.contiguous()
+            if coin.device != self.device or coin.numel() != self.num_envs:
+                raise ValueError("choices must be a uint8[N] tensor on the env's device")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.qttt_reset_step(
+                self.state.data_ptr(), act.data_ptr(), fmt, _lib.ptr(coin), self.seed,
+                self.game_base, self.reward.data_ptr(), self.done.data_ptr(),
+                self.mask.data_ptr(), self.status.data_ptr(), self.num_envs,
+                _stream_ptr(self.device)))
+        return self._result()
+
     def step_random(self, record: bool = False):
         """One ply of the uniform-random policy of ``MCTS._simulate`` (mcts.py:185-198) for
         every env that is not terminated; terminated envs are left untouched
@@ -213,13 +232,12 @@ class BatchedEnv:
             raise ValueError("capture_episode expects uint8[T,N] device tensors")
         actions, choices = actions.contiguous(), choices.contiguous()
         self._graph_inputs = (actions, choices)        # keep the captured buffers alive
-        self.reset()
-        self.step(actions[0], choices[0])              # warm-up outside the capture
+        self.reset_step(actions[0], choices[0])        # warm-up outside the capture
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            self.reset()
-            for t in range(actions.shape[0]):
+            self.reset_step(actions[0], choices[0])          # reset fused into the first ply
+            for t in range(1, actions.shape[0]):
                 self.step(actions[t], choices[t])
         return graph
 

@@ -25,7 +25,7 @@ def built_lib():
 
 def test_header_declares_the_expected_surface():
     assert _declared_symbols() == {
-        "qttt_abi_version", "qttt_strerror", "qttt_reset", "qttt_step", "qttt_step_packed", "qttt_step_packed_host", "qttt_step_random",
+        "qttt_abi_version", "qttt_strerror", "qttt_reset", "qttt_reset_step", "qttt_step", "qttt_step_packed", "qttt_step_packed_host", "qttt_step_random",
         "qttt_observe", "qttt_features", "qttt_pack", "qttt_qeval_both", "qttt_rollout", "qttt_sweep",
         "qttt_mcts_node_bytes", "qttt_mcts_init", "qttt_mcts_run", "qttt_mcts_stats", "qttt_mcts_sync"}
 

@@ -415,3 +415,21 @@ def test_batched_env_api_surface(cuda):
         env.step(torch.zeros(6, dtype=torch.uint8))
     packed = Q.BatchedEnv(6).reset()[0]
     assert set(packed) == {"packed"} and packed["packed"].shape == (6, 4)
+
+
+def test_reset_step_equals_reset_then_step(cuda):
+    import torch
+    import qtttgym_b200 as Q
+    n = 30_011
+    a, b = Q.BatchedEnv(n, seed=2), Q.BatchedEnv(n, seed=2)
+    for env in (a, b):                       # leave garbage mid-game states behind
+        for _ in range(5):
+            env.step_random()
+    act = torch.randint(0, 40, (n,), device="cuda").to(torch.uint8)      # some illegal indices
+    coin = torch.randint(0, 2, (n,), device="cuda").to(torch.uint8)
+    a.reset()
+    ra = a.step(act, coin)
+    rb = b.reset_step(act, coin)
+    assert torch.equal(a.state, b.state)
+    assert torch.equal(ra[1].view(torch.int32), rb[1].view(torch.int32)) and torch.equal(ra[2], rb[2])
+    assert torch.equal(ra[4]["action_mask"], rb[4]["action_mask"]) and torch.equal(ra[4]["status"], rb[4]["status"])
