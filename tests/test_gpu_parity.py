@@ -433,3 +433,24 @@ def test_reset_step_equals_reset_then_step(cuda):
     assert torch.equal(a.state, b.state)
     assert torch.equal(ra[1].view(torch.int32), rb[1].view(torch.int32)) and torch.equal(ra[2], rb[2])
     assert torch.equal(ra[4]["action_mask"], rb[4]["action_mask"]) and torch.equal(ra[4]["status"], rb[4]["status"])
+
+
+def test_integration_md_stub_runs_verbatim(cuda):
+    """The ctypes stub printed in INTEGRATION.md section 1 is executable as written."""
+    import re
+    import torch
+    import qtttgym_b200._lib as L
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"## 1\..*?```python\n(.*?)```", text, re.S).group(1)
+    block = block.replace('C.CDLL("libqttt_b200.so")', f'C.CDLL("{L.LIB}")')
+    ns = {}
+    exec(block, ns)
+    env = ns["VecEnv"](8, seed=3)
+    env.reset()
+    pairs = torch.tensor([[0, 1], [1, 0], [3, 3], [2, 8], [9, 1], [4, 5], [7, 6], [0, 8]], dtype=torch.int8, device="cuda")
+    reward, done, mask, status = env.step(pairs)
+    torch.cuda.synchronize()
+    assert status.tolist() == [0, 0, 1, 0, 1, 0, 0, 0]
+    assert reward.view(torch.int32).tolist() == [-2147483648] * 8 and not bool(done.any())
+    assert int(mask[0]) == (1 << 36) - 1
