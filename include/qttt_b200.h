@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define QTTT_ABI_VERSION 1
+#define QTTT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define QTTT_API __attribute__((visibility("default")))
@@ -58,6 +58,12 @@ extern "C" {
 #define QTTT_ST_OK 0        /* move accepted */
 #define QTTT_ST_ILLEGAL 1   /* the reference would have raised; swallowed no-op (env.py:41-43) */
 #define QTTT_ST_FINISHED 2  /* random-policy step on a terminated game: nothing to do */
+#define QTTT_ST_RESET 4     /* OR-ed in: the game was over on entry and was reset first (autoreset) */
+
+/* flags of qttt_step_ex / qttt_step_random_ex (at most one) */
+#define QTTT_STEP_FRESH 1u           /* Env.reset then Env.step: the incoming state is ignored */
+#define QTTT_STEP_AUTORESET 2u       /* a game that is over on entry is reset, then the action is applied */
+#define QTTT_STEP_AUTORESET_NEXT 4u  /* ... is reset and its action ignored (vector-env "next step" autoreset) */
 
 typedef struct { uint32_t w[4]; } qttt_state;
 
@@ -68,6 +74,11 @@ QTTT_API const char* qttt_strerror(int rc);
  * ignored there, Q4).  Writes n empty games; mask (optional) gets the 36-bit legal mask of
  * the empty board (all 36 actions). */
 QTTT_API int qttt_reset(qttt_state* state, uint64_t* mask, int64_t n, void* stream);
+
+/* qttt_reset that also writes what Env.step would report for a fresh game (optional outputs):
+ * reward -0.0f (env.py:49 with no line), done 0, status QTTT_ST_OK. */
+QTTT_API int qttt_reset_all(qttt_state* state, uint64_t* mask, float* reward, uint8_t* done,
+                            uint8_t* status, int64_t n, void* stream);
 
 /* Env.step (qtttgym/env.py:34-53) for n independent games, including Board.make_move /
  * update_qstructs (board.py:9-69), QEvalClassic.eval (qeval.py:5-51) and check_win
@@ -92,6 +103,23 @@ QTTT_API int qttt_reset_step(qttt_state* state, const void* action, int action_f
                              const uint8_t* coin, uint64_t seed, uint64_t game_base, float* reward,
                              uint8_t* done, uint64_t* mask, uint8_t* status, int64_t n, void* stream);
 
+/* qttt_step with an episode counter and a mode.
+ *   epoch : folded into the Philox counter of the collapse coin (coin == NULL): the coin of game
+ *           g at ply p in epoch e is a function of (seed, g, p, e).  The reference draws a fresh
+ *           random.choice per collapse (qeval.py:35); a caller that plays episode after episode
+ *           in the same env slots passes a different epoch per episode (qtttgym_b200.BatchedEnv
+ *           bumps it in reset()) or the episodes would all see the same coins.  epoch 0 is the
+ *           stream of qttt_step.  (24 bits are used.)
+ *   flags : 0, or one of QTTT_STEP_FRESH (== qttt_reset_step), QTTT_STEP_AUTORESET,
+ *           QTTT_STEP_AUTORESET_NEXT.  With an autoreset flag a game that is over on entry
+ *           (a line exists or len(moves) == 9: what Env.step reports as terminated, env.py:51)
+ *           restarts from the empty board inside the same launch (status gets QTTT_ST_RESET),
+ *           so a batch driven by a policy never idles and never needs a host round trip. */
+QTTT_API int qttt_step_ex(qttt_state* state, const void* action, int action_format, const uint8_t* coin,
+                          uint64_t seed, uint64_t game_base, uint64_t epoch, uint32_t flags,
+                          float* reward, uint8_t* done, uint64_t* mask, uint8_t* status, int64_t n,
+                          void* stream);
+
 /* qttt_step with compact I/O, for callers whose buffers live in HOST memory (there the PCIe
  * link, not HBM, is the bound: 3 bytes per game cross it instead of 15).
  *   action_coin uint8[n]  : bits 0..5 action index (QTTT_ACT_INDEX; 36..63 = illegal),
@@ -106,6 +134,19 @@ QTTT_API int qttt_reset_step(qttt_state* state, const void* action, int action_f
 QTTT_API int qttt_step_packed(qttt_state* state, const uint8_t* action_coin, uint16_t* result,
                               int64_t n, void* stream);
 
+/* qttt_step_packed that also writes the observation: obs qttt_state[n] (optional) receives the
+ * post-step packed state of every game (for an illegal no-op: the unchanged state), i.e. what
+ * Env.step returns as obs (env.py:46,68-85) in packed form. */
+QTTT_API int qttt_step_packed_obs(qttt_state* state, const uint8_t* action_coin, uint16_t* result,
+                                  qttt_state* obs, int64_t n, void* stream);
+
+/* qttt_step_packed_obs for MAPPED PINNED HOST buffers (cudaHostAlloc / cudaHostRegister memory,
+ * device-accessible under unified addressing): the kernel itself reads action_coin_host and
+ * writes result_host / obs_host (optional) across PCIe in 512-byte bursts -- no copy engine, no
+ * device staging buffers, one launch.  The caller synchronises the stream before reading. */
+QTTT_API int qttt_step_packed_mapped(qttt_state* state, const uint8_t* action_coin_host,
+                                     uint16_t* result_host, qttt_state* obs_host, int64_t n, void* stream);
+
 /* The host-buffer form of qttt_step_packed: action_coin_host / result_host are PINNED HOST
  * arrays; in_dev (uint8[n]) / out_dev (uint16[n]) are caller-provided device staging buffers.
  * The batch is cut into slices of `slice` games; slice k is copied in, stepped and copied out
@@ -115,6 +156,14 @@ QTTT_API int qttt_step_packed_host(qttt_state* state, const uint8_t* action_coin
                                    uint16_t* result_host, uint8_t* in_dev, uint16_t* out_dev,
                                    int64_t n, int64_t slice, void* const* streams, int n_streams);
 
+/* qttt_step_packed_host that also brings the observation back: obs_host qttt_state[n] (pinned,
+ * optional) receives each slice of the state array after its kernel (16 more bytes per game
+ * over PCIe). */
+QTTT_API int qttt_step_packed_host_obs(qttt_state* state, const uint8_t* action_coin_host,
+                                       uint16_t* result_host, qttt_state* obs_host, uint8_t* in_dev,
+                                       uint16_t* out_dev, int64_t n, int64_t slice, void* const* streams,
+                                       int n_streams);
+
 /* Env.step driven by the uniform-random policy of MCTS._simulate (mcts.py:185-198,
  * 287-292): action ~ U(legal actions), coin ~ U{0,1}, both from Philox4x32-10 with counter
  * (game_lo, game_hi, len(moves), 0) and key seed.  Terminated games (mcts.py:52-65) are left
@@ -123,6 +172,13 @@ QTTT_API int qttt_step_packed_host(qttt_state* state, const uint8_t* action_coin
 QTTT_API int qttt_step_random(qttt_state* state, uint64_t seed, uint64_t game_base, uint8_t* action_out,
                      uint8_t* coin_out, float* reward, uint8_t* done, uint64_t* mask,
                      uint8_t* status, int64_t n, void* stream);
+
+/* qttt_step_random with an epoch and a mode (see qttt_step_ex).  With QTTT_STEP_AUTORESET every
+ * call plays one ply in every game, finished games restarting from the empty board: continuous
+ * random self-play through the step API. */
+QTTT_API int qttt_step_random_ex(qttt_state* state, uint64_t seed, uint64_t game_base, uint64_t epoch,
+                                 uint32_t flags, uint8_t* action_out, uint8_t* coin_out, float* reward,
+                                 uint8_t* done, uint64_t* mask, uint8_t* status, int64_t n, void* stream);
 
 /* Env._observation / Env.turn / Env._reward / check_win / update_winner / action_mask in
  * tensor form (qtttgym/env.py:62-112, board.py:71-115, mcts.py:52-65,87-91).

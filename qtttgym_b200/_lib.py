@@ -8,12 +8,13 @@ import os
 from .build import LIB
 
 ACT_INDEX, ACT_PAIR = 0, 1
-ST_OK, ST_ILLEGAL, ST_FINISHED = 0, 1, 2
-ABI_VERSION = 1
+ST_OK, ST_ILLEGAL, ST_FINISHED, ST_RESET = 0, 1, 2, 4
+STEP_FRESH, STEP_AUTORESET, STEP_AUTORESET_NEXT = 1, 2, 4
+ABI_VERSION = 2
 
 _lib = None
 
-_vp, _i64, _u64, _i32, _int = C.c_void_p, C.c_int64, C.c_uint64, C.c_int32, C.c_int
+_vp, _i64, _u64, _i32, _u32, _int = C.c_void_p, C.c_int64, C.c_uint64, C.c_int32, C.c_uint32, C.c_int
 
 _SIGNATURES = {
     "qttt_abi_version": ([], _int),
@@ -21,9 +22,15 @@ _SIGNATURES = {
     "qttt_reset": ([_vp, _vp, _i64, _vp], _int),
     "qttt_step": ([_vp, _vp, _int, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _i64, _vp], _int),
     "qttt_reset_step": ([_vp, _vp, _int, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _i64, _vp], _int),
+    "qttt_reset_all": ([_vp, _vp, _vp, _vp, _vp, _i64, _vp], _int),
+    "qttt_step_ex": ([_vp, _vp, _int, _vp, _u64, _u64, _u64, _u32, _vp, _vp, _vp, _vp, _i64, _vp], _int),
     "qttt_step_packed": ([_vp, _vp, _vp, _i64, _vp], _int),
+    "qttt_step_packed_obs": ([_vp, _vp, _vp, _vp, _i64, _vp], _int),
+    "qttt_step_packed_mapped": ([_vp, _vp, _vp, _vp, _i64, _vp], _int),
     "qttt_step_packed_host": ([_vp, _vp, _vp, _vp, _vp, _i64, _i64, C.POINTER(C.c_void_p), _int], _int),
+    "qttt_step_packed_host_obs": ([_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, C.POINTER(C.c_void_p), _int], _int),
     "qttt_step_random": ([_vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp], _int),
+    "qttt_step_random_ex": ([_vp, _u64, _u64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp], _int),
     "qttt_observe": ([_vp] * 11 + [_i64, _vp], _int),
     "qttt_features": ([_vp, _vp, _i64, _vp], _int),
     "qttt_pack": ([_vp, _vp, _vp, _vp, _i64, _vp], _int),

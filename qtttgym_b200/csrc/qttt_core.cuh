@@ -82,6 +82,16 @@ QTTT_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 
+// Largest value among the lanes of the warp that are executing this call together (the value
+// itself on the host).
+QTTT_HD uint32_t warp_max_u32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __reduce_max_sync(__activemask(), v);
+#else
+    return v;
+#endif
+}
+
 QTTT_HD State empty_state() { return State{0u, 0u, 0u, 0u}; }
 QTTT_HD uint32_t n_moves(const State& s) { return (s.x >> 27) & 15u; }
 QTTT_HD uint32_t plane3(const State& s) { return (s.y >> 27) | ((s.z >> 22) & 0x1E0u); }
@@ -283,6 +293,31 @@ QTTT_HD void sweep(uint32_t x, uint32_t y, uint32_t z, uint32_t& R, uint32_t& W,
     }
 }
 
+// The same sweep from TWO start squares at once (the two measurement outcomes of one closing
+// move, qeval.py:35): one pass over the move slots advances both rootings, so enumerating both
+// outcomes costs one loop instead of two transitions.  The two absorptions of a slot are
+// independent instruction chains (ILP 2).
+template <int N>
+QTTT_HD void sweep2(uint32_t x, uint32_t y, uint32_t z, uint32_t& Ra, uint32_t& Wa, uint32_t& A3a,
+                    uint32_t& Rb, uint32_t& Wb, uint32_t& A3b) {
+    const uint32_t E0 = N > 0 ? slot<0>(x, y, z) : 0u, E1 = N > 1 ? slot<1>(x, y, z) : 0u;
+    const uint32_t E2 = N > 2 ? slot<2>(x, y, z) : 0u, E3 = N > 3 ? slot<3>(x, y, z) : 0u;
+    const uint32_t E4 = N > 4 ? slot<4>(x, y, z) : 0u, E5 = N > 5 ? slot<5>(x, y, z) : 0u;
+    const uint32_t E6 = N > 6 ? slot<6>(x, y, z) : 0u, E7 = N > 7 ? slot<7>(x, y, z) : 0u;
+    uint32_t before;
+    do {
+        before = Ra + (Rb << 9);
+        if (N > 0) { absorb<0>(E0, Ra, Wa, A3a); absorb<0>(E0, Rb, Wb, A3b); }
+        if (N > 1) { absorb<1>(E1, Ra, Wa, A3a); absorb<1>(E1, Rb, Wb, A3b); }
+        if (N > 2) { absorb<2>(E2, Ra, Wa, A3a); absorb<2>(E2, Rb, Wb, A3b); }
+        if (N > 3) { absorb<3>(E3, Ra, Wa, A3a); absorb<3>(E3, Rb, Wb, A3b); }
+        if (N > 4) { absorb<4>(E4, Ra, Wa, A3a); absorb<4>(E4, Rb, Wb, A3b); }
+        if (N > 5) { absorb<5>(E5, Ra, Wa, A3a); absorb<5>(E5, Rb, Wb, A3b); }
+        if (N > 6) { absorb<6>(E6, Ra, Wa, A3a); absorb<6>(E6, Rb, Wb, A3b); }
+        if (N > 7) { absorb<7>(E7, Ra, Wa, A3a); absorb<7>(E7, Rb, Wb, A3b); }
+    } while (N > 1 && (Ra + (Rb << 9)) != before);
+}
+
 // Board.make_move for one game.  `enew`: E mask of the requested pair (0 = malformed);
 // `coin`: 0 -> the closing move falls into its smaller square (qeval.py:35).
 //
@@ -318,9 +353,12 @@ QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, const Luts&
     uint32_t W = t * row.kp;          // planes 0..2 of the closing move (index n) on square t
     uint32_t A3 = (n >= 7u) ? t : 0u; // plane 3: v = n + 1 in {8, 9}
     uint32_t T[9] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, t};
-    // An illegal request (a swallowed no-op) has nothing to sweep: send it down the empty
-    // case so that idle games of other lengths do not make the warp run extra cases.
-    switch (legal ? n : 0u) {
+    // An illegal request (a swallowed no-op) has nothing to sweep.  The case is chosen ONCE PER
+    // WARP -- the largest len(moves) among its lanes -- so the switch never diverges: empty
+    // slots hold E = 0 and can never touch R, which makes sweep<N> exact for every n <= N.  A
+    // batch stepped in lock-step pays exactly its own n; a desynchronised batch (envs at
+    // different plies in one warp) pays one sweep<max n> instead of one case per distinct n.
+    switch (warp_max_u32(legal ? n : 0u)) {
         case 1: sweep<1, kTargets>(x, y, z, R, W, A3, T); break;
         case 2: sweep<2, kTargets>(x, y, z, R, W, A3, T); break;
         case 3: sweep<3, kTargets>(x, y, z, R, W, A3, T); break;
@@ -379,6 +417,74 @@ QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, const Luts&
     out.classical = Cn;
     out.n = n + inc;
     return out;
+}
+
+// One outcome's commit, shared by step_both: the accumulated plane words become part of the
+// board when the move closed a cycle (board.py:53-54), then the autofill (board.py:21-25).
+// (xa, ya, za): the move words with the new move already appended.
+QTTT_HD uint32_t commit_outcome(State& out, uint32_t xa, uint32_t ya, uint32_t za, uint32_t w, uint32_t C,
+                                uint32_t R, uint32_t W, uint32_t A3, uint32_t colf, uint32_t inc, uint32_t& n_out) {
+    uint32_t wn = w + W * colf;
+    A3 *= colf;
+    uint32_t Cn = C | (R * colf);
+    const uint32_t fr = ~Cn & M9;
+    const bool fill = (colf != 0u) & (popc32(fr) == 1);
+    const uint32_t fs = fill ? fr : 0u;
+    wn += fs;
+    A3 += fs;
+    Cn |= fs;
+    inc += fill ? 1u : 0u;
+    out.x = xa + (inc << 27);
+    out.y = ya + (A3 << 27);
+    out.z = za + (fs << 18) + ((A3 >> 5) << 27);
+    out.w = wn;
+    n_out = inc;
+    return Cn;
+}
+
+// Both measurement outcomes of one move in ONE sweep (board.py:42-56 with qeval.py:35 taking
+// either value; what MCTS._step enumerates by rejection sampling, mcts.py:233-267).  The two
+// outcomes are the rootings of the same tree at the closing move's two squares; sweep2 grows
+// both in one pass over the move slots.  When no cycle closes the two successors are equal.
+struct BothResult {
+    uint32_t illegal, collapsed;
+    uint32_t classical0, classical1;   // classical squares of the two successors
+    uint32_t n0, n1;                   // len(moves) of the two successors
+};
+QTTT_HD BothResult step_both(const State& s, uint32_t enew, const Luts& L, State& s0, State& s1) {
+    const uint32_t x = s.x, y = s.y, z = s.z, w = s.w;
+    const uint32_t n = (x >> 27) & 15u;
+    const NRow row = L.nrow[n];
+    const uint32_t C = classical(s);
+    const bool legal = (enew != 0u) & ((enew & C) == 0u) & (n < 9u);   // board.py:10-15
+    enew = legal ? enew : 0u;
+    const uint32_t a = enew & (0u - enew), b = enew ^ a;                // coin 0 -> a, coin 1 -> b
+    uint32_t Ra = a, Rb = b;
+    uint32_t Wa = a * row.kp, Wb = b * row.kp;
+    uint32_t A3a = (n >= 7u) ? a : 0u, A3b = (n >= 7u) ? b : 0u;
+    switch (warp_max_u32(legal ? n : 0u)) {
+        case 1: sweep2<1>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b); break;
+        case 2: sweep2<2>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b); break;
+        case 3: sweep2<3>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b); break;
+        case 4: sweep2<4>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b); break;
+        case 5: sweep2<5>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b); break;
+        case 6: sweep2<6>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b); break;
+        case 7: sweep2<7>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b); break;
+        case 8: sweep2<8>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b); break;
+        default: break;
+    }
+    const uint32_t colf = (Ra & b) != 0u ? 1u : 0u;                     // board.py:42
+    const uint32_t xa = x + enew * row.mx, ya = y + enew * row.my, za = z + enew * row.mz;   // board.py:19
+    const uint32_t inc = legal ? 1u : 0u;
+    BothResult r;
+    uint32_t i0, i1;
+    r.classical0 = commit_outcome(s0, xa, ya, za, w, C, Ra, Wa, A3a, colf, inc, i0);
+    r.classical1 = commit_outcome(s1, xa, ya, za, w, C, Rb, Wb, A3b, colf, inc, i1);
+    r.n0 = n + i0;
+    r.n1 = n + i1;
+    r.illegal = legal ? 0u : 1u;
+    r.collapsed = colf;
+    return r;
 }
 
 // Env.step's scalar outputs from the post-step state (env.py:48-51).
@@ -465,9 +571,17 @@ QTTT_HD uint32_t policy_edge(uint32_t free_set, uint32_t x0, const Luts& L) {
     return m ? e : 0u;
 }
 
+// Word 3 of the Philox counter: the draw domain (0 step API / sweep, 1 rollouts, 2 MCTS
+// selection, 3 MCTS playouts) in bits 0..7 and the EPOCH in bits 8..31.  The epoch is what
+// separates the episodes an env slot plays one after the other: (seed, game, ply) alone would
+// hand every episode the same coin at the same ply.  Callers bump it on every reset (and on
+// every step of an auto-resetting batch); epoch 0 is the plain (seed, game, ply) stream.
+QTTT_HD uint32_t domain_word(uint32_t domain, uint64_t epoch) { return domain | ((uint32_t)epoch << 8); }
+
 // The random draw of one ply: (action word, coin bit) = f(seed, game, ply, domain).  One
 // Philox4x32-10 block, counter (game_lo, game_hi, ply >> 1, domain), serves TWO consecutive
 // plies: the even ply takes (x0, x1 & 1), the odd ply (x2, x3 & 1).
+// (`domain` is counter word 3 as given: a plain domain number, or domain_word(domain, epoch).)
 QTTT_HD void ply_draw(uint64_t seed, uint64_t game, uint32_t ply, uint32_t domain,
                       uint32_t& action_word, uint32_t& coin) {
     uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = ply >> 1, c3 = domain;
@@ -533,6 +647,74 @@ QTTT_HD void emit_step_outputs(const State& s, const StepResult& r, uint32_t sta
     if (done) done[i] = (uint8_t)((win != 0u) | (r.n > 8u));                  // env.py:51
     if (mask) mask[i] = L.legal[~r.classical & M9];                           // mcts.py:87-91
     if (status_out) status_out[i] = (uint8_t)status;
+}
+
+// ------------------------------------------------------------------------------------
+// One game's Env.step with everything around the transition that does not touch memory
+// (shared by the step kernels and the host emulation the CPU tests run).
+//   kStepPlain    : Env.step (env.py:34-53)
+//   kStepFresh    : Env.reset then Env.step (env.py:55-57, 34-53): the incoming state is ignored
+//   kStepAuto     : if the game is over on entry (a line exists or 9 entries in moves) it is
+//                   reset first, then the action is applied -- a batch never idles
+//   kStepAutoNext : as kStepAuto but the action of a just-reset game is ignored (the
+//                   "next-step" autoreset convention of vector envs): the step returns the
+//                   fresh game
+// ------------------------------------------------------------------------------------
+enum : int { kStepPlain = 0, kStepFresh = 1, kStepAuto = 2, kStepAutoNext = 3 };
+constexpr uint32_t kStFinished = 2u, kStReset = 4u;
+
+struct StepOut {
+    uint32_t win;          // a line exists after the step (reward = win ? -1.0f : -0.0f)
+    uint32_t done;         // env.py:51
+    uint32_t classical;    // classical squares after the step (legal mask = legal[~classical])
+    uint32_t status;       // QTTT_ST_* (| kStReset when the game was auto-reset on entry)
+    uint32_t write_state;  // the state changed (an illegal no-op leaves it as it is)
+    uint32_t action, coin; // the random policy's choice (kRandom), 255 / 0 when nothing was played
+};
+
+template <bool kRandom, int kMode>
+QTTT_HD StepOut step_game(State& s, uint32_t enew, bool have_coin, uint32_t coin, uint64_t seed, uint64_t game,
+                          uint32_t dword, const Luts& L) {
+    StepOut o;
+    uint32_t was_reset = 0u, st_extra = 0u;
+    if (kMode == kStepFresh) s = empty_state();
+    if (kMode == kStepAuto || kMode == kStepAutoNext) {
+        const uint32_t C0 = classical(s);
+        if ((any_line(s, C0, L) != 0u) | (n_moves(s) >= 9u)) {               // mcts.py:52-65
+            s = empty_state();
+            was_reset = 1u;
+        }
+    }
+    o.action = 255u;
+    o.coin = 0u;
+    if (kRandom) {
+        const uint32_t C = classical(s);
+        const uint32_t nm = n_moves(s);
+        uint32_t act;
+        policy_draw(seed, game, nm, dword, L.legal[~C & M9], act, coin);
+        if (kMode == kStepPlain) {
+            // terminated games are left untouched (the random policy has nothing to play)
+            if ((any_line(s, C, L) != 0u) | (nm >= 9u)) { act = 255u; coin = 0u; st_extra = kStFinished; }
+        }
+        if (kMode == kStepAutoNext && was_reset) { act = 255u; coin = 0u; }
+        enew = L.pair[act];
+        o.action = act;
+        o.coin = coin;
+    } else {
+        if (!have_coin) {
+            uint32_t word;
+            ply_draw(seed, game, n_moves(s), dword, word, coin);
+        }
+        if (kMode == kStepAutoNext && was_reset) enew = 0u;
+    }
+    const StepResult r = step_core(s, enew, coin, L);
+    o.win = any_line(s, r.classical, L);
+    o.done = (o.win != 0u) | (r.n > 8u);
+    o.classical = r.classical;
+    o.status = st_extra ? st_extra : ((kMode == kStepAutoNext && was_reset) ? 0u : r.illegal);
+    o.status |= was_reset ? kStReset : 0u;
+    o.write_state = (kMode == kStepFresh) | was_reset | (r.illegal ^ 1u);
+    return o;
 }
 
 // mcts.py:52-65 terminal test on a state (winner exists or 9 entries in moves).
@@ -633,27 +815,50 @@ QTTT_HD void qeval_game(const State& s, uint32_t action, const Luts& L, State* n
     const uint32_t enew = L.pair[action & 255u];
     float px_prob = 0.f, po_prob = 0.f;
     uint32_t col = 0u;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        State t = s;
-        uint32_t tgt[9];
-        const StepResult r = step_core<kSquares>(t, enew, (uint32_t)c, L, tgt);
+    if (!kSquares) {
+        // one sweep serves both coins
+        State t0, t1;
+        const BothResult r = step_both(s, enew, L, t0, t1);
         col = r.collapsed;
-        State* nx = c ? next1 : next0;
-        uint64_t* bd = c ? board1 : board0;
-        int8_t* sq = c ? sq1 : sq0;
-        if (nx) nx[i] = t;
-        if (bd) bd[i] = board_nibbles(t, L);
-        if (kSquares && sq) {
-#pragma unroll
-            for (int m = 0; m < 9; ++m) sq[9 * i + m] = (int8_t)(tgt[m] ? ctz32(tgt[m]) : -1);
-        }
+        if (next0) next0[i] = t0;
+        if (next1) next1[i] = t1;
+        if (board0) board0[i] = board_nibbles(t0, L);
+        if (board1) board1[i] = board_nibbles(t1, L);
         if (result_prob) {
             int px, po;
-            win_rounds(t, L, px, po);
-            const uint32_t wnr = winner_of(px, po);
+            win_rounds(t0, L, px, po);
+            uint32_t wnr = winner_of(px, po);
             px_prob += wnr == 1u ? 0.5f : 0.f;
             po_prob += wnr == 2u ? 0.5f : 0.f;
+            win_rounds(t1, L, px, po);
+            wnr = winner_of(px, po);
+            px_prob += wnr == 1u ? 0.5f : 0.f;
+            po_prob += wnr == 2u ? 0.5f : 0.f;
+        }
+    } else {
+        // eval()'s per-move return value is wanted: run the transition per coin with targets
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            State t = s;
+            uint32_t tgt[9];
+            const StepResult r = step_core<true>(t, enew, (uint32_t)c, L, tgt);
+            col = r.collapsed;
+            State* nx = c ? next1 : next0;
+            uint64_t* bd = c ? board1 : board0;
+            int8_t* sq = c ? sq1 : sq0;
+            if (nx) nx[i] = t;
+            if (bd) bd[i] = board_nibbles(t, L);
+            if (sq) {
+#pragma unroll
+                for (int m = 0; m < 9; ++m) sq[9 * i + m] = (int8_t)(tgt[m] ? ctz32(tgt[m]) : -1);
+            }
+            if (result_prob) {
+                int px, po;
+                win_rounds(t, L, px, po);
+                const uint32_t wnr = winner_of(px, po);
+                px_prob += wnr == 1u ? 0.5f : 0.f;
+                po_prob += wnr == 2u ? 0.5f : 0.f;
+            }
         }
     }
     if (closes) closes[i] = (uint8_t)col;

@@ -6,6 +6,7 @@
 // Python side passes raw device pointers and a stream.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/qttt_b200.h"
 #include "qttt_core.cuh"
@@ -33,99 +34,200 @@ __device__ __forceinline__ void store_state(qttt_state* p, int64_t i, const Stat
     *reinterpret_cast<uint4*>(p + i) = make_uint4(s.x, s.y, s.z, s.w);
 }
 
+// ------------------------------------------------------------------------------ work distribution
+// Every batch kernel below cuts its games into chunks of kThreads and gives each block a short
+// run of consecutive chunks (`iters`), with many more blocks than fit the machine at once.  The
+// hardware block scheduler then refills an SM as soon as one of its blocks retires.  (Round 1
+// launched exactly one resident wave of persistent grid-stride blocks: ncu showed the SMs
+// running out of warps long before the kernel ended -- 46 of 64 warps resident on average at
+// ply 8 -- because the warp arbiter is not fair and nothing replaces a warp that finishes early.)
+constexpr int kStepIters = 4;       // chunks per block of the step kernels (tables restaged per block)
+
+static int chunk_grid(int64_t n, int iters) {
+    const int64_t per_block = (int64_t)kThreads * iters;
+    const int64_t g = (n + per_block - 1) / per_block;
+    return (int)(g < 1 ? 1 : g);
+}
+
 // ------------------------------------------------------------------------------ K2 reset
-__global__ void __launch_bounds__(kThreads) k_reset(qttt_state* state, uint64_t* mask, int64_t n) {
+// Board.__init__ / Env.reset: empty games; optionally the outputs a step would have produced
+// for them (legal mask of the empty board, reward -0.0f, not terminated, status ok).
+__global__ void __launch_bounds__(kThreads) k_reset(qttt_state* state, uint64_t* mask, float* reward,
+                                                    uint8_t* done, uint8_t* status, int64_t n) {
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
         *reinterpret_cast<uint4*>(state + i) = make_uint4(0u, 0u, 0u, 0u);
         if (mask) mask[i] = 0xFFFFFFFFFull;   // all 36 pairs legal on the empty board
+        if (reward) reinterpret_cast<uint32_t*>(reward)[i] = 0x80000000u;   // -0.0f: no line (env.py:49)
+        if (done) done[i] = 0;
+        if (status) status[i] = 0;
     }
 }
 
 // ------------------------------------------------------------------------------ K1 step
-template <class T>
-__device__ __forceinline__ T* elem(T* base, uint32_t i) { return base + i; }
+struct StepArgs {
+    qttt_state* state;
+    const uint8_t* action;
+    const uint8_t* coin;
+    uint64_t seed, game_base;
+    uint32_t dword;             // Philox counter word 3: domain 0 | epoch << 8
+    float* reward;
+    uint8_t* done;
+    uint64_t* mask;
+    uint8_t* status;
+    uint8_t* action_out;
+    uint8_t* coin_out;
+    uint32_t n;                 // <= 2^31 games per launch (32-bit indices)
+    int iters;                  // chunks of kThreads games per block
+};
+
+struct StepIn { uint4 sv; uint32_t act, coin; };
 
 // kFmt: QTTT_ACT_INDEX / QTTT_ACT_PAIR; kRandom: Philox policy instead of given actions;
-// kFull: reward, done, mask and status are all requested (no per-game NULL tests).
-// Launched with n <= 2^31 so that game indices fit 32 bits.
-// kFresh: the games start from the empty board (Env.reset fused in): the state is not read.
-template <int kFmt, bool kRandom, bool kFull, bool kFresh = false>
-__global__ void __launch_bounds__(kThreads)
-k_step(qttt_state* __restrict__ state, const uint8_t* __restrict__ action,
-       const uint8_t* __restrict__ coin, uint64_t seed, uint64_t game_base,
-       float* __restrict__ reward, uint8_t* __restrict__ done, uint64_t* __restrict__ mask,
-       uint8_t* __restrict__ status, uint8_t* __restrict__ action_out,
-       uint8_t* __restrict__ coin_out, uint32_t n) {
+// kFull: reward, done, mask and status are all requested and coins are given (no NULL tests);
+// kMode: kStepPlain / kStepFresh / kStepAuto / kStepAutoNext (qttt_core.cuh);
+// kPrefetch: the next chunk's inputs are loaded before the current chunk is computed.
+template <int kFmt, bool kRandom, bool kFull, int kMode, bool kPrefetch>
+__global__ void __launch_bounds__(kThreads) k_step(const StepArgs a) {
     __shared__ __align__(16) uint8_t smem[kLutStepBytes];
     stage_luts(smem, kLutStepBytes);
     const Luts L = luts_from_image(smem);
 
-    const uint32_t stride = gridDim.x * kThreads;
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-        uint4* sp = reinterpret_cast<uint4*>(elem(state, i));
-        State s = empty_state();
-        if (!kFresh) {
-            const uint4 sv = *sp;
-            s = State{sv.x, sv.y, sv.z, sv.w};
-        }
-        uint32_t enew, c, st_extra = 0u;
-        if (kRandom) {
-            const uint32_t C = classical(s);
-            const uint32_t nm = n_moves(s);
-            const bool finished = (any_line(s, C, L) != 0u) | (nm >= 9u);   // mcts.py:52-65
-            uint32_t act;
-            policy_draw(seed, game_base + (uint64_t)i, nm, 0u, L.legal[~C & M9], act, c);
-            if (finished) { act = 255u; c = 0u; st_extra = QTTT_ST_FINISHED; }
-            enew = L.pair[act];
-            if (action_out) *elem(action_out, i) = (uint8_t)act;
-            if (coin_out) *elem(coin_out, i) = (uint8_t)c;
-        } else {
-            if (kFmt == QTTT_ACT_INDEX) {
-                enew = L.pair[*elem(action, i)];
-            } else {
-                const uchar2 ab = *elem(reinterpret_cast<const uchar2*>(action), i);
-                enew = pair_to_edge(ab.x, ab.y);
-            }
-            if (coin) {
-                c = *elem(coin, i) & 1u;
-            } else {
-                uint32_t word;
-                ply_draw(seed, game_base + (uint64_t)i, n_moves(s), 0u, word, c);
+    auto load = [&](uint32_t i) {
+        StepIn in;
+        in.sv = make_uint4(0u, 0u, 0u, 0u);
+        in.act = 255u;
+        in.coin = 0u;
+        if (i < a.n) {
+            if (kMode != kStepFresh) in.sv = *reinterpret_cast<const uint4*>(a.state + i);
+            if (!kRandom) {
+                if (kFmt == QTTT_ACT_INDEX) {
+                    in.act = a.action[i];
+                } else {
+                    const uchar2 ab = reinterpret_cast<const uchar2*>(a.action)[i];
+                    in.act = (uint32_t)ab.x | ((uint32_t)ab.y << 8);
+                }
+                if (kFull || a.coin) in.coin = a.coin[i];
             }
         }
-        const StepResult r = step_core(s, enew, c, L);
-        if (kFresh || !r.illegal) *sp = make_uint4(s.x, s.y, s.z, s.w);     // a no-op leaves the state as it is
-        const uint32_t win = any_line(s, r.classical, L);
-        const uint32_t st = st_extra ? st_extra : r.illegal;
+        return in;
+    };
+    auto run = [&](uint32_t i, const StepIn& in) {
+        if (i >= a.n) return;
+        State s{in.sv.x, in.sv.y, in.sv.z, in.sv.w};
+        uint32_t enew = 0u;
+        if (!kRandom)
+            enew = kFmt == QTTT_ACT_INDEX ? (uint32_t)L.pair[in.act] : pair_to_edge(in.act & 255u, in.act >> 8);
+        const StepOut o = step_game<kRandom, kMode>(s, enew, kFull || a.coin != nullptr, in.coin & 1u, a.seed,
+                                                    a.game_base + (uint64_t)i, a.dword, L);
+        if (o.write_state) *reinterpret_cast<uint4*>(a.state + i) = make_uint4(s.x, s.y, s.z, s.w);
         // the reward is stored through an integer pointer: its two values differ only in bit
         // patterns (-0.0f / -1.0f), and a float-typed select gets "simplified" by the compiler
         // into an int->float conversion that loses the sign of zero
-        if (kFull || reward) *reinterpret_cast<uint32_t*>(elem(reward, i)) = reward_bits(win);   // env.py:49
-        if (kFull || done) *elem(done, i) = (uint8_t)((win != 0u) | (r.n > 8u));              // env.py:51
-        if (kFull || mask) *elem(mask, i) = L.legal[~r.classical & M9];  // mcts.py:87-91
-        if (kFull || status) *elem(status, i) = (uint8_t)st;
+        if (kFull || a.reward) reinterpret_cast<uint32_t*>(a.reward)[i] = reward_bits(o.win);   // env.py:49
+        if (kFull || a.done) a.done[i] = (uint8_t)o.done;                                       // env.py:51
+        if (kFull || a.mask) a.mask[i] = L.legal[~o.classical & M9];                            // mcts.py:87-91
+        if (kFull || a.status) a.status[i] = (uint8_t)o.status;
+        if (kRandom) {
+            if (a.action_out) a.action_out[i] = (uint8_t)o.action;
+            if (a.coin_out) a.coin_out[i] = (uint8_t)o.coin;
+        }
+    };
+
+    const uint32_t first = (blockIdx.x * (uint32_t)a.iters) * kThreads + threadIdx.x;
+    if (kPrefetch) {
+        StepIn cur = load(first);
+        for (int it = 0; it < a.iters; ++it) {
+            const uint32_t i = first + (uint32_t)it * kThreads;
+            StepIn nxt = cur;
+            if (it + 1 < a.iters) nxt = load(i + kThreads);
+            run(i, cur);
+            cur = nxt;
+        }
+    } else {
+        for (int it = 0; it < a.iters; ++it) {
+            const uint32_t i = first + (uint32_t)it * kThreads;
+            run(i, load(i));
+        }
     }
 }
 
 // K1 with compact I/O (one byte in, one 16-bit word out per game): see qttt_step_packed.
+// obs (optional): the post-step packed state is ALSO written there (the observation of a caller
+// whose buffers are not the state array itself, e.g. mapped host memory).
 __global__ void __launch_bounds__(kThreads)
 k_step_packed(qttt_state* __restrict__ state, const uint8_t* __restrict__ action_coin,
-              uint16_t* __restrict__ result, uint32_t n) {
+              uint16_t* __restrict__ result, qttt_state* __restrict__ obs, uint32_t n, int iters) {
     __shared__ __align__(16) uint8_t smem[kLutStepBytes];
     stage_luts(smem, kLutStepBytes);
     const Luts L = luts_from_image(smem);
-    const uint32_t stride = gridDim.x * kThreads;
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const uint32_t first = (blockIdx.x * (uint32_t)iters) * kThreads + threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+        const uint32_t i = first + (uint32_t)it * kThreads;
+        if (i >= n) break;
         uint4* sp = reinterpret_cast<uint4*>(state + i);
         const uint4 sv = *sp;
         State s{sv.x, sv.y, sv.z, sv.w};
         const uint32_t ac = action_coin[i];
         const StepResult r = step_core(s, (uint32_t)L.pair[ac & 63u], ac >> 7, L);
-        if (!r.illegal) *sp = make_uint4(s.x, s.y, s.z, s.w);
+        const uint4 out = make_uint4(s.x, s.y, s.z, s.w);
+        if (!r.illegal) *sp = out;
+        if (obs) *reinterpret_cast<uint4*>(obs + i) = out;
         const uint32_t win = any_line(s, r.classical, L) != 0u;
         const uint32_t term = win | (uint32_t)(r.n > 8u);
         result[i] = (uint16_t)((~r.classical & M9) | (term << 9) | (win << 10) | (r.illegal << 11));
+    }
+}
+
+// The same step for buffers in MAPPED PINNED HOST memory, read and written by the kernel itself
+// (no copy engine, no staging buffers): a block moves its chunk's 256 action bytes in as sixteen
+// 16-byte loads and its 256 result words out as thirty-two 16-byte stores, so every PCIe
+// transaction is a full 512-byte burst; the observation (16 B per game) is written by each
+// thread directly (512 contiguous bytes per warp).
+__global__ void __launch_bounds__(kThreads)
+k_step_packed_zc(qttt_state* __restrict__ state, const uint8_t* __restrict__ action_coin_host,
+                 uint16_t* __restrict__ result_host, qttt_state* __restrict__ obs_host, uint32_t n, int iters) {
+    __shared__ __align__(16) uint8_t smem[kLutStepBytes];
+    __shared__ __align__(16) uint8_t sh_in[kThreads];
+    __shared__ __align__(16) uint16_t sh_out[kThreads];
+    stage_luts(smem, kLutStepBytes);
+    const Luts L = luts_from_image(smem);
+    const uint32_t t = threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+        const uint32_t base = (blockIdx.x * (uint32_t)iters + (uint32_t)it) * kThreads;
+        if (base >= n) break;
+        const uint32_t valid = n - base < (uint32_t)kThreads ? n - base : (uint32_t)kThreads;
+        const bool wide = valid == (uint32_t)kThreads &&
+                          ((reinterpret_cast<uintptr_t>(action_coin_host + base) |
+                            reinterpret_cast<uintptr_t>(result_host + base)) & 15u) == 0u;
+        if (wide) {
+            if (t < kThreads / 16)
+                reinterpret_cast<uint4*>(sh_in)[t] = reinterpret_cast<const uint4*>(action_coin_host + base)[t];
+        } else if (t < valid) {
+            sh_in[t] = action_coin_host[base + t];
+        }
+        __syncthreads();
+        if (t < valid) {
+            const uint32_t i = base + t;
+            uint4* sp = reinterpret_cast<uint4*>(state + i);
+            const uint4 sv = *sp;
+            State s{sv.x, sv.y, sv.z, sv.w};
+            const uint32_t ac = sh_in[t];
+            const StepResult r = step_core(s, (uint32_t)L.pair[ac & 63u], ac >> 7, L);
+            const uint4 out = make_uint4(s.x, s.y, s.z, s.w);
+            if (!r.illegal) *sp = out;
+            if (obs_host) *reinterpret_cast<uint4*>(obs_host + i) = out;
+            const uint32_t win = any_line(s, r.classical, L) != 0u;
+            const uint32_t term = win | (uint32_t)(r.n > 8u);
+            sh_out[t] = (uint16_t)((~r.classical & M9) | (term << 9) | (win << 10) | (r.illegal << 11));
+        }
+        __syncthreads();
+        if (wide) {
+            if (t < kThreads / 8)
+                reinterpret_cast<uint4*>(result_host + base)[t] = reinterpret_cast<const uint4*>(sh_out)[t];
+        } else if (t < valid) {
+            result_host[base + t] = sh_out[t];
+        }
     }
 }
 
@@ -605,19 +707,27 @@ k_mcts_sync(MctsNode* __restrict__ pool, int64_t capacity, int32_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------ launch helpers
-// Persistent grid: exactly as many blocks as are resident at once (SM count x occupancy of
-// this kernel), so the grid-stride loops finish in one balanced wave.
+// Resident blocks of a kernel on the current device (SM count x occupancy), for the kernels
+// that still run as one persistent wave.  Cached per (kernel, device).
+static int resident_blocks(const void* kernel, int threads) {
+    struct Entry { const void* k; int dev, threads, blocks; };
+    static Entry cache[64];
+    static int used = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    for (int i = 0; i < used; ++i)
+        if (cache[i].k == kernel && cache[i].dev == dev && cache[i].threads == threads) return cache[i].blocks;
+    int sms = 148, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 4;
+    const int blocks = sms * per_sm;
+    if (used < 64) cache[used++] = Entry{kernel, dev, threads, blocks};   // benign race: worst case a recompute
+    return blocks;
+}
 template <class Kernel>
 static int grid_for(Kernel kernel, int64_t n) {
-    // resident blocks of this kernel on this kind of device: queried once per kernel (all
-    // devices of a box are the same part), so a launch costs no extra driver calls
-    static const int resident = [kernel]() {
-        int dev = 0, sms = 148, per_sm = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1)
-            per_sm = 4;
-        return sms * per_sm;
-    }();
+    const int resident = resident_blocks(reinterpret_cast<const void*>(kernel), kThreads);
     const int64_t want = (n + kThreads - 1) / kThreads;
     return (int)(want < resident ? (want < 1 ? 1 : want) : resident);
 }
@@ -626,6 +736,38 @@ static int check_launch() {
     return e == cudaSuccess ? QTTT_OK : -(1000 + (int)e);
 }
 static bool misaligned(const void* p, uintptr_t a) { return p && (reinterpret_cast<uintptr_t>(p) & (a - 1)); }
+
+// QTTT_NO_DEVICE unless the current device can run the sm_100a kernels of this library.
+static int device_ok() {
+    static int verdict[64];                 // 0 unknown, 1 ok, 2 not usable
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return QTTT_ERR_NO_DEVICE; }
+    if (dev < 0 || dev >= 64) return QTTT_OK;
+    if (verdict[dev] == 0) {
+        int major = 0;
+        const bool ok = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess && major == 10;
+        verdict[dev] = ok ? 1 : 2;
+    }
+    return verdict[dev] == 1 ? QTTT_OK : QTTT_ERR_NO_DEVICE;
+}
+
+// Tuning knobs of the step kernels, read once from the environment (experiments only; the
+// defaults are what the numbers in DESIGN.md were measured with).
+static int step_iters() {
+    static const int v = []() {
+        const char* e = getenv("QTTT_STEP_ITERS");
+        const int x = e ? atoi(e) : kStepIters;
+        return x < 1 ? 1 : (x > 64 ? 64 : x);
+    }();
+    return v;
+}
+static bool step_prefetch() {
+    static const bool v = []() {
+        const char* e = getenv("QTTT_STEP_PREFETCH");
+        return e ? atoi(e) != 0 : false;
+    }();
+    return v;
+}
 
 }  // namespace qttt
 
@@ -640,7 +782,7 @@ const char* qttt_strerror(int rc) {
         case QTTT_OK: return "ok";
         case QTTT_ERR_ARG: return "qttt: invalid argument (NULL buffer, negative size or bad enum)";
         case QTTT_ERR_ALIGN: return "qttt: buffer not aligned for its element type";
-        case QTTT_ERR_NO_DEVICE: return "qttt: no usable CUDA device";
+        case QTTT_ERR_NO_DEVICE: return "qttt: no usable CUDA device (the kernels are built for sm_100a only)";
         default: break;
     }
     if (rc <= -1000) return cudaGetErrorString((cudaError_t)(-rc - 1000));
@@ -648,43 +790,93 @@ const char* qttt_strerror(int rc) {
 }
 
 int qttt_reset(qttt_state* state, uint64_t* mask, int64_t n, void* stream) {
+    return qttt_reset_all(state, mask, nullptr, nullptr, nullptr, n, stream);
+}
+
+int qttt_reset_all(qttt_state* state, uint64_t* mask, float* reward, uint8_t* done, uint8_t* status,
+                   int64_t n, void* stream) {
     if (n == 0) return QTTT_OK;
     if (!state || n < 0) return QTTT_ERR_ARG;
-    if (misaligned(state, 16) || misaligned(mask, 8)) return QTTT_ERR_ALIGN;
-    k_reset<<<grid_for(k_reset, n), kThreads, 0, (cudaStream_t)stream>>>(state, mask, n);
+    if (misaligned(state, 16) || misaligned(mask, 8) || misaligned(reward, 4)) return QTTT_ERR_ALIGN;
+    if (const int rc = device_ok()) return rc;
+    k_reset<<<grid_for(k_reset, n), kThreads, 0, (cudaStream_t)stream>>>(state, mask, reward, done, status, n);
     return check_launch();
 }
 
 }  // extern "C"
 
 // Launches k_step over [0, n) in slices of at most 2^31 games (32-bit indices in the kernel).
-template <int kFmt, bool kRandom, bool kFresh = false>
-static int launch_step(qttt_state* state, const uint8_t* action, const uint8_t* coin, uint64_t seed,
-                       uint64_t game_base, float* reward, uint8_t* done, uint64_t* mask,
-                       uint8_t* status, uint8_t* action_out, uint8_t* coin_out, int64_t n,
-                       cudaStream_t st) {
+template <int kFmt, bool kRandom, int kMode>
+static int launch_step_mode(StepArgs a, int64_t n, cudaStream_t st) {
     const int64_t kSlice = 1ll << 31;
-    const bool full = reward && done && mask && status;
+    const bool full = !kRandom && a.coin && a.reward && a.done && a.mask && a.status;
+    const int iters = step_iters();
+    const bool pf = step_prefetch();
+    const int act_bytes = kFmt == QTTT_ACT_PAIR ? 2 : 1;
     for (int64_t lo = 0; lo < n; lo += kSlice) {
         const int64_t m = n - lo < kSlice ? n - lo : kSlice;
-        const int act_bytes = kFmt == QTTT_ACT_PAIR ? 2 : 1;
-        qttt_state* s_ = state + lo;
-        const uint8_t* a_ = action ? action + act_bytes * lo : nullptr;
-        const uint8_t* c_ = coin ? coin + lo : nullptr;
-        float* r_ = reward ? reward + lo : nullptr;
-        uint8_t* d_ = done ? done + lo : nullptr;
-        uint64_t* m_ = mask ? mask + lo : nullptr;
-        uint8_t* t_ = status ? status + lo : nullptr;
-        uint8_t* ao = action_out ? action_out + lo : nullptr;
-        uint8_t* co = coin_out ? coin_out + lo : nullptr;
-        if (full)
-            k_step<kFmt, kRandom, true, kFresh><<<grid_for(k_step<kFmt, kRandom, true, kFresh>, m), kThreads, 0, st>>>(s_, a_, c_, seed, game_base + (uint64_t)lo, r_, d_, m_, t_, ao, co, (uint32_t)m);
-        else
-            k_step<kFmt, kRandom, false, kFresh><<<grid_for(k_step<kFmt, kRandom, false, kFresh>, m), kThreads, 0, st>>>(s_, a_, c_, seed, game_base + (uint64_t)lo, r_, d_, m_, t_, ao, co, (uint32_t)m);
+        StepArgs b = a;
+        b.state = a.state + lo;
+        b.action = a.action ? a.action + act_bytes * lo : nullptr;
+        b.coin = a.coin ? a.coin + lo : nullptr;
+        b.game_base = a.game_base + (uint64_t)lo;
+        b.reward = a.reward ? a.reward + lo : nullptr;
+        b.done = a.done ? a.done + lo : nullptr;
+        b.mask = a.mask ? a.mask + lo : nullptr;
+        b.status = a.status ? a.status + lo : nullptr;
+        b.action_out = a.action_out ? a.action_out + lo : nullptr;
+        b.coin_out = a.coin_out ? a.coin_out + lo : nullptr;
+        b.n = (uint32_t)m;
+        b.iters = iters;
+        const int grid = chunk_grid(m, iters);
+        bool launched = false;
+        if constexpr (kFmt == QTTT_ACT_INDEX && !kRandom && kMode != kStepAutoNext) {
+            if (full) {                           // the headline shape gets the specialised variants
+                if (pf) k_step<kFmt, false, true, kMode, true><<<grid, kThreads, 0, st>>>(b);
+                else    k_step<kFmt, false, true, kMode, false><<<grid, kThreads, 0, st>>>(b);
+                launched = true;
+            }
+        }
+        if (!launched) k_step<kFmt, kRandom, false, kMode, false><<<grid, kThreads, 0, st>>>(b);
         const int rc = check_launch();
         if (rc != QTTT_OK) return rc;
     }
     return QTTT_OK;
+}
+
+template <int kFmt, bool kRandom>
+static int launch_step(const StepArgs& a, uint32_t flags, int64_t n, cudaStream_t st) {
+    if (flags & QTTT_STEP_FRESH) return launch_step_mode<kFmt, kRandom, kStepFresh>(a, n, st);
+    if (flags & QTTT_STEP_AUTORESET) return launch_step_mode<kFmt, kRandom, kStepAuto>(a, n, st);
+    if (flags & QTTT_STEP_AUTORESET_NEXT) return launch_step_mode<kFmt, kRandom, kStepAutoNext>(a, n, st);
+    return launch_step_mode<kFmt, kRandom, kStepPlain>(a, n, st);
+}
+
+static int step_entry(qttt_state* state, const void* action, int action_format, const uint8_t* coin,
+                      uint64_t seed, uint64_t game_base, uint64_t epoch, uint32_t flags, float* reward,
+                      uint8_t* done, uint64_t* mask, uint8_t* status, int64_t n, void* stream) {
+    if (action_format != QTTT_ACT_INDEX && action_format != QTTT_ACT_PAIR) return QTTT_ERR_ARG;
+    const uint32_t modes = flags & (QTTT_STEP_FRESH | QTTT_STEP_AUTORESET | QTTT_STEP_AUTORESET_NEXT);
+    if ((flags & ~(QTTT_STEP_FRESH | QTTT_STEP_AUTORESET | QTTT_STEP_AUTORESET_NEXT)) || (modes & (modes - 1)))
+        return QTTT_ERR_ARG;                                   // unknown flag, or two modes at once
+    if (n == 0) return QTTT_OK;
+    if (!state || !action || n < 0) return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(mask, 8) || misaligned(reward, 4)) return QTTT_ERR_ALIGN;
+    if (action_format == QTTT_ACT_PAIR && misaligned(action, 2)) return QTTT_ERR_ALIGN;
+    if (const int rc = device_ok()) return rc;
+    StepArgs a{};
+    a.state = state;
+    a.action = static_cast<const uint8_t*>(action);
+    a.coin = coin;
+    a.seed = seed;
+    a.game_base = game_base;
+    a.dword = domain_word(0u, epoch);
+    a.reward = reward;
+    a.done = done;
+    a.mask = mask;
+    a.status = status;
+    if (action_format == QTTT_ACT_INDEX) return launch_step<QTTT_ACT_INDEX, false>(a, flags, n, (cudaStream_t)stream);
+    return launch_step<QTTT_ACT_PAIR, false>(a, flags, n, (cudaStream_t)stream);
 }
 
 extern "C" {
@@ -692,68 +884,96 @@ extern "C" {
 int qttt_step(qttt_state* state, const void* action, int action_format, const uint8_t* coin,
               uint64_t seed, uint64_t game_base, float* reward, uint8_t* done, uint64_t* mask,
               uint8_t* status, int64_t n, void* stream) {
-    if (action_format != QTTT_ACT_INDEX && action_format != QTTT_ACT_PAIR) return QTTT_ERR_ARG;
-    if (n == 0) return QTTT_OK;
-    if (!state || !action || n < 0) return QTTT_ERR_ARG;
-    if (misaligned(state, 16) || misaligned(mask, 8) || misaligned(reward, 4)) return QTTT_ERR_ALIGN;
-    if (action_format == QTTT_ACT_PAIR && misaligned(action, 2)) return QTTT_ERR_ALIGN;
-    const uint8_t* act = static_cast<const uint8_t*>(action);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (action_format == QTTT_ACT_INDEX)
-        return launch_step<QTTT_ACT_INDEX, false>(state, act, coin, seed, game_base, reward, done, mask, status, nullptr, nullptr, n, st);
-    return launch_step<QTTT_ACT_PAIR, false>(state, act, coin, seed, game_base, reward, done, mask, status, nullptr, nullptr, n, st);
+    return step_entry(state, action, action_format, coin, seed, game_base, 0, 0, reward, done, mask, status, n, stream);
 }
 
 int qttt_reset_step(qttt_state* state, const void* action, int action_format, const uint8_t* coin,
                     uint64_t seed, uint64_t game_base, float* reward, uint8_t* done, uint64_t* mask,
                     uint8_t* status, int64_t n, void* stream) {
-    if (action_format != QTTT_ACT_INDEX && action_format != QTTT_ACT_PAIR) return QTTT_ERR_ARG;
-    if (n == 0) return QTTT_OK;
-    if (!state || !action || n < 0) return QTTT_ERR_ARG;
-    if (misaligned(state, 16) || misaligned(mask, 8) || misaligned(reward, 4)) return QTTT_ERR_ALIGN;
-    if (action_format == QTTT_ACT_PAIR && misaligned(action, 2)) return QTTT_ERR_ALIGN;
-    const uint8_t* act = static_cast<const uint8_t*>(action);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (action_format == QTTT_ACT_INDEX)
-        return launch_step<QTTT_ACT_INDEX, false, true>(state, act, coin, seed, game_base, reward, done, mask, status, nullptr, nullptr, n, st);
-    return launch_step<QTTT_ACT_PAIR, false, true>(state, act, coin, seed, game_base, reward, done, mask, status, nullptr, nullptr, n, st);
+    return step_entry(state, action, action_format, coin, seed, game_base, 0, QTTT_STEP_FRESH, reward, done, mask,
+                      status, n, stream);
 }
 
-int qttt_step_packed(qttt_state* state, const uint8_t* action_coin, uint16_t* result, int64_t n,
-                     void* stream) {
-    if (n == 0) return QTTT_OK;
-    if (!state || !action_coin || !result || n < 0) return QTTT_ERR_ARG;
-    if (misaligned(state, 16) || misaligned(result, 2)) return QTTT_ERR_ALIGN;
+int qttt_step_ex(qttt_state* state, const void* action, int action_format, const uint8_t* coin,
+                 uint64_t seed, uint64_t game_base, uint64_t epoch, uint32_t flags, float* reward,
+                 uint8_t* done, uint64_t* mask, uint8_t* status, int64_t n, void* stream) {
+    return step_entry(state, action, action_format, coin, seed, game_base, epoch, flags, reward, done, mask, status,
+                      n, stream);
+}
+
+static int packed_entry(qttt_state* state, const uint8_t* action_coin, uint16_t* result, qttt_state* obs,
+                        int64_t n, bool zero_copy, cudaStream_t st) {
     const int64_t kSlice = 1ll << 31;
+    const int iters = step_iters();
     for (int64_t lo = 0; lo < n; lo += kSlice) {
         const int64_t m = n - lo < kSlice ? n - lo : kSlice;
-        k_step_packed<<<grid_for(k_step_packed, m), kThreads, 0, (cudaStream_t)stream>>>(
-            state + lo, action_coin + lo, result + lo, (uint32_t)m);
+        qttt_state* o = obs ? obs + lo : nullptr;
+        if (zero_copy)
+            k_step_packed_zc<<<chunk_grid(m, iters), kThreads, 0, st>>>(state + lo, action_coin + lo, result + lo, o,
+                                                                         (uint32_t)m, iters);
+        else
+            k_step_packed<<<chunk_grid(m, iters), kThreads, 0, st>>>(state + lo, action_coin + lo, result + lo, o,
+                                                                      (uint32_t)m, iters);
         const int rc = check_launch();
         if (rc != QTTT_OK) return rc;
     }
     return QTTT_OK;
 }
 
+int qttt_step_packed(qttt_state* state, const uint8_t* action_coin, uint16_t* result, int64_t n,
+                     void* stream) {
+    return qttt_step_packed_obs(state, action_coin, result, nullptr, n, stream);
+}
+
+int qttt_step_packed_obs(qttt_state* state, const uint8_t* action_coin, uint16_t* result, qttt_state* obs,
+                         int64_t n, void* stream) {
+    if (n == 0) return QTTT_OK;
+    if (!state || !action_coin || !result || n < 0) return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(result, 2) || misaligned(obs, 16)) return QTTT_ERR_ALIGN;
+    if (const int rc = device_ok()) return rc;
+    return packed_entry(state, action_coin, result, obs, n, false, (cudaStream_t)stream);
+}
+
+int qttt_step_packed_mapped(qttt_state* state, const uint8_t* action_coin_host, uint16_t* result_host,
+                            qttt_state* obs_host, int64_t n, void* stream) {
+    if (n == 0) return QTTT_OK;
+    if (!state || !action_coin_host || !result_host || n < 0) return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(result_host, 2) || misaligned(obs_host, 16)) return QTTT_ERR_ALIGN;
+    if (const int rc = device_ok()) return rc;
+    return packed_entry(state, action_coin_host, result_host, obs_host, n, true, (cudaStream_t)stream);
+}
+
 int qttt_step_packed_host(qttt_state* state, const uint8_t* action_coin_host, uint16_t* result_host,
                           uint8_t* in_dev, uint16_t* out_dev, int64_t n, int64_t slice,
                           void* const* streams, int n_streams) {
+    return qttt_step_packed_host_obs(state, action_coin_host, result_host, nullptr, in_dev, out_dev, n, slice,
+                                     streams, n_streams);
+}
+
+int qttt_step_packed_host_obs(qttt_state* state, const uint8_t* action_coin_host, uint16_t* result_host,
+                              qttt_state* obs_host, uint8_t* in_dev, uint16_t* out_dev, int64_t n,
+                              int64_t slice, void* const* streams, int n_streams) {
     if (n == 0) return QTTT_OK;
     if (!state || !action_coin_host || !result_host || !in_dev || !out_dev || !streams || n < 0 ||
         slice < 1 || slice > (1ll << 31) || n_streams < 1)
         return QTTT_ERR_ARG;
-    if (misaligned(state, 16) || misaligned(out_dev, 2) || misaligned(result_host, 2)) return QTTT_ERR_ALIGN;
+    if (misaligned(state, 16) || misaligned(out_dev, 2) || misaligned(result_host, 2) || misaligned(obs_host, 16))
+        return QTTT_ERR_ALIGN;
+    if (const int rc = device_ok()) return rc;
     int k = 0;
     for (int64_t lo = 0; lo < n; lo += slice, ++k) {
         const int64_t m = n - lo < slice ? n - lo : slice;
         cudaStream_t st = (cudaStream_t)streams[k % n_streams];
         cudaError_t e = cudaMemcpyAsync(in_dev + lo, action_coin_host + lo, (size_t)m, cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) return -(1000 + (int)e);
-        k_step_packed<<<grid_for(k_step_packed, m), kThreads, 0, st>>>(state + lo, in_dev + lo, out_dev + lo, (uint32_t)m);
-        const int rc = check_launch();
+        const int rc = packed_entry(state + lo, in_dev + lo, out_dev + lo, nullptr, m, false, st);
         if (rc != QTTT_OK) return rc;
         e = cudaMemcpyAsync(result_host + lo, out_dev + lo, (size_t)m * 2, cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return -(1000 + (int)e);
+        if (obs_host) {     // the observation: the packed states themselves, straight from the state array
+            e = cudaMemcpyAsync(obs_host + lo, state + lo, (size_t)m * sizeof(qttt_state), cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return -(1000 + (int)e);
+        }
     }
     return QTTT_OK;
 }
@@ -761,10 +981,31 @@ int qttt_step_packed_host(qttt_state* state, const uint8_t* action_coin_host, ui
 int qttt_step_random(qttt_state* state, uint64_t seed, uint64_t game_base, uint8_t* action_out,
                      uint8_t* coin_out, float* reward, uint8_t* done, uint64_t* mask,
                      uint8_t* status, int64_t n, void* stream) {
+    return qttt_step_random_ex(state, seed, game_base, 0, 0, action_out, coin_out, reward, done, mask, status, n, stream);
+}
+
+int qttt_step_random_ex(qttt_state* state, uint64_t seed, uint64_t game_base, uint64_t epoch, uint32_t flags,
+                        uint8_t* action_out, uint8_t* coin_out, float* reward, uint8_t* done,
+                        uint64_t* mask, uint8_t* status, int64_t n, void* stream) {
+    const uint32_t modes = flags & (QTTT_STEP_FRESH | QTTT_STEP_AUTORESET | QTTT_STEP_AUTORESET_NEXT);
+    if ((flags & ~(QTTT_STEP_FRESH | QTTT_STEP_AUTORESET | QTTT_STEP_AUTORESET_NEXT)) || (modes & (modes - 1)))
+        return QTTT_ERR_ARG;
     if (n == 0) return QTTT_OK;
     if (!state || n < 0) return QTTT_ERR_ARG;
     if (misaligned(state, 16) || misaligned(mask, 8) || misaligned(reward, 4)) return QTTT_ERR_ALIGN;
-    return launch_step<QTTT_ACT_INDEX, true>(state, nullptr, nullptr, seed, game_base, reward, done, mask, status, action_out, coin_out, n, (cudaStream_t)stream);
+    if (const int rc = device_ok()) return rc;
+    StepArgs a{};
+    a.state = state;
+    a.seed = seed;
+    a.game_base = game_base;
+    a.dword = domain_word(0u, epoch);
+    a.reward = reward;
+    a.done = done;
+    a.mask = mask;
+    a.status = status;
+    a.action_out = action_out;
+    a.coin_out = coin_out;
+    return launch_step<QTTT_ACT_INDEX, true>(a, flags, n, (cudaStream_t)stream);
 }
 
 int qttt_observe(const qttt_state* state, int8_t* classical, int8_t* moves, uint8_t* n_moves,

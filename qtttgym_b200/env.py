@@ -57,18 +57,40 @@ class BatchedEnv:
         self.mask = torch.empty(n, dtype=torch.int64, device=dev)     # 36-bit legal mask
         self.status = torch.empty(n, dtype=torch.uint8, device=dev)
         self._host_streams = None            # lazily created by step_host
-        self._d_act = self._d_coin = None
+        self._stream_array = None
+        self._d_act = self._d_coin = self._d_res16 = None
+        # Episode counter folded into the Philox counter of the collapse coins: bumped by every
+        # reset (and by every step of an auto-resetting batch), so that successive episodes in
+        # the same env slots do not replay the same coins.  Part of state_dict().
+        self.epoch = 0
+        self._first_reset = True
         self.reset()
 
     # ------------------------------------------------------------------ gym-like API
     def reset(self, *, seed=None, options=None):
         """env.py:55-57.  ``seed`` / ``options`` are accepted and ignored, as in the reference (Q4)."""
+        if self._first_reset:
+            self._first_reset = False         # the constructor's reset: epoch 0 is the first episode
+        else:
+            self.epoch += 1
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.qttt_reset(self.state.data_ptr(), self.mask.data_ptr(),
-                                           self.num_envs, _stream_ptr(self.device)))
-        return self._obs(), {"action_mask": self.mask}
+            _lib.check(self.lib.qttt_reset_all(self.state.data_ptr(), self.mask.data_ptr(),
+                                               self.reward.data_ptr(), self.done.data_ptr(),
+                                               self.status.data_ptr(), self.num_envs,
+                                               _stream_ptr(self.device)))
+        return self._obs(), _Info(self, {"action_mask": self.mask})
 
-    def step(self, actions, choices=None):
+    @staticmethod
+    def _mode_flags(autoreset):
+        if not autoreset:
+            return 0
+        if autoreset is True or autoreset == "apply":
+            return _lib.STEP_AUTORESET
+        if autoreset == "next":
+            return _lib.STEP_AUTORESET_NEXT
+        raise ValueError("autoreset must be False, True / 'apply' or 'next'")
+
+    def step(self, actions, choices=None, autoreset=False):
         """env.py:34-53 for every env.
 
         actions : uint8[N] action indices 0..35 (mcts.py:339-349) **or** int8[N,2] ``(a, b)``
@@ -77,61 +99,99 @@ class BatchedEnv:
         choices : uint8[N] forced collapse coins (0 -> the closing move falls into its smaller
                   square, qeval.py:35), consumed only by envs whose move closes a cycle;
                   ``None`` -> Philox coins.
+        autoreset : ``False`` -- the reference's behaviour: finished games keep accepting moves
+                  (Q3) or idle on illegal ones; ``True`` / ``"apply"`` -- a game that is over on
+                  entry restarts from the empty board inside the same launch and the action is
+                  applied to the fresh game; ``"next"`` -- it restarts and its action is ignored
+                  (the next-step autoreset of vector envs).  ``info["status"] & 4`` marks the envs
+                  that were reset.
         Returns ``(obs, reward f32[N], terminated bool[N], truncated bool[N], info)``; reward is
         the reference's -1.0 / -0.0 (quirk Q1).  The returned tensors are views of buffers that
         the next ``step`` overwrites.
         """
         act, fmt = self._check_actions(actions)
-        coin = None
-        if choices is not None:
-            coin = choices if choices.dtype == torch.uint8 else choices.to(torch.uint8)
-            coin = coin.contiguous()
-            if coin.device != self.device or coin.numel() != self.num_envs:
-                raise ValueError("choices must be a uint8[N] tensor on the env's device")
+        coin = self._check_choices(choices)
+        flags = self._mode_flags(autoreset)
+        if flags:
+            self.epoch += 1        # per-env episodes diverge: every step of the batch gets its own epoch
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.qttt_step(
+            _lib.check(self.lib.qttt_step_ex(
                 self.state.data_ptr(), act.data_ptr(), fmt, _lib.ptr(coin), self.seed,
-                self.game_base, self.reward.data_ptr(), self.done.data_ptr(),
+                self.game_base, self.epoch, flags, self.reward.data_ptr(), self.done.data_ptr(),
                 self.mask.data_ptr(), self.status.data_ptr(), self.num_envs,
                 _stream_ptr(self.device)))
         return self._result()
+
+    def _check_choices(self, choices):
+        if choices is None:
+            return None
+        coin = choices if choices.dtype == torch.uint8 else choices.to(torch.uint8)
+        coin = coin.contiguous()
+        if coin.device != self.device or coin.numel() != self.num_envs:
+            raise ValueError("choices must be a uint8[N] tensor on the env's device")
+        return coin
 
     def reset_step(self, actions, choices=None):
         """``reset()`` followed by ``step(actions, choices)`` as ONE kernel launch
         (``qttt_reset_step``): the games restart from the empty board, so the packed state is
         written but never read.  Returns what ``step`` returns."""
         act, fmt = self._check_actions(actions)
-        coin = None
-        if choices is not None:
-            coin = choices if choices.dtype == torch.uint8 else choices.to(torch.uint8)
-            coin = coin.contiguous()
-            if coin.device != self.device or coin.numel() != self.num_envs:
-                raise ValueError("choices must be a uint8[N] tensor on the env's device")
+        coin = self._check_choices(choices)
+        self.epoch += 1                       # a reset: the next episode
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.qttt_reset_step(
+            _lib.check(self.lib.qttt_step_ex(
                 self.state.data_ptr(), act.data_ptr(), fmt, _lib.ptr(coin), self.seed,
-                self.game_base, self.reward.data_ptr(), self.done.data_ptr(),
-                self.mask.data_ptr(), self.status.data_ptr(), self.num_envs,
+                self.game_base, self.epoch, _lib.STEP_FRESH, self.reward.data_ptr(),
+                self.done.data_ptr(), self.mask.data_ptr(), self.status.data_ptr(), self.num_envs,
                 _stream_ptr(self.device)))
         return self._result()
 
-    def step_random(self, record: bool = False):
+    def step_random(self, record: bool = False, autoreset=False, out=None):
         """One ply of the uniform-random policy of ``MCTS._simulate`` (mcts.py:185-198) for
         every env that is not terminated; terminated envs are left untouched
-        (``info["status"] == 2``)."""
+        (``info["status"] == 2``) unless ``autoreset`` restarts them (see ``step``): then every
+        call plays one ply in every env -- continuous random self-play through the step API.
+        ``record``: the chosen actions / coins are returned in ``info`` (``out``: a pair of
+        uint8[N] tensors to record into)."""
         a_out = c_out = None
-        if record:
+        if out is not None:
+            a_out, c_out = out
+        elif record:
             a_out = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
             c_out = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
+        flags = self._mode_flags(autoreset)
+        if flags:
+            self.epoch += 1
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.qttt_step_random(
-                self.state.data_ptr(), self.seed, self.game_base, _lib.ptr(a_out), _lib.ptr(c_out),
-                self.reward.data_ptr(), self.done.data_ptr(), self.mask.data_ptr(),
-                self.status.data_ptr(), self.num_envs, _stream_ptr(self.device)))
-        out = self._result()
-        if record:
-            out[4]["action"], out[4]["coin"] = a_out, c_out
-        return out
+            _lib.check(self.lib.qttt_step_random_ex(
+                self.state.data_ptr(), self.seed, self.game_base, self.epoch, flags,
+                _lib.ptr(a_out), _lib.ptr(c_out), self.reward.data_ptr(), self.done.data_ptr(),
+                self.mask.data_ptr(), self.status.data_ptr(), self.num_envs,
+                _stream_ptr(self.device)))
+        res = self._result()
+        if a_out is not None:
+            res[4]["action"], res[4]["coin"] = a_out, c_out
+        return res
+
+    def _host_pipeline(self, n_streams: int):
+        """Side streams and device staging buffers of the host-buffer paths; (re)built whenever
+        the stream count changes, together with the ctypes array of their handles."""
+        import ctypes as C
+        if self._host_streams is None or len(self._host_streams) != n_streams:
+            n, dev = self.num_envs, self.device
+            self._host_streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
+            self._stream_array = (C.c_void_p * n_streams)(*[st.cuda_stream for st in self._host_streams])
+            if self._d_act is None:
+                self._d_act = torch.empty(n, dtype=torch.uint8, device=dev)
+                self._d_coin = torch.empty(n, dtype=torch.uint8, device=dev)
+                self._d_res16 = torch.empty(n, dtype=torch.int16, device=dev)
+        return self._host_streams
+
+    def _slices(self, chunks: int):
+        n = self.num_envs
+        chunks = max(1, min(chunks, (n + 255) // 256))
+        per = -(-n // chunks)
+        return -(-per // 256) * 256
 
     def step_host(self, actions_host, choices_host, reward_host, done_host, mask_host,
                   chunks: int = 8, n_streams: int = 4):
@@ -151,22 +211,15 @@ class BatchedEnv:
             if t.dtype != dt or t.numel() != n or t.device.type != "cpu" or not t.is_contiguous():
                 raise ValueError("step_host expects contiguous CPU tensors of N elements "
                                  "(uint8 actions, uint8 coins, f32 reward, bool done, int64 mask)")
-        if self._host_streams is None or len(self._host_streams) != n_streams:
-            self._host_streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
-            self._d_act = torch.empty(n, dtype=torch.uint8, device=dev)
-            self._d_coin = torch.empty(n, dtype=torch.uint8, device=dev)
+        streams = self._host_pipeline(n_streams)
         cur = torch.cuda.current_stream(dev)
         ready = torch.cuda.Event()
         ready.record(cur)
-        chunks = max(1, min(chunks, (n + 255) // 256))
-        per = -(-n // chunks)
-        per = -(-per // 256) * 256
+        per = self._slices(chunks)
         with torch.cuda.device(dev):
-            for c in range(chunks):
+            for c in range(-(-n // per)):
                 lo, hi = c * per, min(n, (c + 1) * per)
-                if lo >= hi:
-                    break
-                st = self._host_streams[c % n_streams]
+                st = streams[c % n_streams]
                 st.wait_event(ready)
                 with torch.cuda.stream(st):
                     self._d_act[lo:hi].copy_(actions_host[lo:hi], non_blocking=True)
@@ -180,43 +233,55 @@ class BatchedEnv:
                     reward_host[lo:hi].copy_(self.reward[lo:hi], non_blocking=True)
                     done_host[lo:hi].copy_(self.done[lo:hi], non_blocking=True)
                     mask_host[lo:hi].copy_(self.mask[lo:hi], non_blocking=True)
-            for st in self._host_streams:
+            for st in streams:
                 fin = torch.cuda.Event()
                 fin.record(st)
                 cur.wait_event(fin)
         return reward_host, done_host, mask_host
 
-    def step_host_packed(self, action_coin_host, result_host, chunks: int = 8, n_streams: int = 4):
-        """``step_host`` with compact I/O (``qttt_step_packed_host``): 1 byte in and 2 bytes out
-        per env cross PCIe instead of 2 + 13.  ``action_coin_host`` uint8[N] from
-        ``pack_actions``; ``result_host`` int16[N], decoded with ``unpack_result`` (the 36-bit
-        legal mask is re-expanded on the host from the 9-bit free-square set).  Same transition,
-        bit for bit.  The slices are pipelined over side streams inside the C call."""
-        import ctypes as C
+    def step_host_packed(self, action_coin_host, result_host, obs_host=None, chunks: int = 8,
+                         n_streams: int = 4, mapped: bool = False):
+        """``step_host`` with compact I/O: 1 byte in and 2 bytes out per env cross PCIe instead of
+        2 + 13.  ``action_coin_host`` uint8[N] from ``pack_actions``; ``result_host`` int16[N],
+        decoded with ``unpack_result`` (the 36-bit legal mask is re-expanded on the host from the
+        9-bit free-square set).  ``obs_host`` (optional, pinned int32[N,4]) also receives the
+        observation -- the packed post-step states, 16 more bytes per env (what the reference's
+        ``Env.step`` returns as ``obs``, env.py:46; decode with ``observe_states`` or on the host).
+        Same transition, bit for bit.
+
+        ``mapped=False`` (``qttt_step_packed_host[_obs]``): slices pipelined over side streams with
+        one ``cudaMemcpyAsync`` per array per slice.  ``mapped=True`` (``qttt_step_packed_mapped``):
+        ONE kernel launch on the current stream reads and writes the pinned host buffers itself
+        across PCIe (no copy engine, no staging); the buffers must be pinned (``pin_memory()``)."""
         n, dev = self.num_envs, self.device
-        for t, dt in ((action_coin_host, torch.uint8), (result_host, torch.int16)):
-            if t.dtype != dt or t.numel() != n or t.device.type != "cpu" or not t.is_contiguous():
-                raise ValueError("step_host_packed expects contiguous CPU uint8[N] / int16[N] tensors")
-        if self._host_streams is None or len(self._host_streams) != n_streams:
-            self._host_streams = [torch.cuda.Stream(dev) for _ in range(n_streams)]
-            self._d_act = torch.empty(n, dtype=torch.uint8, device=dev)
-            self._d_coin = torch.empty(n, dtype=torch.uint8, device=dev)
-        if getattr(self, "_d_res16", None) is None:
-            self._d_res16 = torch.empty(n, dtype=torch.int16, device=dev)
-            self._stream_array = (C.c_void_p * n_streams)(*[st.cuda_stream for st in self._host_streams])
+        checks = [(action_coin_host, torch.uint8, n), (result_host, torch.int16, n)]
+        if obs_host is not None:
+            checks.append((obs_host, torch.int32, 4 * n))
+        for t, dt, numel in checks:
+            if t.dtype != dt or t.numel() != numel or t.device.type != "cpu" or not t.is_contiguous():
+                raise ValueError("step_host_packed expects contiguous CPU uint8[N] / int16[N] (/ int32[N,4]) tensors")
+        if mapped:
+            if not (action_coin_host.is_pinned() and result_host.is_pinned()
+                    and (obs_host is None or obs_host.is_pinned())):
+                raise ValueError("mapped=True needs pinned host tensors (tensor.pin_memory())")
+            with torch.cuda.device(dev):
+                _lib.check(self.lib.qttt_step_packed_mapped(
+                    self.state.data_ptr(), action_coin_host.data_ptr(), result_host.data_ptr(),
+                    _lib.ptr(obs_host), n, _stream_ptr(dev)))
+            return result_host
+        streams = self._host_pipeline(n_streams)
         cur = torch.cuda.current_stream(dev)
         ready = torch.cuda.Event()
         ready.record(cur)
-        chunks = max(1, min(chunks, (n + 255) // 256))
-        per = -(-(-(-n // chunks)) // 256) * 256
+        per = self._slices(chunks)
         with torch.cuda.device(dev):
-            for st in self._host_streams:
+            for st in streams:
                 st.wait_event(ready)
-            _lib.check(self.lib.qttt_step_packed_host(
+            _lib.check(self.lib.qttt_step_packed_host_obs(
                 self.state.data_ptr(), action_coin_host.data_ptr(), result_host.data_ptr(),
-                self._d_act.data_ptr(), self._d_res16.data_ptr(), n, per, self._stream_array, n_streams),
-                launches=-(-n // per))
-            for st in self._host_streams:
+                _lib.ptr(obs_host), self._d_act.data_ptr(), self._d_res16.data_ptr(), n, per,
+                self._stream_array, n_streams), launches=-(-n // per))
+            for st in streams:
                 fin = torch.cuda.Event()
                 fin.record(st)
                 cur.wait_event(fin)
@@ -246,13 +311,14 @@ class BatchedEnv:
         """Everything needed to resume: the packed states plus the RNG keying.  (The reference
         has no checkpointing of games; here the whole batch is one tensor.)"""
         return {"state": self.state.clone(), "seed": self.seed, "game_base": self.game_base,
-                "num_envs": self.num_envs}
+                "num_envs": self.num_envs, "epoch": self.epoch}
 
     def load_state_dict(self, sd):
         if int(sd["num_envs"]) != self.num_envs:
             raise ValueError("checkpoint holds a different number of envs")
         self.state.copy_(sd["state"].to(self.device))
         self.seed, self.game_base = int(sd["seed"]), int(sd["game_base"])
+        self.epoch = int(sd.get("epoch", 0))
         # reward / done / mask are functions of the state: recompute them with a no-op step
         noop = torch.full((self.num_envs,), 255, dtype=torch.uint8, device=self.device)
         self.step(noop)
@@ -260,7 +326,12 @@ class BatchedEnv:
 
     def turn(self):
         """env.py:65-66: len(moves) per env (uint8[N])."""
-        return ((self.state[:, 0] >> 27) & 15).to(torch.uint8)
+        out = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.qttt_observe(self.state.data_ptr(), None, None, out.data_ptr(), None, None,
+                                             None, None, None, None, None, self.num_envs,
+                                             _stream_ptr(self.device)))
+        return out
 
     def observ(self):
         return self.observation()
@@ -282,9 +353,22 @@ class BatchedEnv:
         return out
 
     def action_mask(self):
-        """mcts.py:87-91 for every env: bool[N,36]."""
-        bits = torch.arange(36, device=self.device, dtype=torch.int64)
-        return ((self.mask.unsqueeze(1) >> bits) & 1).bool()
+        """mcts.py:87-91 for every env: bool[N,36] (``qttt_observe``'s ``mask_bool`` output)."""
+        out = torch.empty((self.num_envs, 36), dtype=torch.bool, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.qttt_observe(self.state.data_ptr(), None, None, None, None, None, None,
+                                             None, None, None, out.data_ptr(), self.num_envs,
+                                             _stream_ptr(self.device)))
+        return out
+
+    def reward_p1(self):
+        """``Env._reward()`` (env.py:87-112) per env: +1 X has the earlier line, -1 O, else 0."""
+        out = torch.empty(self.num_envs, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.qttt_observe(self.state.data_ptr(), None, None, None, None, None, None,
+                                             None, out.data_ptr(), None, None, self.num_envs,
+                                             _stream_ptr(self.device)))
+        return out
 
     # ------------------------------------------------------------------ helpers
     def load_positions(self, classical, moves, n_moves):
@@ -299,7 +383,10 @@ class BatchedEnv:
             raise ValueError("actions must live on the env's device")
         if actions.dim() == 1:
             if actions.dtype != torch.uint8:
-                actions = actions.to(torch.uint8)
+                # anything outside 0..35 is an illegal action; keep it one after the cast too
+                # (260 must not wrap into the legal index 4)
+                actions = torch.where((actions >= 0) & (actions < 36), actions,
+                                      torch.full_like(actions, 255)).to(torch.uint8)
             fmt = _lib.ACT_INDEX
         elif actions.dim() == 2 and actions.shape[1] == 2:
             if actions.dtype != torch.int8:
@@ -319,12 +406,58 @@ class BatchedEnv:
 
     def invalid(self):
         """bool[N]: the last ``step`` was a swallowed illegal action for this env (env.py:41-43)."""
-        return self.status == 1
+        return (self.status & 3) == 1
 
     def _result(self):
-        # no extra kernels here: everything returned is a buffer the step kernel wrote
-        info = {"action_mask": self.mask, "status": self.status}
+        # no extra kernels here: everything returned is a buffer the step kernel wrote; the
+        # derived entries of ``info`` are computed when (and only when) they are looked up
+        info = _Info(self, {"action_mask": self.mask, "status": self.status})
         return self._obs(), self.reward, self.done, self._never, info
+
+
+class _Info(dict):
+    """``info`` of ``BatchedEnv.reset`` / ``step``.  ``action_mask`` (int64[N], bit k = action k
+    is legal) and ``status`` are buffers the step kernel wrote.  The other entries SURVEY (b)
+    lists are derived from the state on first lookup (one ``qttt_observe`` launch each), so a
+    training loop that never reads them pays nothing:
+
+    ``invalid``          bool[N]   the action was a swallowed illegal no-op (env.py:41-43)
+    ``reward_p1``        f32[N]    ``Env._reward()`` (env.py:87-112)
+    ``winner``           uint8[N]  0 none / draw, 1 X, 2 O (mcts.py:52-65)
+    ``action_mask_bool`` bool[N,36] ``GameState.action_mask()`` (mcts.py:87-91)
+    ``reset``            bool[N]   the env was auto-reset at the start of this step
+    """
+    _LAZY = ("invalid", "reward_p1", "winner", "action_mask_bool", "reset")
+
+    def __init__(self, env, eager):
+        super().__init__(eager)
+        self._env = env
+
+    def __missing__(self, key):
+        env = self._env
+        if key == "invalid":
+            v = (env.status & 3) == 1
+        elif key == "reset":
+            v = (env.status & 4) != 0
+        elif key == "reward_p1":
+            v = env.reward_p1()
+        elif key == "winner":
+            v = env.winner()
+        elif key == "action_mask_bool":
+            v = env.action_mask()
+        else:
+            raise KeyError(key)
+        self[key] = v
+        return v
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._LAZY
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
 
 
 def pack_actions(actions, choices):

@@ -116,6 +116,27 @@ class EmuGames:
                           C.c_int64(self.n))
         return o
 
+    def step_ex(self, actions, coins=None, seed=0, game_base=0, epoch=0, flags=0):
+        ac = np.ascontiguousarray(actions, dtype=np.uint8)
+        co = None if coins is None else np.ascontiguousarray(coins, dtype=np.uint8)
+        o = self._outs()
+        rc = self.lib.emu_step_ex(_p(self.state), _p(ac), 0, _p(co), C.c_uint64(seed), C.c_uint64(game_base),
+                                  C.c_uint64(epoch), C.c_uint32(flags), _p(o["reward"]), _p(o["done"]),
+                                  _p(o["mask"]), _p(o["status"]), C.c_int64(self.n))
+        assert rc == 0
+        return o
+
+    def step_random_ex(self, seed, game_base=0, epoch=0, flags=0):
+        o = self._outs()
+        o["action"] = np.empty(self.n, np.uint8)
+        o["coin"] = np.empty(self.n, np.uint8)
+        rc = self.lib.emu_step_random_ex(_p(self.state), C.c_uint64(seed), C.c_uint64(game_base),
+                                         C.c_uint64(epoch), C.c_uint32(flags), _p(o["action"]), _p(o["coin"]),
+                                         _p(o["reward"]), _p(o["done"]), _p(o["mask"]), _p(o["status"]),
+                                         C.c_int64(self.n))
+        assert rc == 0
+        return o
+
     def step_packed(self, action_coin):
         ac = np.ascontiguousarray(action_coin, dtype=np.uint8)
         res = np.empty(self.n, np.uint16)
@@ -155,15 +176,17 @@ class EmuGames:
         self.lib.emu_pack(_p(self.state), _p(cl), _p(mv), _p(nm), C.c_int64(self.n))
         return self
 
-    def qeval_both(self, actions):
+    def qeval_both(self, actions, squares=True):
+        """squares=False takes the one-sweep path (no per-move squares), like the library."""
         n = self.n
         ac = np.ascontiguousarray(actions, np.uint8)
         o = dict(next0=np.empty((n, 4), np.uint32), next1=np.empty((n, 4), np.uint32),
                  board0=np.empty(n, np.uint64), board1=np.empty(n, np.uint64),
-                 sq0=np.empty((n, 9), np.int8), sq1=np.empty((n, 9), np.int8),
                  closes=np.empty(n, np.uint8), result_prob=np.empty((n, 3), np.float32))
+        if squares:
+            o.update(sq0=np.empty((n, 9), np.int8), sq1=np.empty((n, 9), np.int8))
         self.lib.emu_qeval_both(_p(self.state), _p(ac), _p(o["next0"]), _p(o["next1"]),
-                                _p(o["board0"]), _p(o["board1"]), _p(o["sq0"]), _p(o["sq1"]),
+                                _p(o["board0"]), _p(o["board1"]), _p(o.get("sq0")), _p(o.get("sq1")),
                                 _p(o["closes"]), _p(o["result_prob"]), C.c_int64(n))
         return o
 
@@ -252,12 +275,43 @@ class CudaGames:
         co = None if coins is None else t.from_numpy(np.ascontiguousarray(coins, np.uint8)).cuda()
         return self._outs(self.env.step(ac, co))
 
-    def step_packed(self, action_coin):
+    _AUTORESET = {0: False, 2: True, 4: "next"}
+
+    def step_ex(self, actions, coins=None, seed=0, game_base=0, epoch=0, flags=0):
+        """through BatchedEnv.step / reset_step (which own the epoch counter: it is preset here
+        so that the call lands on the requested epoch)."""
+        t = self.torch
+        env = self.env
+        env.seed, env.game_base = seed, game_base
+        ac = t.from_numpy(np.ascontiguousarray(actions, np.uint8)).cuda()
+        co = None if coins is None else t.from_numpy(np.ascontiguousarray(coins, np.uint8)).cuda()
+        if flags == 1:
+            env.epoch = epoch - 1
+            return self._outs(env.reset_step(ac, co))
+        env.epoch = epoch - (1 if flags else 0)
+        return self._outs(env.step(ac, co, autoreset=self._AUTORESET[flags]))
+
+    def step_random_ex(self, seed, game_base=0, epoch=0, flags=0):
+        env = self.env
+        env.seed, env.game_base = seed, game_base
+        env.epoch = epoch - (1 if flags else 0)
+        res = env.step_random(record=True, autoreset=self._AUTORESET[flags])
+        o = self._outs(res)
+        o["action"] = res[4]["action"].cpu().numpy()
+        o["coin"] = res[4]["coin"].cpu().numpy()
+        return o
+
+    def step_packed(self, action_coin, variant="copy"):
+        """variant: "copy" (cudaMemcpyAsync pipeline), "copy_obs" (+ observation), "mapped"
+        (the kernel reads/writes the pinned host buffers itself), "mapped_obs"."""
         t = self.torch
         ac = t.from_numpy(np.ascontiguousarray(action_coin, np.uint8)).pin_memory()
         res = t.empty(self.n, dtype=t.int16).pin_memory()
-        self.env.step_host_packed(ac, res, chunks=3, n_streams=2)
+        obs = t.empty((self.n, 4), dtype=t.int32).pin_memory() if variant.endswith("obs") else None
+        self.env.step_host_packed(ac, res, obs_host=obs, chunks=3, n_streams=2, mapped=variant.startswith("mapped"))
         t.cuda.synchronize()
+        if obs is not None:
+            self.last_obs = obs.numpy().view(np.uint32).copy()
         return res.numpy().view(np.uint16).copy()
 
     def step_random(self, seed, game_base=0):
@@ -287,10 +341,10 @@ class CudaGames:
     def state(self):
         return self.env.state.cpu().numpy().view(np.uint32)
 
-    def qeval_both(self, actions):
+    def qeval_both(self, actions, squares=True):
         t = self.torch
         ac = t.from_numpy(np.ascontiguousarray(actions, np.uint8)).cuda()
-        res = self.Q.qeval_both(self.env.state, ac, want_squares=True)
+        res = self.Q.qeval_both(self.env.state, ac, want_squares=squares)
         out = {k: v.cpu().numpy() for k, v in res.items()}
         for k in ("next0", "next1"):
             out[k] = out[k].view(np.uint32)

@@ -14,6 +14,43 @@ using namespace qttt;
 static const LutImage g_img = make_lut_image();
 static Luts luts() { return luts_from_image(&g_img); }
 
+// The per-game body is qttt_core.cuh's step_game -- the very function the step kernels call.
+template <bool kRandom, int kMode>
+static void emu_step_mode(State* state, const void* action, int fmt, const uint8_t* coin, uint64_t seed,
+                          uint64_t game_base, uint64_t epoch, uint8_t* action_out, uint8_t* coin_out,
+                          float* reward, uint8_t* done, uint64_t* mask, uint8_t* status, int64_t n) {
+    const Luts L = luts();
+    const uint8_t* act = static_cast<const uint8_t*>(action);
+    const uint32_t dword = domain_word(0u, epoch);
+    for (int64_t i = 0; i < n; ++i) {
+        State s = state[i];
+        uint32_t enew = 0u;
+        if (!kRandom) enew = fmt == 0 ? (uint32_t)L.pair[act[i]] : pair_to_edge(act[2 * i], act[2 * i + 1]);
+        const StepOut o = step_game<kRandom, kMode>(s, enew, coin != nullptr, coin ? (coin[i] & 1u) : 0u, seed,
+                                                    game_base + (uint64_t)i, dword, L);
+        if (o.write_state) state[i] = s;
+        if (reward) reinterpret_cast<uint32_t*>(reward)[i] = reward_bits(o.win);
+        if (done) done[i] = (uint8_t)o.done;
+        if (mask) mask[i] = L.legal[~o.classical & M9];
+        if (status) status[i] = (uint8_t)o.status;
+        if (kRandom && action_out) action_out[i] = (uint8_t)o.action;
+        if (kRandom && coin_out) coin_out[i] = (uint8_t)o.coin;
+    }
+}
+
+template <bool kRandom>
+static int emu_step_flags(uint32_t flags, State* state, const void* action, int fmt, const uint8_t* coin,
+                          uint64_t seed, uint64_t game_base, uint64_t epoch, uint8_t* action_out,
+                          uint8_t* coin_out, float* reward, uint8_t* done, uint64_t* mask, uint8_t* status,
+                          int64_t n) {
+    if (flags == 0u) emu_step_mode<kRandom, kStepPlain>(state, action, fmt, coin, seed, game_base, epoch, action_out, coin_out, reward, done, mask, status, n);
+    else if (flags == 1u) emu_step_mode<kRandom, kStepFresh>(state, action, fmt, coin, seed, game_base, epoch, action_out, coin_out, reward, done, mask, status, n);
+    else if (flags == 2u) emu_step_mode<kRandom, kStepAuto>(state, action, fmt, coin, seed, game_base, epoch, action_out, coin_out, reward, done, mask, status, n);
+    else if (flags == 4u) emu_step_mode<kRandom, kStepAutoNext>(state, action, fmt, coin, seed, game_base, epoch, action_out, coin_out, reward, done, mask, status, n);
+    else return -1;
+    return 0;
+}
+
 extern "C" {
 
 int emu_reset(State* state, uint64_t* mask, int64_t n) {
@@ -24,23 +61,13 @@ int emu_reset(State* state, uint64_t* mask, int64_t n) {
 int emu_step(State* state, const void* action, int fmt, const uint8_t* coin, uint64_t seed,
              uint64_t game_base, float* reward, uint8_t* done, uint64_t* mask, uint8_t* status,
              int64_t n) {
-    const Luts L = luts();
-    const uint8_t* act = static_cast<const uint8_t*>(action);
-    for (int64_t i = 0; i < n; ++i) {
-        State s = state[i];
-        uint32_t enew, c;
-        if (fmt == 0) enew = L.pair[act[i]];
-        else enew = pair_to_edge(act[2 * i], act[2 * i + 1]);
-        if (coin) c = coin[i] & 1u;
-        else {
-            uint32_t word;
-            ply_draw(seed, game_base + (uint64_t)i, n_moves(s), 0u, word, c);
-        }
-        const StepResult r = step_core(s, enew, c, L);
-        state[i] = s;
-        emit_step_outputs(s, r, r.illegal, L, reward, done, mask, status, i);
-    }
-    return 0;
+    return emu_step_flags<false>(0u, state, action, fmt, coin, seed, game_base, 0, nullptr, nullptr, reward, done, mask, status, n);
+}
+
+int emu_step_ex(State* state, const void* action, int fmt, const uint8_t* coin, uint64_t seed,
+                uint64_t game_base, uint64_t epoch, uint32_t flags, float* reward, uint8_t* done,
+                uint64_t* mask, uint8_t* status, int64_t n) {
+    return emu_step_flags<false>(flags, state, action, fmt, coin, seed, game_base, epoch, nullptr, nullptr, reward, done, mask, status, n);
 }
 
 int emu_step_packed(State* state, const uint8_t* action_coin, uint16_t* result, int64_t n) {
@@ -60,21 +87,13 @@ int emu_step_packed(State* state, const uint8_t* action_coin, uint16_t* result, 
 int emu_step_random(State* state, uint64_t seed, uint64_t game_base, uint8_t* action_out,
                     uint8_t* coin_out, float* reward, uint8_t* done, uint64_t* mask,
                     uint8_t* status, int64_t n) {
-    const Luts L = luts();
-    for (int64_t i = 0; i < n; ++i) {
-        State s = state[i];
-        const uint32_t C = classical(s), nm = n_moves(s);
-        const bool finished = (any_line(s, C, L) != 0u) | (nm >= 9u);
-        uint32_t act, c;
-        policy_draw(seed, game_base + (uint64_t)i, nm, 0u, L.legal[~C & M9], act, c);
-        if (finished) { act = 255u; c = 0u; }
-        if (action_out) action_out[i] = (uint8_t)act;
-        if (coin_out) coin_out[i] = (uint8_t)c;
-        const StepResult r = step_core(s, (uint32_t)L.pair[act], c, L);
-        state[i] = s;
-        emit_step_outputs(s, r, finished ? 2u : r.illegal, L, reward, done, mask, status, i);
-    }
-    return 0;
+    return emu_step_flags<true>(0u, state, nullptr, 0, nullptr, seed, game_base, 0, action_out, coin_out, reward, done, mask, status, n);
+}
+
+int emu_step_random_ex(State* state, uint64_t seed, uint64_t game_base, uint64_t epoch, uint32_t flags,
+                       uint8_t* action_out, uint8_t* coin_out, float* reward, uint8_t* done,
+                       uint64_t* mask, uint8_t* status, int64_t n) {
+    return emu_step_flags<true>(flags, state, nullptr, 0, nullptr, seed, game_base, epoch, action_out, coin_out, reward, done, mask, status, n);
 }
 
 int emu_observe(const State* state, int8_t* classical_out, int8_t* moves, uint8_t* nmoves,
@@ -105,9 +124,14 @@ int emu_qeval_both(const State* state, const uint8_t* action, State* next0, Stat
                    uint64_t* board0, uint64_t* board1, int8_t* sq0, int8_t* sq1, uint8_t* closes,
                    float* result_prob, int64_t n) {
     const Luts L = luts();
-    for (int64_t i = 0; i < n; ++i)
-        qeval_game(state[i], action[i], L, next0, next1, board0, board1, sq0, sq1, closes,
-                   result_prob, i);
+    for (int64_t i = 0; i < n; ++i) {
+        if (sq0 || sq1)      // the same dispatch as qttt_qeval_both: per-move squares wanted or not
+            qeval_game<true>(state[i], action[i], L, next0, next1, board0, board1, sq0, sq1, closes,
+                             result_prob, i);
+        else
+            qeval_game<false>(state[i], action[i], L, next0, next1, board0, board1, sq0, sq1, closes,
+                              result_prob, i);
+    }
     return 0;
 }
 

@@ -89,7 +89,7 @@ def check_golden_mcts_step(backend):
     for i, r in enumerate(recs):
         assert obs["mask_bool"][i].astype(bool).tolist() == r["mask"]
     acts = np.array([r["action"] for r in recs], np.uint8)
-    res = games.qeval_both(acts)
+    res = games.qeval_both(acts, squares=False)      # what MCTS expansion uses: the one-sweep path
     kids = [games.with_state(res["next0"]).observe(), games.with_state(res["next1"]).observe()]
     for i, r in enumerate(recs):
         assert int(res["closes"][i]) == (len(r["children"]) == 2), i
@@ -230,6 +230,11 @@ def check_qeval_both(backend, n_boards, seed):
         res = dut.qeval_both(act)
         for k in ("closes", "sq0", "sq1"):
             assert np.array_equal(res[k], want_res[k]), f"{backend.name} qeval {want}: {k}"
+        # the one-sweep path (no per-move squares: both rootings grown in one loop) must give the
+        # very same successors, boards, closes and probabilities as the per-coin path
+        fast = dut.qeval_both(act, squares=False)
+        for k in ("closes", "next0", "next1", "board0", "board1", "result_prob"):
+            assert np.array_equal(fast[k], res[k]), f"{backend.name} qeval {want} one-sweep: {k}"
         assert np.array_equal(res["board0"], want_res["out0"]) and np.array_equal(res["board1"], want_res["out1"])
         probs = np.zeros((len(act), 3), np.float64)
         for c in (0, 1):
@@ -349,7 +354,115 @@ def check_philox_coin(backend, n_games=3000, seed=99, game_base=1234):
     assert_same_obs(dut.observe(), ref.observe(), "philox coin final")
 
 
-def check_packed_step(backend, n_games=5000, seed=31):
+def check_autoreset(backend, n_games=3000, seed=77, mode="apply", steps=40, illegal_rate=0.05):
+    """qttt_step_ex with QTTT_STEP_AUTORESET / _NEXT against the oracle driven the long way: a
+    game that is over on entry is replaced by a fresh game (Env.reset, env.py:55-57) and then
+    stepped (apply) or left alone for this call (next).  Envs drift apart, so after a few steps
+    every ply 0..8 is present in the batch at once: this is also the desynchronised-batch parity
+    case (the transition's sweep is dispatched on the warp's largest len(moves))."""
+    flags = {"apply": 2, "next": 4}[mode]
+    rng = np.random.default_rng(seed)
+    ref = CO.Games(n_games)
+    fresh = CO.Games(1).raw[0].copy()
+    full_mask = np.uint64((1 << 36) - 1)
+    dut = backend.games(n_games)
+    mask = np.full(n_games, full_mask, np.uint64)
+    over = np.zeros(n_games, bool)
+    resets = 0
+    plies_seen = set()
+    for t in range(steps):
+        # actions are drawn against the position the step will see: the fresh board for envs that
+        # are about to be reset
+        eff_mask = np.where(over, full_mask, mask)
+        legal = expand_mask(eff_mask)
+        k = (rng.random((n_games, 36)) * legal).argmax(1).astype(np.uint8)
+        k[~legal.any(1)] = 255
+        bad = rng.random(n_games) < illegal_rate
+        k[bad] = rng.integers(0, 64, int(bad.sum())).astype(np.uint8)      # any index: often illegal
+        coins = rng.integers(0, 2, n_games).astype(np.uint8)
+        ref.raw[over] = fresh
+        plies_seen |= set(np.unique(ref.observe()["n_moves"]).tolist())
+        pairs = np.full((n_games, 2), -1, np.int8)
+        apply = (k < 36) & (~over if mode == "next" else np.ones(n_games, bool))
+        pairs[apply] = PAIRS[k[apply]]
+        r = ref.step(pairs, coins)
+        o = dut.step_ex(k, coins, epoch=t + 1, flags=flags)
+        where = f"{backend.name} autoreset={mode} step {t}"
+        want_status = r["status"].copy()
+        if mode == "next":
+            want_status[over] = 0
+        want_status[over] |= 4
+        assert np.array_equal(o["status"], want_status), where
+        assert np.array_equal(o["reward"].view(np.uint32), r["reward"].view(np.uint32)), where
+        assert np.array_equal(o["done"], r["done"]) and np.array_equal(o["mask"], r["mask"]), where
+        assert_same_obs(dut.observe(), ref.observe(), where)
+        resets += int(over.sum())
+        mask, over = r["mask"], r["done"].astype(bool)
+    assert resets > n_games and plies_seen >= set(range(9))     # every env restarted; all plies mixed
+
+
+def check_autoreset_random(backend, n_games=2000, seed=5, steps=30):
+    """qttt_step_random_ex with QTTT_STEP_AUTORESET: continuous random self-play.  The emitted
+    (action, coin) trace replayed through the oracle (with resets where the oracle says the game
+    was over) reproduces every output; the draws are those of (seed, game, ply, epoch)."""
+    ref = CO.Games(n_games)
+    fresh = CO.Games(1).raw[0].copy()
+    dut = backend.games(n_games)
+    over = np.zeros(n_games, bool)
+    for t in range(steps):
+        ref.raw[over] = fresh
+        nm = ref.observe()["n_moves"]
+        lm = ref.legal_mask()
+        o = dut.step_random_ex(seed, game_base=900, epoch=t + 1, flags=2)
+        for g in range(0, n_games, 97):                   # spot-check the keyed draws
+            x0, x1 = O.policy_draw(seed, 900 + g, int(nm[g]), ((t + 1) << 8))
+            legal = [a for a in range(36) if (int(lm[g]) >> a) & 1]
+            assert int(o["action"][g]) == legal[(x0 * len(legal)) >> 32] and int(o["coin"][g]) == (x1 & 1)
+        pairs = PAIRS[o["action"]]
+        r = ref.step(pairs, o["coin"])
+        where = f"{backend.name} random autoreset step {t}"
+        assert (r["status"] == 0).all(), where
+        assert np.array_equal(o["status"], np.where(over, 4, 0).astype(np.uint8)), where
+        assert np.array_equal(o["reward"].view(np.uint32), r["reward"].view(np.uint32)), where
+        assert np.array_equal(o["done"], r["done"]) and np.array_equal(o["mask"], r["mask"]), where
+        over = r["done"].astype(bool)
+    assert_same_obs(dut.observe(), ref.observe(), f"{backend.name} random autoreset final")
+
+
+def check_epoch_coin(backend, n_games=2000, seed=99, game_base=7):
+    """The collapse coin of step(..., choices=None) is keyed (seed, game, len(moves), EPOCH):
+    replaying the same actions in a later epoch draws different coins (a different Philox
+    counter), each epoch matching the oracle's keyed draw.  Episode loops with reset() must not
+    replay the same coins (the reference draws a fresh random.choice per collapse, qeval.py:35)."""
+    rng = np.random.default_rng(seed)
+    # one fixed action trace that is legal whatever the coins are: disjoint pairs then re-plays
+    trace = [0, 0, 15, 15, 26, 26, 33, 33]           # (0,1)x2 (2,3)x2 (4,5)x2 (6,7)x2 -> 4 collapses
+    finals = []
+    for epoch in (0, 1, 2, 5):
+        ref = CO.Games(n_games)
+        dut = backend.games(n_games)
+        for ply, a in enumerate(trace):
+            k = np.full(n_games, a, np.uint8)
+            nm = ref.observe()["n_moves"]
+            coins = np.array([O.policy_draw(seed, game_base + g, int(nm[g]), epoch << 8)[1] & 1
+                              for g in range(n_games)], np.uint8)
+            r = ref.step(PAIRS[k], coins)
+            if ply == 0:
+                o = dut.step_ex(k, None, seed=seed, game_base=game_base, epoch=epoch, flags=1)   # reset + step
+            else:
+                o = dut.step_ex(k, None, seed=seed, game_base=game_base, epoch=epoch)
+            assert_same_step(o, r, f"{backend.name} epoch {epoch} ply {ply}")
+        obs = dut.observe()
+        assert_same_obs(obs, ref.observe(), f"{backend.name} epoch {epoch} final")
+        finals.append(obs["classical"].copy())
+    for i in range(len(finals)):
+        for j in range(i + 1, len(finals)):
+            # same actions, different epoch: a large share of the games must collapse differently
+            assert (finals[i] != finals[j]).any(1).mean() > 0.8
+    del rng
+
+
+def check_packed_step(backend, n_games=5000, seed=31, variant=None):
     """qttt_step_packed: one byte in (action | coin << 7), one 16-bit word out (free squares |
     terminated << 9 | line << 10 | status << 11) -- same transition as the oracle, bit for bit."""
     rng = np.random.default_rng(seed)
@@ -366,8 +479,13 @@ def check_packed_step(backend, n_games=5000, seed=31):
         pairs = np.full((n_games, 2), -1, np.int8)
         pairs[k < 36] = PAIRS[k[k < 36]]
         r = ref.step(pairs, coins)
-        res = dut.step_packed(k | (coins << 7)).astype(np.uint32)
-        where = f"{backend.name} packed ply {ply}"
+        if variant is None:
+            res = dut.step_packed(k | (coins << 7)).astype(np.uint32)
+        else:
+            res = dut.step_packed(k | (coins << 7), variant=variant).astype(np.uint32)
+            if variant.endswith("obs"):          # the observation that came back IS the new state
+                assert np.array_equal(dut.last_obs, dut.state), f"{variant} ply {ply}: obs"
+        where = f"{backend.name} packed {variant} ply {ply}"
         robs = ref.observe()
         free = ((robs["classical"] < 0) * (1 << np.arange(9))).sum(1).astype(np.uint32)
         assert np.array_equal(res & 0x1FF, free), where

@@ -25,7 +25,9 @@ def built_lib():
 
 def test_header_declares_the_expected_surface():
     assert _declared_symbols() == {
-        "qttt_abi_version", "qttt_strerror", "qttt_reset", "qttt_reset_step", "qttt_step", "qttt_step_packed", "qttt_step_packed_host", "qttt_step_random",
+        "qttt_abi_version", "qttt_strerror", "qttt_reset", "qttt_reset_all", "qttt_reset_step", "qttt_step", "qttt_step_ex",
+        "qttt_step_packed", "qttt_step_packed_obs", "qttt_step_packed_mapped", "qttt_step_packed_host",
+        "qttt_step_packed_host_obs", "qttt_step_random", "qttt_step_random_ex",
         "qttt_observe", "qttt_features", "qttt_pack", "qttt_qeval_both", "qttt_rollout", "qttt_sweep",
         "qttt_mcts_node_bytes", "qttt_mcts_init", "qttt_mcts_run", "qttt_mcts_stats", "qttt_mcts_sync"}
 
@@ -41,7 +43,7 @@ def test_ctypes_binding_matches_header(built_lib):
     from qtttgym_b200 import _lib
     assert set(_lib.EXPORTED_SYMBOLS) == _declared_symbols()
     lib = _lib.lib()
-    assert lib.qttt_abi_version() == 1
+    assert lib.qttt_abi_version() == 2
     assert lib.qttt_strerror(0) == b"ok"
     assert b"invalid argument" in lib.qttt_strerror(-1)
     # argument validation happens before any CUDA call, so it is testable without a GPU

@@ -228,6 +228,63 @@ def test_packed_step_host(cuda):
     S.check_packed_step(cuda, 40_001)
 
 
+@pytest.mark.parametrize("variant", ["copy_obs", "mapped", "mapped_obs"])
+def test_packed_step_host_variants(cuda, variant):
+    """the observation coming back with the result words, and the zero-copy path (the kernel
+    reads / writes the pinned host buffers itself) -- ragged size: full and partial 256-chunks"""
+    S.check_packed_step(cuda, 20_003, variant=variant)
+
+
+@pytest.mark.parametrize("mode", ["apply", "next"])
+def test_autoreset_desynchronised_batch(cuda, mode):
+    S.check_autoreset(cuda, 30_000, 77, mode)
+
+
+def test_autoreset_random_selfplay(cuda):
+    S.check_autoreset_random(cuda, 20_000, 5)
+
+
+def test_epoch_separates_episodes(cuda):
+    S.check_epoch_coin(cuda, 3000)
+
+
+def test_reset_between_episodes_changes_the_coins(cuda):
+    """an episode loop with env.reset() must not replay the same Philox coins."""
+    import torch
+    import qtttgym_b200 as Q
+    n = 4096
+    env = Q.BatchedEnv(n, seed=0)
+    trace = [0, 0, 15, 15, 26, 26, 33, 33]
+    boards = []
+    for episode in range(3):
+        if episode:
+            env.reset()
+        assert env.epoch == episode
+        assert not bool(env.done.any()) and not bool(env.status.any())       # reset clears the step outputs
+        assert bool((env.reward.view(torch.int32) == -2147483648).all())     # -0.0f
+        for a in trace:
+            env.step(torch.full((n,), a, dtype=torch.uint8, device="cuda"))
+        boards.append(env.observation()["classical"].clone())
+    assert float((boards[0] != boards[1]).any(1).float().mean()) > 0.8
+    assert float((boards[1] != boards[2]).any(1).float().mean()) > 0.8
+    sd = env.state_dict()
+    assert sd["epoch"] == 2
+
+
+def test_info_keys_and_out_of_range_actions(cuda):
+    import torch
+    import qtttgym_b200 as Q
+    env = Q.BatchedEnv(5, seed=1)
+    # int64 indices outside 0..35 must be illegal, not wrap modulo 256 (260 -> 4)
+    _, _, _, _, info = env.step(torch.tensor([260, -1, 36, 4, 0], device="cuda"))
+    assert info["invalid"].tolist() == [True, True, True, False, False]
+    assert "winner" in info and "reward_p1" in info and "invalid" in info
+    assert info["winner"].tolist() == [0] * 5 and info["reward_p1"].tolist() == [0.0] * 5
+    assert info["action_mask_bool"].shape == (5, 36)
+    assert torch.equal(info["action_mask_bool"], env.action_mask())
+    assert env.turn().tolist() == [0, 0, 0, 1, 1]
+
+
 def test_pack_unpack_helpers_match_step(cuda):
     import torch
     import qtttgym_b200 as Q

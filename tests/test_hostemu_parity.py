@@ -87,3 +87,16 @@ def test_mcts_batch_vs_oracle(emu):
 
 def test_rollout_frequencies_vs_reference_simulate(emu):
     S.check_rollout_frequencies_vs_reference_simulate(emu, n_rollouts=2048)
+
+
+@pytest.mark.parametrize("mode", ["apply", "next"])
+def test_autoreset(emu, mode):
+    S.check_autoreset(emu, 1500, 77, mode)
+
+
+def test_autoreset_random(emu):
+    S.check_autoreset_random(emu, 1000, 5)
+
+
+def test_epoch_coin(emu):
+    S.check_epoch_coin(emu, 600)
