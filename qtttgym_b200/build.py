@@ -11,7 +11,8 @@ CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 SOURCES = [os.path.join(CSRC, "qttt_kernels.cu")]
 DEPS = SOURCES + [os.path.join(CSRC, "qttt_core.cuh"), os.path.join(CSRC, "qttt_mcts.cuh"),
                   os.path.join(os.path.dirname(CSRC), "..", "include", "qttt_b200.h")]
-LIB = os.path.join(CSRC, "libqttt_b200.so")
+# QTTT_B200_LIB: load another build of the library instead (kernel experiments only)
+LIB = os.environ.get("QTTT_B200_LIB") or os.path.join(CSRC, "libqttt_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

@@ -92,6 +92,15 @@ QTTT_HD uint32_t warp_max_u32(uint32_t v) {
 #endif
 }
 
+// true if the predicate holds in any lane executing this call together (the value on the host)
+QTTT_HD bool warp_any(bool p) {
+#if defined(__CUDA_ARCH__)
+    return __any_sync(__activemask(), p) != 0;
+#else
+    return p;
+#endif
+}
+
 QTTT_HD State empty_state() { return State{0u, 0u, 0u, 0u}; }
 QTTT_HD uint32_t n_moves(const State& s) { return (s.x >> 27) & 15u; }
 QTTT_HD uint32_t plane3(const State& s) { return (s.y >> 27) | ((s.z >> 22) & 0x1E0u); }
@@ -224,13 +233,21 @@ template <int I> struct PlanePattern {
     static constexpr uint32_t value = (v & 1u) | ((v & 2u) << 8) | ((v & 4u) << 16);
 };
 
+#ifndef QTTT_ABSORB
+#define QTTT_ABSORB 1
+#endif
+
 template <int I>
 QTTT_HD void absorb(uint32_t E, uint32_t& R, uint32_t& W, uint32_t& A3) {
 #if defined(__CUDA_ARCH__)
-    // PTX pins the shape: LOP3 with predicate out (does E touch R?), LOP3 for c = E & ~R,
-    // then predicated multiply-add / add, which ptxas places on the IMAD pipe -- the integer
-    // ALU pipe is the binding resource of these kernels.  Left alone the compiler emits
-    // select-based code on the ALU pipe that is twice as long.
+    // PTX pins the shape.  The integer ALU pipe (LOP3 / SHF / ISETP / SEL: one warp instruction
+    // per TWO cycles) is the binding resource of these kernels, the FMA pipe (IMAD: one per
+    // cycle) is mostly idle, so everything that can be a multiply-add is one:
+    //   h = E & R, p = (h != 0)      one LOP3 with a predicate output            (ALU pipe)
+    //   c = E - h                    the endpoint not yet reached: IMAD h * -1 + E (FMA pipe)
+    //   @p W += c * pattern(I)       books c as owned by move I in the plane word  (FMA pipe)
+    //   @p R += c                                                                 (FMA pipe)
+#if QTTT_ABSORB == 0
     if (I < 7) {
         asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 h, c;\n\t"
             "and.b32 h, %2, %1;\n\t"
@@ -249,6 +266,25 @@ QTTT_HD void absorb(uint32_t E, uint32_t& R, uint32_t& W, uint32_t& A3) {
             : "+r"(A3), "+r"(R) : "r"(E));
     }
 #else
+    if (I < 7) {
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 h, c;\n\t"
+            "and.b32 h, %2, %1;\n\t"
+            "setp.ne.u32 p, h, 0;\n\t"
+            "mad.lo.u32 c, h, 0xffffffff, %2;\n\t"
+            "@p mad.lo.u32 %0, c, %3, %0;\n\t"
+            "@p mad.lo.u32 %1, c, 1, %1;\n\t}"
+            : "+r"(W), "+r"(R) : "r"(E), "n"(PlanePattern<I>::value));
+    } else {
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 h, c;\n\t"
+            "and.b32 h, %2, %1;\n\t"
+            "setp.ne.u32 p, h, 0;\n\t"
+            "mad.lo.u32 c, h, 0xffffffff, %2;\n\t"
+            "@p mad.lo.u32 %0, c, 1, %0;\n\t"
+            "@p mad.lo.u32 %1, c, 1, %1;\n\t}"
+            : "+r"(A3), "+r"(R) : "r"(E));
+    }
+#endif
+#else
     if (E & R) {
         const uint32_t c = E & ~R;
         if (I < 7) W += c * PlanePattern<I>::value; else A3 += c;
@@ -257,19 +293,54 @@ QTTT_HD void absorb(uint32_t E, uint32_t& R, uint32_t& W, uint32_t& A3) {
 #endif
 }
 
+// The 64-bit form: acc = R (bits 0..8) | W << 9, so that ONE wide multiply-add books both the
+// reached square and its owner: acc += c * (1 | pattern(I) << 9).
+template <int I>
+QTTT_HD void absorb_wide(uint32_t E, uint64_t& acc, uint32_t& A3) {
+    // plain C++: ptxas turns this into LOP3 (h and the predicate), @p IMAD.IADD (c), @p IMAD.WIDE
+    const uint32_t h = E & (uint32_t)acc;       // E < 512, so only the R bits of acc matter
+    const uint32_t c = E - h;
+    if (I < 7) {
+        if (h) acc = (uint64_t)c * (uint64_t)(1u | (PlanePattern<I>::value << 9)) + acc;
+    } else {
+        if (h) { acc += c; A3 += c; }
+    }
+}
+
 template <int I> QTTT_HD uint32_t slot(uint32_t x, uint32_t y, uint32_t z) {
     const uint32_t word = I < 3 ? x : (I < 6 ? y : z);
     return (I % 3 == 0) ? (word & M9) : ((word >> (9 * (I % 3))) & M9);
 }
 
 // Forward sweeps over move slots 0..N-1 until the reached set stops growing.
+// `stop`: a set R cannot grow beyond, or ~0 when none is known.  With 8 moves on the board the
+// live edges form ONE spanning tree of the free squares (every measured component of k squares
+// consumed exactly k moves, so #free = #live edges + 9 - len(moves)): the sweep is complete the
+// moment R holds every free square and the pass that would find nothing is skipped.
 template <int N, bool kTargets>
-QTTT_HD void sweep(uint32_t x, uint32_t y, uint32_t z, uint32_t& R, uint32_t& W, uint32_t& A3, uint32_t* T) {
+QTTT_HD void sweep(uint32_t x, uint32_t y, uint32_t z, uint32_t& R, uint32_t& W, uint32_t& A3, uint32_t* T,
+                   uint32_t stop = ~0u) {
     const uint32_t E0 = N > 0 ? slot<0>(x, y, z) : 0u, E1 = N > 1 ? slot<1>(x, y, z) : 0u;
     const uint32_t E2 = N > 2 ? slot<2>(x, y, z) : 0u, E3 = N > 3 ? slot<3>(x, y, z) : 0u;
     const uint32_t E4 = N > 4 ? slot<4>(x, y, z) : 0u, E5 = N > 5 ? slot<5>(x, y, z) : 0u;
     const uint32_t E6 = N > 6 ? slot<6>(x, y, z) : 0u, E7 = N > 7 ? slot<7>(x, y, z) : 0u;
     uint32_t before;
+#if QTTT_ABSORB == 2
+    uint64_t acc = (uint64_t)R + ((uint64_t)W << 9);
+    do {
+        before = (uint32_t)acc;
+        if (N > 0) absorb_wide<0>(E0, acc, A3);
+        if (N > 1) absorb_wide<1>(E1, acc, A3);
+        if (N > 2) absorb_wide<2>(E2, acc, A3);
+        if (N > 3) absorb_wide<3>(E3, acc, A3);
+        if (N > 4) absorb_wide<4>(E4, acc, A3);
+        if (N > 5) absorb_wide<5>(E5, acc, A3);
+        if (N > 6) absorb_wide<6>(E6, acc, A3);
+        if (N > 7) absorb_wide<7>(E7, acc, A3);
+    } while (N > 1 && (uint32_t)acc != before && (N < 8 || ((uint32_t)acc & M9) != stop));
+    R = (uint32_t)acc & M9;
+    W = (uint32_t)(acc >> 9);
+#else
     do {
         before = R;
         if (N > 0) absorb<0>(E0, R, W, A3);
@@ -280,7 +351,8 @@ QTTT_HD void sweep(uint32_t x, uint32_t y, uint32_t z, uint32_t& R, uint32_t& W,
         if (N > 5) absorb<5>(E5, R, W, A3);
         if (N > 6) absorb<6>(E6, R, W, A3);
         if (N > 7) absorb<7>(E7, R, W, A3);
-    } while (N > 1 && R != before);
+    } while (N > 1 && R != before && (N < 8 || R != stop));
+#endif
     if (kTargets) {
         // Which square did each absorbed edge bring in?  Only the qeval kernel asks: replay
         // the rooting from the start square (T[8]) with plain code.
@@ -299,7 +371,7 @@ QTTT_HD void sweep(uint32_t x, uint32_t y, uint32_t z, uint32_t& R, uint32_t& W,
 // independent instruction chains (ILP 2).
 template <int N>
 QTTT_HD void sweep2(uint32_t x, uint32_t y, uint32_t z, uint32_t& Ra, uint32_t& Wa, uint32_t& A3a,
-                    uint32_t& Rb, uint32_t& Wb, uint32_t& A3b) {
+                    uint32_t& Rb, uint32_t& Wb, uint32_t& A3b, uint32_t stop = ~0u) {
     const uint32_t E0 = N > 0 ? slot<0>(x, y, z) : 0u, E1 = N > 1 ? slot<1>(x, y, z) : 0u;
     const uint32_t E2 = N > 2 ? slot<2>(x, y, z) : 0u, E3 = N > 3 ? slot<3>(x, y, z) : 0u;
     const uint32_t E4 = N > 4 ? slot<4>(x, y, z) : 0u, E5 = N > 5 ? slot<5>(x, y, z) : 0u;
@@ -315,7 +387,7 @@ QTTT_HD void sweep2(uint32_t x, uint32_t y, uint32_t z, uint32_t& Ra, uint32_t& 
         if (N > 5) { absorb<5>(E5, Ra, Wa, A3a); absorb<5>(E5, Rb, Wb, A3b); }
         if (N > 6) { absorb<6>(E6, Ra, Wa, A3a); absorb<6>(E6, Rb, Wb, A3b); }
         if (N > 7) { absorb<7>(E7, Ra, Wa, A3a); absorb<7>(E7, Rb, Wb, A3b); }
-    } while (N > 1 && (Ra + (Rb << 9)) != before);
+    } while (N > 1 && (Ra + (Rb << 9)) != before && (N < 8 || (Ra & Rb) != stop));
 }
 
 // Board.make_move for one game.  `enew`: E mask of the requested pair (0 = malformed);
@@ -351,7 +423,7 @@ QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, const Luts&
     // raw E fields can be used unfiltered.
     uint32_t R = t;
     uint32_t W = t * row.kp;          // planes 0..2 of the closing move (index n) on square t
-    uint32_t A3 = (n >= 7u) ? t : 0u; // plane 3: v = n + 1 in {8, 9}
+    uint32_t A3 = 0u;                 // plane 3 (v = 8) of squares taken by move 7, from sweep<8>
     uint32_t T[9] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, t};
     // An illegal request (a swallowed no-op) has nothing to sweep.  The case is chosen ONCE PER
     // WARP -- the largest len(moves) among its lanes -- so the switch never diverges: empty
@@ -366,7 +438,7 @@ QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, const Luts&
         case 5: sweep<5, kTargets>(x, y, z, R, W, A3, T); break;
         case 6: sweep<6, kTargets>(x, y, z, R, W, A3, T); break;
         case 7: sweep<7, kTargets>(x, y, z, R, W, A3, T); break;
-        case 8: sweep<8, kTargets>(x, y, z, R, W, A3, T); break;
+        case 8: sweep<8, kTargets>(x, y, z, R, W, A3, T, n == 8u ? (~C & M9) : ~0u); break;
         default: break;
     }
 
@@ -376,7 +448,6 @@ QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, const Luts&
     // board[square] = move index for every move of the component (board.py:53-54): the
     // accumulated plane words are committed only when the move closed a cycle.
     uint32_t wn = w + W * colf;
-    A3 *= colf;
     uint32_t Cn = C | (R * colf);
 
     // moves.append((a, b, n))  (board.py:19): slot n is empty, so add == or.
@@ -385,19 +456,24 @@ QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, const Luts&
     uint32_t zn = z + enew * row.mz;
     uint32_t inc = legal ? 1u : 0u;
 
-    // Autofill (board.py:21-25): one free square left.  Only reachable right after the
-    // collapse triggered by move 7, so the entry is always (s, s, 8): v = 9 -> planes 0, 3.
-    const uint32_t fr = ~Cn & M9;
-    const bool fill = (colf != 0u) & (popc32(fr) == 1);
-    const uint32_t fs = fill ? fr : 0u;
-    zn += fs << 18;
-    wn += fs;
-    A3 += fs;
-    Cn |= fs;
-    inc += fill ? 1u : 0u;
-
-    yn += A3 << 27;                 // squares 0..4 of plane 3 (higher bits fall off the word)
-    zn += (A3 >> 5) << 27;          // squares 5..8
+    // Plane 3 (move indices 7 and 8) and the autofill exist only once 7 moves are on the board:
+    // a branch on the WARP's largest len(moves), so earlier plies do not pay for them.
+    if (warp_any(n >= 7u)) {
+        A3 += (n >= 7u) ? t : 0u;       // the closing move itself: v = n + 1 in {8, 9}
+        A3 *= colf;
+        // Autofill (board.py:21-25): one free square left.  Only reachable right after the
+        // collapse triggered by move 7, so the entry is always (s, s, 8): v = 9 -> planes 0, 3.
+        const uint32_t fr = ~Cn & M9;
+        const bool fill = (colf != 0u) & (popc32(fr) == 1);
+        const uint32_t fs = fill ? fr : 0u;
+        zn += fs << 18;
+        wn += fs;
+        A3 += fs;
+        Cn |= fs;
+        inc += fill ? 1u : 0u;
+        yn += A3 << 27;                 // squares 0..4 of plane 3 (higher bits fall off the word)
+        zn += (A3 >> 5) << 27;          // squares 5..8
+    }
     xn += inc << 27;
 
     if (kTargets) {
@@ -470,7 +546,7 @@ QTTT_HD BothResult step_both(const State& s, uint32_t enew, const Luts& L, State
         case 5: sweep2<5>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b); break;
         case 6: sweep2<6>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b); break;
         case 7: sweep2<7>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b); break;
-        case 8: sweep2<8>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b); break;
+        case 8: sweep2<8>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b, n == 8u ? (~C & M9) : ~0u); break;
         default: break;
     }
     const uint32_t colf = (Ra & b) != 0u ? 1u : 0u;                     // board.py:42

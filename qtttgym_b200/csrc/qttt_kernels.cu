@@ -14,16 +14,34 @@
 
 namespace qttt {
 
-__device__ const LutImage g_lut = make_lut_image();
+__device__ __align__(128) const LutImage g_lut = make_lut_image();
 
 constexpr int kThreads = 256;
 
-// Stage the first `bytes` of the table image into shared memory (16-byte vectors).
+// Stage the first `bytes` of the table image into shared memory: ONE bulk asynchronous copy
+// (cp.async.bulk, the 1-D TMA path: global -> shared, completion counted in bytes on an
+// mbarrier) issued by thread 0, instead of every thread looping over 16-byte loads and stores.
+// With blocks that live for only a few chunks of games the staging is paid often, and as a
+// loop it was ~90 instructions per thread per block.
 __device__ __forceinline__ void stage_luts(uint8_t* smem, int bytes) {
-    const uint4* src = reinterpret_cast<const uint4*>(&g_lut);
-    uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
-    __syncthreads();
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+    const uint32_t dst_a = (uint32_t)__cvta_generic_to_shared(smem);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst_a), "l"(&g_lut), "r"(bytes), "r"(bar_a) : "memory");
+    }
+    __syncthreads();                  // the barrier object is initialised for everybody
+    uint32_t done = 0;                // every thread observes the completion itself: that is what
+    while (!done) {                   // makes the bytes written by the copy engine visible to it
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar_a) : "memory");
+    }
 }
 
 __device__ __forceinline__ State load_state(const qttt_state* p, int64_t i) {
@@ -41,12 +59,13 @@ __device__ __forceinline__ void store_state(qttt_state* p, int64_t i, const Stat
 // launched exactly one resident wave of persistent grid-stride blocks: ncu showed the SMs
 // running out of warps long before the kernel ended -- 46 of 64 warps resident on average at
 // ply 8 -- because the warp arbiter is not fair and nothing replaces a warp that finishes early.)
-constexpr int kStepIters = 4;       // chunks per block of the step kernels (tables restaged per block)
+constexpr int kStepIters = 8;       // chunks per block of the step kernels (tables restaged per block)
+constexpr int kSweepIters = 32;     // 8192 self-play games per block of the sweep (19 KB of tables per block)
 
 static int chunk_grid(int64_t n, int iters) {
     const int64_t per_block = (int64_t)kThreads * iters;
     const int64_t g = (n + per_block - 1) / per_block;
-    return (int)(g < 1 ? 1 : g);
+    return (int)(g < 1 ? 1 : (g > 0x7FFFFFFF ? 0x7FFFFFFF : g));     // grid-stride loops take any grid
 }
 
 // ------------------------------------------------------------------------------ K2 reset
@@ -88,7 +107,7 @@ struct StepIn { uint4 sv; uint32_t act, coin; };
 // kMode: kStepPlain / kStepFresh / kStepAuto / kStepAutoNext (qttt_core.cuh);
 // kPrefetch: the next chunk's inputs are loaded before the current chunk is computed.
 template <int kFmt, bool kRandom, bool kFull, int kMode, bool kPrefetch>
-__global__ void __launch_bounds__(kThreads) k_step(const StepArgs a) {
+__global__ void __launch_bounds__(kThreads, kPrefetch ? 6 : 8) k_step(const StepArgs a) {   // 8 blocks/SM: 32 registers
     __shared__ __align__(16) uint8_t smem[kLutStepBytes];
     stage_luts(smem, kLutStepBytes);
     const Luts L = luts_from_image(smem);
@@ -1015,7 +1034,7 @@ int qttt_observe(const qttt_state* state, int8_t* classical, int8_t* moves, uint
     if (!state || n < 0) return QTTT_ERR_ARG;
     if (misaligned(state, 16) || misaligned(reward_p1, 4)) return QTTT_ERR_ALIGN;
     if (n == 0) return QTTT_OK;
-    k_observe<<<grid_for(k_observe, n), kThreads, 0, (cudaStream_t)stream>>>(state, classical, moves, n_moves, q_p1, q_p2, turn, rounds, reward_p1, winner, mask_bool, n);
+    k_observe<<<chunk_grid(n, 4), kThreads, 0, (cudaStream_t)stream>>>(state, classical, moves, n_moves, q_p1, q_p2, turn, rounds, reward_p1, winner, mask_bool, n);
     return check_launch();
 }
 
@@ -1053,9 +1072,9 @@ int qttt_qeval_both(const qttt_state* state, const uint8_t* action, qttt_state* 
         return QTTT_ERR_ALIGN;
     if (n == 0) return QTTT_OK;
     if (sq0 || sq1)
-        k_qeval_both<true><<<grid_for(k_qeval_both<true>, n), kThreads, 0, (cudaStream_t)stream>>>(state, action, next0, next1, board0, board1, sq0, sq1, closes, result_prob, n);
+        k_qeval_both<true><<<chunk_grid(n, 4), kThreads, 0, (cudaStream_t)stream>>>(state, action, next0, next1, board0, board1, sq0, sq1, closes, result_prob, n);
     else
-        k_qeval_both<false><<<grid_for(k_qeval_both<false>, n), kThreads, 0, (cudaStream_t)stream>>>(state, action, next0, next1, board0, board1, sq0, sq1, closes, result_prob, n);
+        k_qeval_both<false><<<chunk_grid(n, 4), kThreads, 0, (cudaStream_t)stream>>>(state, action, next0, next1, board0, board1, sq0, sq1, closes, result_prob, n);
     return check_launch();
 }
 
@@ -1066,7 +1085,10 @@ int qttt_rollout(const qttt_state* roots, int64_t n_roots, int32_t n_rollouts, u
     if (misaligned(roots, 16) || misaligned(tallies, 4) || misaligned(value, 4) || misaligned(steps_total, 8))
         return QTTT_ERR_ALIGN;
     if (n_roots == 0) return QTTT_OK;
-    k_rollout<<<grid_for(k_rollout, n_roots * kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+    // one block per root up to 8 resident waves of blocks (then roots are taken grid-stride): the
+    // block scheduler keeps every SM full until the last roots
+    const int64_t cap = 8ll * resident_blocks(reinterpret_cast<const void*>(k_rollout), kThreads);
+    k_rollout<<<(int)(n_roots < cap ? n_roots : cap), kThreads, 0, (cudaStream_t)stream>>>(
         roots, n_roots, n_rollouts, seed, tallies, value, reinterpret_cast<unsigned long long*>(steps_total));
     return check_launch();
 }
@@ -1125,7 +1147,7 @@ int qttt_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, int64_t* stats, 
     if (!stats) return QTTT_ERR_ARG;
     if (misaligned(stats, 8)) return QTTT_ERR_ALIGN;
     if (game_hi == game_lo) return QTTT_OK;
-    k_sweep<<<grid_for(k_sweep, game_hi - game_lo), kThreads, 0, (cudaStream_t)stream>>>(
+    k_sweep<<<chunk_grid(game_hi - game_lo, kSweepIters), kThreads, 0, (cudaStream_t)stream>>>(
         game_lo, game_hi, seed, reinterpret_cast<unsigned long long*>(stats));
     return check_launch();
 }
