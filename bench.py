@@ -4,12 +4,13 @@ reference's CPU path timed on the host cores.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--envs E]
 
-One bench *step* is one pass of the hot path over one batch: ``reset`` + 9 ``step`` calls
-(kernel K1) that play E games from the empty board to termination on pre-generated
-random-legal actions and forced collapse coins (config 2 of BASELINE.json scaled to fill the
-GPU: E = 2^24 envs per GPU; the literal 4096-env config is reported under ``extra``).  The
-metric counts *accepted* moves only (an env-step = one accepted make_move; finished games
-idle as illegal no-ops and are not counted).
+One *pass* of the hot path over one batch is ``reset`` + 9 ``step`` calls (kernel K1) that play
+E games from the empty board to termination on pre-generated random-legal actions and forced
+collapse coins (config 2 of BASELINE.json scaled to fill the GPU: E = 2^24 envs per GPU; the
+literal 4096-env config is reported under ``extra``).  One bench *step* is ``--passes-per-step``
+such passes (40: the timed region of the default run is ~1 s, long enough to show sustained
+clocks).  The metric counts *accepted* moves only (an env-step = one accepted make_move;
+finished games idle as illegal no-ops and are not counted).
 
 ``value``  : inputs already resident in HBM when the timed region starts.
 ``e2e``    : the same pass through the public API with pinned HOST buffers
@@ -186,6 +187,48 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- B200 arm
+def pcie_ceiling(torch, dev, barrier, max_over_ranks, nbytes=256 << 20, reps=4):
+    """Pinned-host copy ceiling of this rank's link, measured with plain cudaMemcpyAsync
+    (torch .copy_ of pinned tensors): each direction alone and both at once on two streams.
+    Under torchrun every rank measures at the same time (barrier first), so the numbers are
+    what the box gives N ranks concurrently.  GB/s per rank."""
+    h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def run(h2d, d2h):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        s1.wait_event(a)
+        s2.wait_event(a)
+        for _ in range(reps):
+            if h2d:
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        e1, e2 = torch.cuda.Event(), torch.cuda.Event()
+        e1.record(s1)
+        e2.record(s2)
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(e1)
+        cur.wait_event(e2)
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b)) * 1e-3
+    run(True, True)
+    t_h2d, t_d2h, t_both = run(True, False), run(False, True), run(True, True)
+    gb = nbytes * reps / 1e9
+    return {"h2d_alone_gbs": gb / t_h2d, "d2h_alone_gbs": gb / t_d2h,
+            "h2d_concurrent_gbs": gb / t_both, "d2h_concurrent_gbs": gb / t_both,
+            "how": f"{reps} x {nbytes >> 20} MiB pinned cudaMemcpyAsync per direction; 'concurrent' = both "
+                   "directions at once on two streams; per rank, all ranks measuring at the same time"}
+
+
 def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -240,10 +283,11 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    E, K, W = args.envs, args.steps, args.warmup
+    E, K, W, P = args.envs, args.steps, args.warmup, args.passes_per_step
     seed = 20261018
     from qtttgym_b200 import _lib as qlib
-    launches = 0          # our kernels launched inside the timed regions (value_eager, value, e2e)
+    launches = 0          # our kernels launched inside the timed regions (value, value_eager, e2e)
+    peak, peak_src = measured_hbm_peak()
 
     # ---- synthetic workload: random-policy traces generated on the device (untimed)
     env = Q.BatchedEnv(E, device=dev, seed=seed, game_base=rank * E)
@@ -251,86 +295,162 @@ def run_b200(args):
     coins = torch.empty((PLIES, E), dtype=torch.uint8, device=dev)
     accepted = []
     for ply in range(PLIES):
-        _, _, _, _, info = env.step_random(record=True)
-        actions[ply].copy_(info["action"])
-        coins[ply].copy_(info["coin"])
+        _, _, _, _, info = env.step_random(out=(actions[ply], coins[ply]))
         accepted.append(int((info["status"] == 0).sum().item()))
     steps_per_pass = sum(accepted)
     final_winner = torch.bincount(env.winner().long(), minlength=3)
+    total_steps_pass = sum_over_ranks(float(steps_per_pass))
 
-    # ---- value: inputs resident in HBM
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2 * PLIES)] for _ in range(K)]
+    # ---- value: inputs resident in HBM; one bench step = P passes, each pass one CUDA graph of the
+    #      9 launches (reset fused into the first).  K steps are timed.
+    graph_full = env.capture_episode(actions, coins)
+    for _ in range(W * P):                     # W warm-up steps
+        graph_full.replay()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler = ClockSampler(dev)
+    g0.record()
+    for _ in range(K * P):
+        graph_full.replay()
+    g1.record()
+    barrier()
+    clocks = sampler.stop()
+    graph_ms = max_over_ranks(g0.elapsed_time(g1))
+    launches += K * P * PLIES
+    value_graph = total_steps_pass * K * P / (graph_ms * 1e-3)
+    assert torch.equal(torch.bincount(env.winner().long(), minlength=3), final_winner), \
+        "timed replay diverged from the generated trace"
+
+    # ---- the same pass issued eagerly, with CUDA events around every launch (per-ply durations)
+    Ke = max(3, min(K, 10))
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2 * PLIES)] for _ in range(Ke)]
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = None
-    for it in range(W + K):
-        if it == W:
+    for it in range(3 + Ke):
+        if it == 3:
             barrier()
-            sampler = ClockSampler(dev)
             launches_before = qlib.LAUNCHES
             start.record()
         for ply in range(PLIES):
-            if it >= W:
-                ev[it - W][2 * ply].record()
+            if it >= 3:
+                ev[it - 3][2 * ply].record()
             if ply == 0:
                 env.reset_step(actions[0], coins[0])       # Env.reset fused into the first ply
             else:
                 env.step(actions[ply], coins[ply])
-            if it >= W:
-                ev[it - W][2 * ply + 1].record()
+            if it >= 3:
+                ev[it - 3][2 * ply + 1].record()
     end.record()
     barrier()
     t_ms = max_over_ranks(start.elapsed_time(end))
-    launches += qlib.LAUNCHES - launches_before          # K x 9 step launches (reset fused)
-    total_steps = sum_over_ranks(float(steps_per_pass)) * K
-    value = total_steps / (t_ms * 1e-3)
-    # the state after the timed passes must be the state the trace generation ended in
-    w_check = torch.bincount(env.winner().long(), minlength=3)
-    assert torch.equal(w_check, final_winner), "timed replay diverged from the generated trace"
+    launches += qlib.LAUNCHES - launches_before
+    value_eager = total_steps_pass * Ke / (t_ms * 1e-3)
+    assert torch.equal(torch.bincount(env.winner().long(), minlength=3), final_winner)
+    per_ply_ms = [sum(ev[k][2 * p].elapsed_time(ev[k][2 * p + 1]) for k in range(Ke)) / Ke for p in range(PLIES)]
+    ev_launch_ms = sum(per_ply_ms) / PLIES
 
-    kdur_ms = [ev[k][2 * p].elapsed_time(ev[k][2 * p + 1]) for k in range(K) for p in range(PLIES)]
-    avg_launch_ms = sum(kdur_ms) / len(kdur_ms)
-    per_ply_ms = [sum(ev[k][2 * p].elapsed_time(ev[k][2 * p + 1]) for k in range(K)) / K for p in range(PLIES)]
-    peak, peak_src = measured_hbm_peak()
     # algorithmic bytes of one pass: 47 B per accepted step, except the first ply, whose launch has
     # the reset fused in and does not read the state (47 - 16 = 31 B per step)
     alg_bytes_pass = BYTES_PER_STEP * steps_per_pass - 16 * accepted[0]
+    avg_launch_ms = graph_ms / (K * P * PLIES)            # the timed region itself: 9 launches per pass
     achieved = (alg_bytes_pass / PLIES) / (avg_launch_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_step<QTTT_ACT_INDEX,false>", "achieved": achieved,
+    achieved_ev = (alg_bytes_pass / PLIES) / (ev_launch_ms * 1e-3) / 1e9
+    alg_by_ply = [BYTES_PER_STEP * a - (16 * a if p == 0 else 0) for p, a in enumerate(accepted)]
+    roofline = {"bound": "hbm", "kernel": "k_step<QTTT_ACT_INDEX, forced coins, all outputs>", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": (args.traffic_bytes if args.traffic_bytes is not None else
                             (profiled_traffic() or {}).get("dram_bytes_per_launch")),
                 "traffic_source": (profiled_traffic() or {}).get("source"),
                 "algorithmic_bytes_per_launch": alg_bytes_pass / PLIES,
-                "avg_launch_ms": avg_launch_ms, "launch_ms_by_ply": per_ply_ms,
+                "avg_launch_ms": avg_launch_ms,
+                "avg_launch_source": "the timed region of `value` itself: CUDA events around K x P graph replays of the "
+                                     "9-launch pass, divided by 9 K P (kernel time plus the gaps between graph nodes)",
+                "per_launch_events": {"avg_launch_ms": ev_launch_ms, "frac": achieved_ev / peak,
+                                      "launch_ms_by_ply": per_ply_ms,
+                                      "frac_by_ply": [b / (m * 1e-3) / 1e9 / peak for b, m in zip(alg_by_ply, per_ply_ms)],
+                                      "note": "the same pass issued eagerly with one CUDA event pair per launch "
+                                              f"({Ke} passes); each pair adds ~2 us of event latency to its launch"},
                 "bytes_per_env_step": BYTES_PER_STEP,
                 "note": "mean over the 9 launches of a pass; the first ply's launch (reset fused in, state not "
-                        "read) is charged 31 B per step"}
+                        "read) is charged 31 B per step; finished games idle as no-ops and earn no bytes although "
+                        "their state is still read and their outputs written (ply 8: half of the lanes)"}
 
-    # ---- the same pass as ONE CUDA graph (BatchedEnv.capture_episode): no per-launch CPU work
-    graph_full = env.capture_episode(actions, coins)
-    for _ in range(W):
-        graph_full.replay()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    g0.record()
-    for _ in range(K):
-        graph_full.replay()
-    g1.record()
-    barrier()
-    clocks = sampler.stop() if sampler else {}      # sampled over the eager and the graph timed regions
-    graph_ms = max_over_ranks(g0.elapsed_time(g1))
-    launches += K * PLIES                                # kernels inside the K replayed graphs
-    value_graph = total_steps / (graph_ms * 1e-3)
-    assert torch.equal(torch.bincount(env.winner().long(), minlength=3), final_winner)
+    extra = {}
+
+    def timed(fn, reps):
+        fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b)) / reps
+
+    # ---- K1 on a DESYNCHRONISED batch: envs spread over all plies inside every warp (what a policy-
+    #      driven vector env with autoreset looks like).  31 autoreset self-play steps mix the batch,
+    #      9 more are recorded and replayed (forced actions + coins, autoreset on) as one CUDA graph.
+    mix = Q.BatchedEnv(E, device=dev, seed=seed + 1, game_base=rank * E)
+    for _ in range(31):
+        mix.step_random(autoreset=True)
+    d_start, d_epoch = mix.state.clone(), mix.epoch
+    d_act = torch.empty((PLIES, E), dtype=torch.uint8, device=dev)
+    d_coin = torch.empty((PLIES, E), dtype=torch.uint8, device=dev)
+    d_accepted = 0
+    for t in range(PLIES):
+        _, _, _, _, info = mix.step_random(autoreset=True, out=(d_act[t], d_coin[t]))
+        d_accepted += int(((info["status"] & 3) == 0).sum().item())
+    d_final = mix.state.clone()
+    ply_hist = torch.bincount(((d_start[:, 0] >> 27) & 15).long(), minlength=10).tolist()
+
+    def desync_pass():
+        mix.epoch = d_epoch
+        for t in range(PLIES):
+            mix.step(d_act[t], d_coin[t], autoreset=True)
+    mix.state.copy_(d_start)
+    desync_pass()
+    torch.cuda.synchronize()
+    assert torch.equal(mix.state, d_final), "desync replay diverged"
+    dg = torch.cuda.CUDAGraph()
+    mix.state.copy_(d_start)
+    with torch.cuda.graph(dg):
+        desync_pass()
+    # (replaying from wherever the last replay ended keeps the batch just as mixed; the actions were
+    #  legal for the recorded trajectory only, so every replay starts from the recorded start state)
+    def desync_replay():
+        mix.state.copy_(d_start)
+        dg.replay()
+    copy_ms = timed(lambda: mix.state.copy_(d_start), 20)
+    ms = timed(desync_replay, 20) - copy_ms
+    d_bytes = BYTES_PER_STEP * d_accepted
+    extra["k1_desync"] = {
+        "ms_per_launch": ms / PLIES, "env_steps_per_s": sum_over_ranks(float(d_accepted)) / (ms * 1e-3),
+        "roofline_frac": d_bytes / (ms * 1e-3) / 1e9 / peak, "accepted_steps_per_launch": d_accepted / PLIES,
+        "envs_by_len_moves_at_start": ply_hist,
+        "note": "2^24 envs at mixed plies in every warp, step(..., autoreset=True): a game that is over restarts "
+                "inside the launch, so every lane plays every step; 9 launches as one CUDA graph; 47 B per step"}
+    del mix, dg, d_start, d_final, d_act, d_coin
+
+    # ---- step + full observation in the timed region (obs_mode='full': classical, q lists, turn)
+    obs_env = Q.BatchedEnv(E, device=dev, seed=seed, game_base=rank * E)
+    obs_buf = obs_env.observation()
+
+    def obs_pass():
+        for ply in range(PLIES):
+            (obs_env.reset_step if ply == 0 else obs_env.step)(actions[ply], coins[ply])
+            obs_env.observation(out=obs_buf)
+    ms = timed(obs_pass, 3)
+    extra["value_with_observation"] = {
+        "env_steps_per_s": total_steps_pass / (ms * 1e-3), "ms_per_pass": ms,
+        "note": "the same pass with qttt_observe (env.py:68-85 tensors: classical int8[N,9], q_states_p1/p2, turn) "
+                "after every step, i.e. what the reference's Env.step returns as obs, decoded on the device"}
+    del obs_env, obs_buf
 
     # ---- e2e: host buffers through the public API, copies inside the timed region
-    h_act = actions.cpu().pin_memory()
-    h_coin = coins.cpu().pin_memory()
+    ceiling = pcie_ceiling(torch, dev, barrier, max_over_ranks)
     h_ac = Q.pack_actions(actions, coins).cpu().pin_memory()          # 1 byte per env per ply
     h_res = torch.empty(E, dtype=torch.int16).pin_memory()            # 2 bytes per env per ply
-    h_reward = torch.empty(E, dtype=torch.float32).pin_memory()
-    h_done = torch.empty(E, dtype=torch.bool).pin_memory()
-    h_mask = torch.empty(E, dtype=torch.int64).pin_memory()
+    h_obs = torch.empty((E, 4), dtype=torch.int32).pin_memory()       # 16 bytes per env per ply
     e2e_K = max(1, min(K, args.e2e_steps))
 
     def e2e_run(step_fn):
@@ -348,38 +468,50 @@ def run_b200(args):
         barrier()
         launches += qlib.LAUNCHES - before
         ms = max_over_ranks(s2.elapsed_time(e2))
-        return sum_over_ranks(float(steps_per_pass)) * e2e_K / (ms * 1e-3), ms / e2e_K
+        return total_steps_pass * e2e_K / (ms * 1e-3), ms / e2e_K
 
-    v_packed, ms_packed = e2e_run(lambda ply: env.step_host_packed(h_ac[ply], h_res))
-    _, term_chk, _, _ = Q.unpack_result(h_res)
-    assert int(term_chk.sum()) == E, "e2e pass did not finish every game"
-    v_sep, ms_sep = e2e_run(lambda ply: env.step_host(h_act[ply], h_coin[ply], h_reward, h_done, h_mask))
-    assert int(h_done.sum()) == E, "e2e pass did not finish every game"
-    e2e = {"value": v_packed, "unit": UNIT, "h2d_bytes_per_step": 1 * E * PLIES,
-           "d2h_bytes_per_step": 2 * E * PLIES, "steps": e2e_K, "ms_per_step": ms_packed,
-           "api": "BatchedEnv.reset + 9 x BatchedEnv.step_host_packed (C ABI qttt_step_packed_host; pinned host "
-                  "buffers: 1 B action|coin in, one 16-bit result word (free-square set = legal mask, "
-                  "terminated, line, status) out per env per ply; 8 slices pipelined over 4 side streams)",
-           "separate_arrays": {"value": v_sep, "ms_per_step": ms_sep, "h2d_bytes_per_step": 2 * E * PLIES,
-                               "d2h_bytes_per_step": 13 * E * PLIES,
-                               "api": "BatchedEnv.step_host (qttt_step): uint8 actions + coins in, f32 reward + "
-                                      "bool done + int64 mask out"}}
+    def link_floor_ms(b_in, b_out):
+        return 1e3 * max(b_in / (ceiling["h2d_concurrent_gbs"] * 1e9), b_out / (ceiling["d2h_concurrent_gbs"] * 1e9))
+
+    variants = {}
+    for name, kw, b_in, b_out in (
+            ("packed_copy", dict(), 1, 2),
+            ("packed_copy_obs", dict(obs_host=h_obs), 1, 18),
+            ("packed_mapped", dict(mapped=True), 1, 2),
+            ("packed_mapped_obs", dict(obs_host=h_obs, mapped=True), 1, 18)):
+        v, ms = e2e_run(lambda ply, kw=kw: env.step_host_packed(h_ac[ply], h_res, **kw))
+        _, term_chk, _, _ = Q.unpack_result(h_res)
+        assert int(term_chk.sum()) == E, "e2e pass did not finish every game"
+        if "obs_host" in kw:
+            assert torch.equal(h_obs, env.state.cpu()), "e2e observation is not the final state"
+        floor = link_floor_ms(b_in * E * PLIES, b_out * E * PLIES)
+        variants[name] = {"value": v, "ms_per_pass": ms, "h2d_bytes_per_pass": b_in * E * PLIES,
+                          "d2h_bytes_per_pass": b_out * E * PLIES, "link_floor_ms_per_pass": floor,
+                          "frac_of_link_ceiling": floor / ms}
+    best = "packed_copy" if variants["packed_copy"]["value"] >= variants["packed_mapped"]["value"] else "packed_mapped"
+    best_obs = ("packed_copy_obs" if variants["packed_copy_obs"]["value"] >= variants["packed_mapped_obs"]["value"]
+                else "packed_mapped_obs")
+    e2e = {"value": variants[best]["value"], "unit": UNIT, "h2d_bytes_per_step": 1 * E * PLIES * P,
+           "d2h_bytes_per_step": 2 * E * PLIES * P, "passes_timed": e2e_K, "ms_per_pass": variants[best]["ms_per_pass"],
+           "variant": best,
+           "fields_returned": "per env per ply one 16-bit word: free-square set (= the 36-bit legal mask, re-expanded by "
+                              "unpack_result), terminated, line (= reward -1.0 / -0.0), status.  The observation stays "
+                              "in HBM (the packed state tensor); `with_obs` is the same path with the observation "
+                              "(packed 16-B state per env) copied to the host as well",
+           "api": "BatchedEnv.reset + 9 x BatchedEnv.step_host_packed (pinned host buffers: 1 B action|coin in, 2 B out "
+                  "per env per ply).  packed_copy = qttt_step_packed_host_obs: 8 slices pipelined over 4 side "
+                  "streams, one cudaMemcpyAsync per array per slice; packed_mapped = qttt_step_packed_mapped: one "
+                  "launch whose threads read / write the pinned host buffers across PCIe themselves",
+           "with_obs": {"value": variants[best_obs]["value"], "variant": best_obs,
+                        "ms_per_pass": variants[best_obs]["ms_per_pass"],
+                        "h2d_bytes_per_pass": 1 * E * PLIES, "d2h_bytes_per_pass": 18 * E * PLIES},
+           "variants": variants, "pcie_ceiling": ceiling,
+           "note": "frac_of_link_ceiling = (bytes that must cross the link / measured pinned-copy bandwidth of the same "
+                   "direction with both directions busy) / measured time"}
+    del h_obs
 
     # ---- extras: the other configs of BASELINE.json
-    extra = {}
-
-    def timed(fn, reps):
-        fn()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        a.record()
-        for _ in range(reps):
-            fn()
-        b.record()
-        barrier()
-        return max_over_ranks(a.elapsed_time(b)) / reps
-
-    # config 2 literal: 4096 envs (latency-bound: 10 launches of ~2 us of work each)
+    # config 2 literal: 4096 envs (latency-bound: 9 launches of ~2 us of work each)
     small = Q.BatchedEnv(4096, device=dev, seed=seed, game_base=rank * E)
     sa, sc = actions[:, :4096].contiguous(), coins[:, :4096].contiguous()
     small_steps = int(sum(int((sa[p] < 36).sum().item()) for p in range(PLIES)))
@@ -394,7 +526,7 @@ def run_b200(args):
     extra["config2_4096_envs"] = {"env_steps_per_s": small_steps / (ms_graph * 1e-3) * world,
                                   "ms_per_pass_cuda_graph": ms_graph, "ms_per_pass_eager": ms,
                                   "env_steps_per_s_eager": small_steps / (ms * 1e-3) * world,
-                                  "note": "launch-latency bound (10 launches of 4096 threads per pass); the whole "
+                                  "note": "launch-latency bound (9-10 launches of 4096 threads per pass); the whole "
                                           "episode is captured in one CUDA graph (BatchedEnv.capture_episode)"}
 
     # config 5: fused self-play sweep (K5) + the one NCCL all_reduce of the tallies
@@ -428,7 +560,8 @@ def run_b200(args):
     extra["config3_qeval_1M_boards"] = {
         "boards_per_s": nb / (ms * 1e-3) * world, "ms": ms, "ms_per_python_call": ms_api,
         "hbm_frac_at_33B": nb / (ms * 1e-3) * BYTES_PER_BOARD_QEVAL / 1e9 / peak,
-        "note": "device time per launch (10 launches per CUDA-graph replay); a bare Python call costs ms_per_python_call"}
+        "note": "device time per launch (10 launches per CUDA-graph replay); 34.6 MB per launch fit the 126 MB L2, "
+                "so this size is launch-latency / L2 bound; a bare Python call costs ms_per_python_call"}
 
     # the same kernel at a size that fills the GPU (2^24 boards: the trace's ply-4 positions)
     qa_big = torch.where(actions[4] < 36, actions[4], torch.zeros_like(actions[4]))
@@ -471,8 +604,8 @@ def run_b200(args):
         dt = time.perf_counter() - t0
         extra["config1_single_env_adapter"] = {
             "env_steps_per_s": n_single / dt, "us_per_step": 1e6 * dt / n_single,
-            "note": "one env, one step per call through qtttgym_b200.Env (2 launches + 1 device->host copy + "
-                    "1 sync per step): latency-bound by construction, listed for completeness"}
+            "note": "one env, one step per call through qtttgym_b200.Env: wall time of the reference's own loop "
+                    "(legal-move list + random.choice + step) per step"}
 
     # MCTS search around the leaf evaluator (next row #1): 1024 mid-game roots, the reference's
     # default num_simulations=10, 500 rollouts per root; and the config-4 shape (256 playouts per leaf)
@@ -523,13 +656,14 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "envs_per_gpu": E, "global_envs": E * world, "plies_per_pass": PLIES,
+                       "passes_per_step": P, "timed_region_s": graph_ms * 1e-3,
                        "env_steps_per_pass_per_gpu": steps_per_pass,
                        "l2": "inputs exceed L2: 16 B x E state + 2 B x E actions/coins + 13 B x E outputs per launch "
                              f"= {31 * E / 1e6:.0f} MB vs 126 MB L2" if 31 * E > 126e6 else "inputs fit in L2 (small E)",
                        "parallelism": f"dp{world} (independent games per rank, no data-path collective)"},
-            "value_eager": {"value": value, "ms_per_step": t_ms / K,
-                            "note": "the same pass issued as 10 separate BatchedEnv.reset/step calls per pass "
-                                    "(the loop the per-launch roofline events are recorded in)"},
+            "value_eager": {"value": value_eager, "ms_per_pass": t_ms / Ke,
+                            "note": "the same pass issued as 9 separate BatchedEnv.reset_step/step calls per pass "
+                                    "(the loop the per-launch events are recorded in)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks, "extra": extra,
         }
@@ -546,7 +680,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=1 << 24, help="envs per GPU")
     ap.add_argument("--sweep-games", type=int, default=125_000_000, help="config-5 games per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=3, help="passes timed per e2e variant")
+    ap.add_argument("--passes-per-step", type=int, default=40,
+                    help="passes (CUDA-graph replays of reset + 9 steps) per bench step: 20 steps x 40 passes ~ 1 s")
     ap.add_argument("--cpu-seconds", type=float, default=3.0, help="CPU baseline wall seconds per core")
     ap.add_argument("--ref-games", type=int, default=4000, help="--impl reference: games per process per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
