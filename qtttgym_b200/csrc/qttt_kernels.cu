@@ -453,7 +453,7 @@ k_features(const qttt_state* __restrict__ state, float* __restrict__ out, int64_
 
 // ------------------------------------------------------------------------------ K3 qeval
 template <bool kSquares>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, kSquares ? 4 : 8)
 k_qeval_both(const qttt_state* __restrict__ state, const uint8_t* __restrict__ action,
              qttt_state* __restrict__ next0, qttt_state* __restrict__ next1,
              uint64_t* __restrict__ board0, uint64_t* __restrict__ board1,
@@ -780,6 +780,13 @@ static int step_iters() {
     }();
     return v;
 }
+// Chunks per block for a batch of n games: the tuned value when the batch is large enough to give
+// every SM many blocks, fewer for small batches (4096 envs must not end up in two blocks).
+static int iters_for(int64_t n, int tuned) {
+    const int64_t chunks = (n + kThreads - 1) / kThreads;
+    const int64_t it = chunks / (148 * 16);
+    return (int)(it < 1 ? 1 : (it > tuned ? tuned : it));
+}
 static bool step_prefetch() {
     static const bool v = []() {
         const char* e = getenv("QTTT_STEP_PREFETCH");
@@ -829,7 +836,6 @@ template <int kFmt, bool kRandom, int kMode>
 static int launch_step_mode(StepArgs a, int64_t n, cudaStream_t st) {
     const int64_t kSlice = 1ll << 31;
     const bool full = !kRandom && a.coin && a.reward && a.done && a.mask && a.status;
-    const int iters = step_iters();
     const bool pf = step_prefetch();
     const int act_bytes = kFmt == QTTT_ACT_PAIR ? 2 : 1;
     for (int64_t lo = 0; lo < n; lo += kSlice) {
@@ -845,6 +851,7 @@ static int launch_step_mode(StepArgs a, int64_t n, cudaStream_t st) {
         b.status = a.status ? a.status + lo : nullptr;
         b.action_out = a.action_out ? a.action_out + lo : nullptr;
         b.coin_out = a.coin_out ? a.coin_out + lo : nullptr;
+        const int iters = iters_for(m, step_iters());
         b.n = (uint32_t)m;
         b.iters = iters;
         const int grid = chunk_grid(m, iters);
@@ -923,9 +930,9 @@ int qttt_step_ex(qttt_state* state, const void* action, int action_format, const
 static int packed_entry(qttt_state* state, const uint8_t* action_coin, uint16_t* result, qttt_state* obs,
                         int64_t n, bool zero_copy, cudaStream_t st) {
     const int64_t kSlice = 1ll << 31;
-    const int iters = step_iters();
     for (int64_t lo = 0; lo < n; lo += kSlice) {
         const int64_t m = n - lo < kSlice ? n - lo : kSlice;
+        const int iters = iters_for(m, step_iters());
         qttt_state* o = obs ? obs + lo : nullptr;
         if (zero_copy)
             k_step_packed_zc<<<chunk_grid(m, iters), kThreads, 0, st>>>(state + lo, action_coin + lo, result + lo, o,
@@ -1034,7 +1041,7 @@ int qttt_observe(const qttt_state* state, int8_t* classical, int8_t* moves, uint
     if (!state || n < 0) return QTTT_ERR_ARG;
     if (misaligned(state, 16) || misaligned(reward_p1, 4)) return QTTT_ERR_ALIGN;
     if (n == 0) return QTTT_OK;
-    k_observe<<<chunk_grid(n, 4), kThreads, 0, (cudaStream_t)stream>>>(state, classical, moves, n_moves, q_p1, q_p2, turn, rounds, reward_p1, winner, mask_bool, n);
+    k_observe<<<chunk_grid(n, iters_for(n, 4)), kThreads, 0, (cudaStream_t)stream>>>(state, classical, moves, n_moves, q_p1, q_p2, turn, rounds, reward_p1, winner, mask_bool, n);
     return check_launch();
 }
 
@@ -1072,9 +1079,9 @@ int qttt_qeval_both(const qttt_state* state, const uint8_t* action, qttt_state* 
         return QTTT_ERR_ALIGN;
     if (n == 0) return QTTT_OK;
     if (sq0 || sq1)
-        k_qeval_both<true><<<chunk_grid(n, 4), kThreads, 0, (cudaStream_t)stream>>>(state, action, next0, next1, board0, board1, sq0, sq1, closes, result_prob, n);
+        k_qeval_both<true><<<chunk_grid(n, iters_for(n, 4)), kThreads, 0, (cudaStream_t)stream>>>(state, action, next0, next1, board0, board1, sq0, sq1, closes, result_prob, n);
     else
-        k_qeval_both<false><<<chunk_grid(n, 4), kThreads, 0, (cudaStream_t)stream>>>(state, action, next0, next1, board0, board1, sq0, sq1, closes, result_prob, n);
+        k_qeval_both<false><<<chunk_grid(n, iters_for(n, 4)), kThreads, 0, (cudaStream_t)stream>>>(state, action, next0, next1, board0, board1, sq0, sq1, closes, result_prob, n);
     return check_launch();
 }
 
@@ -1147,7 +1154,7 @@ int qttt_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, int64_t* stats, 
     if (!stats) return QTTT_ERR_ARG;
     if (misaligned(stats, 8)) return QTTT_ERR_ALIGN;
     if (game_hi == game_lo) return QTTT_OK;
-    k_sweep<<<chunk_grid(game_hi - game_lo, kSweepIters), kThreads, 0, (cudaStream_t)stream>>>(
+    k_sweep<<<chunk_grid(game_hi - game_lo, iters_for(game_hi - game_lo, kSweepIters)), kThreads, 0, (cudaStream_t)stream>>>(
         game_lo, game_hi, seed, reinterpret_cast<unsigned long long*>(stats));
     return check_launch();
 }
