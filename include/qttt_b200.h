@@ -203,6 +203,38 @@ QTTT_API int qttt_observe(const qttt_state* state, int8_t* classical, int8_t* mo
  * component.  (nn.Model.get_mask, nn.py:44-61, is the complement of the legal mask.) */
 QTTT_API int qttt_features(const qttt_state* state, float* features, int64_t n, void* stream);
 
+/* qtttgym.Env for ONE game at minimum latency (the single-env adapter qtttgym_b200.Env): one
+ * launch applies `op` to state[0] and writes a 128-byte record of everything Env.step / observ /
+ * turn / _reward / check_win report into record_host, which must be MAPPED PINNED HOST memory
+ * (16-byte aligned); the 32-bit word at byte 124 is set to `seq` last, after a system-scope
+ * fence, so the host can spin on it instead of synchronising a stream.
+ *   op 0 : Env.step((a, b)) (env.py:34-53); coin < 0 -> Philox(seed, game 0, len(moves), epoch)
+ *   op 1 : Env.reset (env.py:55-57)         op 2 : re-emit the record of the current state
+ * Record layout (bytes): state 0..15 | legal mask u64 16 | reward f32 24 | terminated 28 |
+ * status 29 | turn 30 | len(moves) 31 | classical i8[9] 32 | q_states_p1 i8[5][2] 48 |
+ * q_states_p2 i8[4][2] 58 | check_win rounds i8[2] 66 | winner 68 | Env._reward f32 72 |
+ * moves i8[9][2] 80 | seq u32 124. */
+QTTT_API int qttt_env1(qttt_state* state, int op, int a, int b, int coin, uint64_t seed, uint64_t epoch,
+                       void* record_host, uint32_t seq, void* stream);
+
+/* nn.Model.get_mask (nn.py:44-61) for packed states: illegal_mask uint8[n][36] (bool bytes,
+ * 4-byte aligned), entry [g][a] = 1 when action a touches a classical square of game g
+ * (occupied[i] or occupied[j]) -- the logits the reference's policy head sets to -inf.  It is
+ * the complement of GameState.action_mask() (mcts.py:87-91). */
+QTTT_API int qttt_get_mask(const qttt_state* state, uint8_t* illegal_mask, int64_t n, void* stream);
+
+/* qttt_step_ex fused with the net-input encoding of the NEW state: features float[n][18][10]
+ * (GameState.to_vector, mcts.py:67-85; required, 16-byte aligned) and, optionally,
+ * illegal_mask uint8[n][36] (nn.Model.get_mask, nn.py:44-61) are written by the same launch that
+ * steps the games, so feeding a policy/value net costs no second pass over the state array
+ * (what AlphaZero-style callers do after every move: alphazero.py:143-144,294-303).  All other
+ * arguments and outputs as in qttt_step_ex; reward / done / mask / status may be NULL. */
+QTTT_API int qttt_step_features(qttt_state* state, const void* action, int action_format,
+                                const uint8_t* coin, uint64_t seed, uint64_t game_base, uint64_t epoch,
+                                uint32_t flags, float* reward, uint8_t* done, uint64_t* mask,
+                                uint8_t* status, float* features, uint8_t* illegal_mask, int64_t n,
+                                void* stream);
+
 /* Inverse of qttt_observe for (classical, moves, n_moves): builds packed states from
  * reference-shaped positions (what MCTS.reset does with game.board / game.moves,
  * mcts.py:139-164 -- but the entanglement is re-derived, so mid-game roots are handled
@@ -256,7 +288,9 @@ QTTT_API int qttt_mcts_stats(const void* pool, int64_t capacity, const int32_t* 
                              int32_t* n_visits, double* q_values, int32_t* n_total, uint8_t* choose,
                              int64_t n_roots, void* stream);
 /* MCTS.sync (mcts.py:317-337): the root moves to the child of action[r] whose position is
- * now[r] (expanding it if needed); meta[r][3] bit 1 is set when there is no such child. */
+ * now[r] (expanding it if needed); meta[r][3] bit 1 is set when there is no such child.
+ * action[r] >= 36 means "no move was played in this game" (a finished game in a batch): the
+ * root stays where it is and no error is flagged. */
 QTTT_API int qttt_mcts_sync(void* pool, int64_t capacity, int32_t* meta, const uint8_t* action,
                             const qttt_state* now, int64_t n_roots, void* stream);
 

@@ -39,24 +39,26 @@ def _finished(env: BatchedEnv) -> torch.Tensor:
 
 
 class RandomStrategy(BatchedStrategy):
-    """mcts.py:287-292: uniform over the legal actions."""
+    """mcts.py:287-292: uniform over the legal actions -- drawn by the step kernel's own random
+    policy (``qttt_step_random`` on a scratch copy of the states: Philox keyed (seed, env, ply,
+    call)), not by eager tensor ops: one launch, no host synchronisation."""
 
     def __init__(self, seed: int = 0):
-        self.gen = None
-        self.seed = seed
+        self.seed = int(seed)
+        self.calls = 0
+        self._scratch = None
 
     def reset(self, env):
         super().reset(env)
-        self.gen = torch.Generator(device=env.device)
-        self.gen.manual_seed(self.seed)
+        self._scratch = BatchedEnv(env.num_envs, device=env.device, seed=self.seed, game_base=env.game_base)
 
     def choose(self):
-        legal = self.env.action_mask().float()
-        none = legal.sum(1) == 0
-        legal[none, 0] = 1.0
-        a = torch.multinomial(legal, 1, generator=self.gen).squeeze(1).to(torch.uint8)
-        a[none | _finished(self.env)] = 255
-        return a
+        sc = self._scratch
+        sc.state.copy_(self.env.state)
+        self.calls += 1
+        sc.epoch = self.calls                      # a fresh draw per call even at the same ply
+        _, _, _, _, info = sc.step_random(record=True)
+        return info["action"]                      # 255 for games that are already over
 
 
 class RolloutStrategy(BatchedStrategy):
@@ -111,20 +113,19 @@ class MCTSStrategy(BatchedStrategy):
 
     def sync(self, actions):
         # trees of games that were still running before this move follow it; finished games
-        # keep their last root (their action is the 255 filler)
-        live = actions < 36
-        safe = torch.where(live, actions, torch.zeros_like(actions))
-        self.search.sync(safe, self.env.state)
+        # (action 255) keep their root: qttt_mcts_sync leaves them alone
+        self.search.sync(actions, self.env.state)
 
 
 def play_games(strat_x: BatchedStrategy, strat_o: BatchedStrategy, n_games: int, seed: int = 0,
                device="cuda"):
     """strat_eval.py:34-63 for ``n_games`` games at once: X (player 1) and O alternate until a
-    line exists or 9 moves are on the board.  Returns (env, winner uint8[N]: 0 draw, 1 X, 2 O)."""
+    line exists or 9 moves are on the board.  Returns (env, winner uint8[N]: 0 draw, 1 X, 2 O).
+    The 9 plies are enqueued back to back: nothing here reads a device value on the host, the
+    caller synchronises when it looks at the result (finished games answer 255 = no move)."""
     env = BatchedEnv(n_games, device=device, seed=seed)
     strat_x.reset(env)
     strat_o.reset(env)
-    env.done.zero_()
     for ply in range(9):
         mover = strat_x if ply % 2 == 0 else strat_o
         mover.contemplate()
@@ -132,8 +133,6 @@ def play_games(strat_x: BatchedStrategy, strat_o: BatchedStrategy, n_games: int,
         env.step(actions)
         strat_x.sync(actions)
         strat_o.sync(actions)
-        if bool(env.done.all()):
-            break
     winner = env.winner()
     return env, winner
 

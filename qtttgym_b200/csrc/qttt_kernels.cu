@@ -407,47 +407,184 @@ __device__ __forceinline__ void feature_move(float* slot, const State& s, uint32
     }
 }
 
+// One warp's 32 games -> features: every lane zero-fills its own slot of `warp_buf` and scatters
+// its game's non-zeros, then the warp streams the `games_here` slots (contiguous in the output) to
+// HBM as lane-contiguous float4 vectors.  `mine_valid`: this lane holds a game.
+__device__ __forceinline__ void emit_features(float* warp_buf, int lane, const State& s, bool mine_valid,
+                                              float* __restrict__ out_base, int games_here) {
+    float* mine = warp_buf + lane * kFeatStride;
+#pragma unroll
+    for (int k = 0; k < 45; ++k) reinterpret_cast<float4*>(mine)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mine_valid) {
+        const uint32_t P0 = plane0(s), P1 = plane1(s), P2 = plane2(s), P3 = plane3(s);
+        const uint32_t C = P0 | P1 | P2 | P3, nm = n_moves(s);
+#pragma unroll
+        for (int sq = 0; sq < 9; ++sq) {                       // rows 0..8: one-hot of board[sq]
+            const int b = board_value(P0, P1, P2, P3, sq);
+            mine[sq * 10 + (b < 0 ? 9 : b)] = 1.0f;
+        }
+        feature_move<0>(mine, s, nm); feature_move<1>(mine, s, nm); feature_move<2>(mine, s, nm);
+        feature_move<3>(mine, s, nm); feature_move<4>(mine, s, nm); feature_move<5>(mine, s, nm);
+        feature_move<6>(mine, s, nm); feature_move<7>(mine, s, nm); feature_move<8>(mine, s, nm);
+        uint32_t live = 0u;                                    // squares with an uncollapsed mark
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const uint32_t E = edge_dyn(s, (uint32_t)t);
+            live |= ((uint32_t)t < nm && !(E & C)) ? E : 0u;
+        }
+#pragma unroll
+        for (int sq = 0; sq < 9; ++sq)
+            if (!(live >> sq & 1u)) mine[(9 + sq) * 10 + 9] = 1.0f;
+    }
+    __syncwarp();
+    float4* dst = reinterpret_cast<float4*>(out_base);
+    for (int q = lane; q < games_here * 45; q += 32) {
+        const int owner = q / 45, r = q - owner * 45;
+        dst[q] = reinterpret_cast<const float4*>(warp_buf + owner * kFeatStride)[r];
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(kFeatThreads)
 k_features(const qttt_state* __restrict__ state, float* __restrict__ out, int64_t n) {
     __shared__ __align__(16) float buf[kFeatThreads / 32][32 * kFeatStride];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* mine = buf[warp] + lane * kFeatStride;
     const int64_t warp0 = ((int64_t)blockIdx.x * kFeatThreads + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * kFeatThreads) >> 5;
     for (int64_t base = warp0 * 32; base < n; base += n_warps * 32) {
         const int64_t g = base + lane;
         const int games_here = (int)((n - base) < 32 ? (n - base) : 32);
+        State s = empty_state();
+        if (g < n) s = load_state(state, g);
+        emit_features(buf[warp], lane, s, g < n, out + base * 180, games_here);
+    }
+}
+
+// nn.Model.get_mask's illegal-action mask as 36 bool bytes (9 words) of one game: the complement
+// of the legal mask (nn.py:44-61: occupied[i] or occupied[j]).
+__device__ __forceinline__ void store_illegal_mask(uint8_t* __restrict__ dst, uint64_t legal) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(dst);
 #pragma unroll
-        for (int k = 0; k < 45; ++k) reinterpret_cast<float4*>(mine)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g < n) {
-            const State s = load_state(state, g);
-            const uint32_t P0 = plane0(s), P1 = plane1(s), P2 = plane2(s), P3 = plane3(s);
-            const uint32_t C = P0 | P1 | P2 | P3, nm = n_moves(s);
-#pragma unroll
-            for (int sq = 0; sq < 9; ++sq) {                       // rows 0..8: one-hot of board[sq]
-                const int b = board_value(P0, P1, P2, P3, sq);
-                mine[sq * 10 + (b < 0 ? 9 : b)] = 1.0f;
+    for (int k = 0; k < 9; ++k)
+        w[k] = ((((uint32_t)(legal >> (4 * k)) & 15u) * 0x00204081u) & 0x01010101u) ^ 0x01010101u;
+}
+
+// Env.step fused with the policy/value net's input encoding: the step of k_step followed, in the
+// same thread, by GameState.to_vector of the NEW state (and optionally nn.Model.get_mask), so the
+// features cost no second pass over the state array.  Same block shape and staging as k_features
+// (the 720 B of features per game are the traffic; the step itself is 48 B).
+struct StepFeatArgs {
+    StepArgs st;
+    float* features;            // [n][18][10], 16-byte aligned
+    uint8_t* illegal_mask;      // [n][36] bool, optional, 4-byte aligned
+};
+
+template <int kFmt, int kMode>
+__global__ void __launch_bounds__(kFeatThreads) k_step_features(const StepFeatArgs fa) {
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    uint8_t* lut = dyn_smem;
+    float* buf = reinterpret_cast<float*>(dyn_smem + kLutStepBytes);
+    stage_luts(lut, kLutStepBytes);
+    const Luts L = luts_from_image(lut);
+    const StepArgs& a = fa.st;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* warp_buf = buf + warp * 32 * kFeatStride;
+    const uint32_t warp0 = (blockIdx.x * kFeatThreads + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * kFeatThreads) >> 5;
+    for (uint32_t base = warp0 * 32u; base < a.n; base += n_warps * 32u) {
+        const uint32_t i = base + lane;
+        const bool valid = i < a.n;
+        const int games_here = (int)((a.n - base) < 32u ? (a.n - base) : 32u);
+        State s = empty_state();
+        if (valid) {
+            if (kMode != kStepFresh) {
+                const uint4 sv = *reinterpret_cast<const uint4*>(a.state + i);
+                s = State{sv.x, sv.y, sv.z, sv.w};
             }
-            feature_move<0>(mine, s, nm); feature_move<1>(mine, s, nm); feature_move<2>(mine, s, nm);
-            feature_move<3>(mine, s, nm); feature_move<4>(mine, s, nm); feature_move<5>(mine, s, nm);
-            feature_move<6>(mine, s, nm); feature_move<7>(mine, s, nm); feature_move<8>(mine, s, nm);
-            uint32_t live = 0u;                                    // squares with an uncollapsed mark
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const uint32_t E = edge_dyn(s, (uint32_t)t);
-                live |= ((uint32_t)t < nm && !(E & C)) ? E : 0u;
+            uint32_t enew;
+            if (kFmt == QTTT_ACT_INDEX) {
+                enew = L.pair[a.action[i]];
+            } else {
+                const uchar2 ab = reinterpret_cast<const uchar2*>(a.action)[i];
+                enew = pair_to_edge(ab.x, ab.y);
             }
-#pragma unroll
-            for (int sq = 0; sq < 9; ++sq)
-                if (!(live >> sq & 1u)) mine[(9 + sq) * 10 + 9] = 1.0f;
+            const uint32_t coin = a.coin ? (a.coin[i] & 1u) : 0u;
+            const StepOut o = step_game<false, kMode>(s, enew, a.coin != nullptr, coin, a.seed,
+                                                      a.game_base + (uint64_t)i, a.dword, L);
+            if (o.write_state) *reinterpret_cast<uint4*>(a.state + i) = make_uint4(s.x, s.y, s.z, s.w);
+            const uint64_t legal = L.legal[~o.classical & M9];
+            if (a.reward) reinterpret_cast<uint32_t*>(a.reward)[i] = reward_bits(o.win);
+            if (a.done) a.done[i] = (uint8_t)o.done;
+            if (a.mask) a.mask[i] = legal;
+            if (a.status) a.status[i] = (uint8_t)o.status;
+            if (fa.illegal_mask) store_illegal_mask(fa.illegal_mask + 36ull * i, legal);
         }
-        __syncwarp();
-        float4* dst = reinterpret_cast<float4*>(out + base * 180);
-        for (int q = lane; q < games_here * 45; q += 32) {
-            const int owner = q / 45, r = q - owner * 45;
-            dst[q] = reinterpret_cast<const float4*>(buf[warp] + owner * kFeatStride)[r];
+        emit_features(warp_buf, lane, s, valid, fa.features + (size_t)base * 180, games_here);
+    }
+}
+
+// nn.Model.get_mask for packed states (one thread per game, 9 word stores).
+__global__ void __launch_bounds__(kThreads)
+k_get_mask(const qttt_state* __restrict__ state, uint8_t* __restrict__ illegal_mask, int64_t n) {
+    __shared__ __align__(16) uint8_t smem[kLutStepBytes];
+    stage_luts(smem, kLutStepBytes);
+    const Luts L = luts_from_image(smem);
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+        const State s = load_state(state, i);
+        store_illegal_mask(illegal_mask + 36 * i, L.legal[~classical(s) & M9]);
+    }
+}
+
+// ------------------------------------------------------------------------------ single env
+// qtttgym.Env for ONE game with the lowest possible latency: one launch steps the game (the
+// action travels as kernel arguments: no host->device copy), decodes everything Env.step /
+// observ / turn / _reward report into a 128-byte record and writes that record straight into
+// MAPPED PINNED HOST memory; the host spins on the sequence word at its end (written last, after
+// a system-scope fence).  No copy engine, no stream synchronisation.
+//   record: state[0:16] mask[16:24] reward[24:28] done[28] status[29] turn[30] n_moves[31]
+//           classical[32:41] q_p1[48:58] q_p2[58:66] rounds[66:68] winner[68] reward_p1[72:76]
+//           moves[80:98] ... seq[124:128]
+__global__ void __launch_bounds__(32)
+k_env1(qttt_state* __restrict__ state, int a, int b, int coin, int op, uint64_t seed, uint32_t dword,
+       uint8_t* __restrict__ rec_host, uint32_t seq) {
+    __shared__ __align__(16) uint8_t smem[kLutStepBytes];
+    __shared__ __align__(16) uint8_t rec[128];
+    stage_luts(smem, kLutStepBytes);
+    const Luts L = luts_from_image(smem);
+    if (threadIdx.x < 8) reinterpret_cast<uint4*>(rec)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        State s = empty_state();
+        if (op != 1) s = load_state(state, 0);                   // op 1: reset (Board.__init__)
+        StepOut o;
+        if (op == 0) {                                            // op 0: Env.step
+            // anything outside 0..8 (negative values included: outside the action domain) is illegal
+            const uint32_t enew = pair_to_edge((uint32_t)a, (uint32_t)b);
+            o = step_game<false, kStepPlain>(s, enew, coin >= 0, (uint32_t)coin & 1u, seed, 0ull, dword, L);
+        } else {                                                  // reset / refresh: outputs of the state as it is
+            const uint32_t C = classical(s);
+            o.win = any_line(s, C, L);
+            o.done = (o.win != 0u) | (n_moves(s) > 8u);
+            o.classical = C;
+            o.status = 0u;
         }
-        __syncwarp();
+        store_state(state, 0, s);
+        *reinterpret_cast<uint4*>(rec) = make_uint4(s.x, s.y, s.z, s.w);
+        *reinterpret_cast<uint64_t*>(rec + 16) = L.legal[~o.classical & M9];
+        *reinterpret_cast<uint32_t*>(rec + 24) = reward_bits(o.win);
+        rec[28] = (uint8_t)o.done;
+        rec[29] = (uint8_t)o.status;
+        observe_game(s, L, reinterpret_cast<int8_t*>(rec + 32), reinterpret_cast<int8_t*>(rec + 80), rec + 31,
+                     reinterpret_cast<int8_t*>(rec + 48), reinterpret_cast<int8_t*>(rec + 58), rec + 30,
+                     reinterpret_cast<int8_t*>(rec + 66), reinterpret_cast<float*>(rec + 72), rec + 68, nullptr, 0);
+    }
+    __syncwarp();
+    if (threadIdx.x < 7) reinterpret_cast<uint4*>(rec_host)[threadIdx.x] = reinterpret_cast<const uint4*>(rec)[threadIdx.x];
+    __threadfence_system();
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        *reinterpret_cast<volatile uint32_t*>(rec_host + 124) = seq;
     }
 }
 
@@ -627,22 +764,28 @@ __device__ __forceinline__ bool warp_expand(MctsNode* tree, int32_t* meta, int64
     State s0 = tree[node].state, s1 = s0;                    // every lane computes the same children
     const StepResult r0 = step_core(s0, enew, 0u, L);
     const int need = r0.collapsed ? 2 : 1;
-    const int c0 = meta[kMetaCount];
-    if ((int64_t)c0 + need > capacity) {
+    if (mcts_nodes_available(meta, capacity) < need) {
         if (lane == 0) meta[kMetaError] |= kMctsErrPoolFull;
         return false;
     }
+    // lane 0 takes the nodes (free list first, mcts_alloc); everybody initialises them
+    int c0 = 0, c1 = -1;
+    if (lane == 0) {
+        c0 = mcts_alloc(tree, meta);
+        if (r0.collapsed) c1 = mcts_alloc(tree, meta);
+    }
+    c0 = __shfl_sync(0xFFFFFFFFu, c0, 0);
+    c1 = __shfl_sync(0xFFFFFFFFu, c1, 0);
     const bool turn = !tree[node].turn;
     warp_init_node(tree[c0], s0, turn, L, lane);
     if (r0.collapsed) {
         step_core(s1, enew, 1u, L);
-        warp_init_node(tree[c0 + 1], s1, turn, L, lane);
+        warp_init_node(tree[c1], s1, turn, L, lane);
     }
     __syncwarp();
     if (lane == 0) {
         tree[node].child[a][0] = c0;
-        if (r0.collapsed) tree[node].child[a][1] = c0 + 1;
-        meta[kMetaCount] = c0 + need;
+        if (r0.collapsed) tree[node].child[a][1] = c1;
     }
     __syncwarp();
     return true;
@@ -1057,6 +1200,109 @@ int qttt_features(const qttt_state* state, float* features, int64_t n, void* str
         k_features<<<(int)(want < cap ? want : cap), kFeatThreads, 0, (cudaStream_t)stream>>>(state, features, n);
     }
     return check_launch();
+}
+
+int qttt_env1(qttt_state* state, int op, int a, int b, int coin, uint64_t seed, uint64_t epoch,
+              void* record_host, uint32_t seq, void* stream) {
+    if (!state || !record_host || op < 0 || op > 2) return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(record_host, 16)) return QTTT_ERR_ALIGN;
+    if (const int rc = device_ok()) return rc;
+    k_env1<<<1, 32, 0, (cudaStream_t)stream>>>(state, a, b, coin, op, seed, domain_word(0u, epoch),
+                                               static_cast<uint8_t*>(record_host), seq);
+    return check_launch();
+}
+
+int qttt_get_mask(const qttt_state* state, uint8_t* illegal_mask, int64_t n, void* stream) {
+    if (n == 0) return QTTT_OK;
+    if (!state || !illegal_mask || n < 0) return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(illegal_mask, 4)) return QTTT_ERR_ALIGN;
+    if (const int rc = device_ok()) return rc;
+    k_get_mask<<<chunk_grid(n, iters_for(n, 4)), kThreads, 0, (cudaStream_t)stream>>>(state, illegal_mask, n);
+    return check_launch();
+}
+
+}  // extern "C"
+
+template <int kFmt, int kMode>
+static int launch_step_features(const StepFeatArgs& fa, int64_t n, cudaStream_t st) {
+    constexpr int kSmem = kLutStepBytes + (kFeatThreads / 32) * 32 * kFeatStride * (int)sizeof(float);
+    static bool configured[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        const cudaError_t e = cudaFuncSetAttribute(k_step_features<kFmt, kMode>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+        if (e != cudaSuccess) return -(1000 + (int)e);
+        configured[dev] = true;
+    }
+    const int64_t kSlice = 1ll << 31;
+    const int act_bytes = kFmt == QTTT_ACT_PAIR ? 2 : 1;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    for (int64_t lo = 0; lo < n; lo += kSlice) {
+        const int64_t m = n - lo < kSlice ? n - lo : kSlice;
+        StepFeatArgs b = fa;
+        b.st.state = fa.st.state + lo;
+        b.st.action = fa.st.action + act_bytes * lo;
+        b.st.coin = fa.st.coin ? fa.st.coin + lo : nullptr;
+        b.st.game_base = fa.st.game_base + (uint64_t)lo;
+        b.st.reward = fa.st.reward ? fa.st.reward + lo : nullptr;
+        b.st.done = fa.st.done ? fa.st.done + lo : nullptr;
+        b.st.mask = fa.st.mask ? fa.st.mask + lo : nullptr;
+        b.st.status = fa.st.status ? fa.st.status + lo : nullptr;
+        b.st.n = (uint32_t)m;
+        b.features = fa.features + 180 * lo;
+        b.illegal_mask = fa.illegal_mask ? fa.illegal_mask + 36 * lo : nullptr;
+        const int64_t want = (m + kFeatThreads - 1) / kFeatThreads;
+        const int64_t cap = (int64_t)sms * 4 * 8;                 // 4 blocks of 53 KB per SM, 8 waves
+        k_step_features<kFmt, kMode><<<(int)(want < cap ? want : cap), kFeatThreads, kSmem, st>>>(b);
+        const int rc = check_launch();
+        if (rc != QTTT_OK) return rc;
+    }
+    return QTTT_OK;
+}
+
+template <int kFmt>
+static int launch_step_features_fmt(const StepFeatArgs& fa, uint32_t flags, int64_t n, cudaStream_t st) {
+    if (flags & QTTT_STEP_FRESH) return launch_step_features<kFmt, kStepFresh>(fa, n, st);
+    if (flags & QTTT_STEP_AUTORESET) return launch_step_features<kFmt, kStepAuto>(fa, n, st);
+    if (flags & QTTT_STEP_AUTORESET_NEXT) return launch_step_features<kFmt, kStepAutoNext>(fa, n, st);
+    return launch_step_features<kFmt, kStepPlain>(fa, n, st);
+}
+
+extern "C" {
+
+int qttt_step_features(qttt_state* state, const void* action, int action_format, const uint8_t* coin,
+                       uint64_t seed, uint64_t game_base, uint64_t epoch, uint32_t flags, float* reward,
+                       uint8_t* done, uint64_t* mask, uint8_t* status, float* features,
+                       uint8_t* illegal_mask, int64_t n, void* stream) {
+    if (action_format != QTTT_ACT_INDEX && action_format != QTTT_ACT_PAIR) return QTTT_ERR_ARG;
+    const uint32_t modes = flags & (QTTT_STEP_FRESH | QTTT_STEP_AUTORESET | QTTT_STEP_AUTORESET_NEXT);
+    if ((flags & ~(QTTT_STEP_FRESH | QTTT_STEP_AUTORESET | QTTT_STEP_AUTORESET_NEXT)) || (modes & (modes - 1)))
+        return QTTT_ERR_ARG;
+    if (n == 0) return QTTT_OK;
+    if (!state || !action || !features || n < 0) return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(mask, 8) || misaligned(reward, 4) || misaligned(features, 16) ||
+        misaligned(illegal_mask, 4))
+        return QTTT_ERR_ALIGN;
+    if (action_format == QTTT_ACT_PAIR && misaligned(action, 2)) return QTTT_ERR_ALIGN;
+    if (const int rc = device_ok()) return rc;
+    StepFeatArgs fa{};
+    fa.st.state = state;
+    fa.st.action = static_cast<const uint8_t*>(action);
+    fa.st.coin = coin;
+    fa.st.seed = seed;
+    fa.st.game_base = game_base;
+    fa.st.dword = domain_word(0u, epoch);
+    fa.st.reward = reward;
+    fa.st.done = done;
+    fa.st.mask = mask;
+    fa.st.status = status;
+    fa.features = features;
+    fa.illegal_mask = illegal_mask;
+    if (action_format == QTTT_ACT_INDEX)
+        return launch_step_features_fmt<QTTT_ACT_INDEX>(fa, flags, n, (cudaStream_t)stream);
+    return launch_step_features_fmt<QTTT_ACT_PAIR>(fa, flags, n, (cudaStream_t)stream);
 }
 
 int qttt_pack(qttt_state* state, const int8_t* classical, const int8_t* moves,

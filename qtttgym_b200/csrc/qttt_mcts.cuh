@@ -40,7 +40,11 @@ struct alignas(16) MctsNode {
 static_assert(sizeof(MctsNode) == 752, "MctsNode layout");
 
 // per-root bookkeeping, int32[8]
-enum { kMetaRoot = 0, kMetaCount = 1, kMetaRollouts = 2, kMetaError = 3, kMetaStride = 8 };
+//   [0] root node   [1] nodes ever taken from the pool's fresh end (high-water mark)
+//   [2] rollouts done   [3] error bits   [4] head of the free list (-1 = empty)
+//   [5] length of the free list   [6] most nodes alive at once
+enum { kMetaRoot = 0, kMetaCount = 1, kMetaRollouts = 2, kMetaError = 3, kMetaFree = 4, kMetaFreeCount = 5,
+       kMetaPeak = 6, kMetaStride = 8 };
 enum { kMctsErrPoolFull = 1, kMctsErrNoSuchChild = 2 };
 
 QTTT_HD double d_add(double a, double b) {
@@ -88,6 +92,48 @@ QTTT_HD void mcts_init_node(MctsNode& nd, const State& s, bool turn, const Luts&
 QTTT_HD void mcts_init_root(MctsNode* tree, int32_t* meta, const State& s, const Luts& L) {
     mcts_init_node(tree[0], s, (n_moves(s) & 1u) == 0u, L);
     meta[kMetaRoot] = 0; meta[kMetaCount] = 1; meta[kMetaRollouts] = 0; meta[kMetaError] = 0;
+    meta[kMetaFree] = -1; meta[kMetaFreeCount] = 0; meta[kMetaPeak] = 1;
+}
+
+// Node allocation: reuse a node reclaimed by mcts_sync (MCTS._prune, mcts.py:222-231) when there
+// is one, else take the next fresh node of the pool.  Which slot a node lives in has no influence
+// on the search (children are referenced by index), so reuse keeps the statistics bit-identical.
+QTTT_HD int mcts_nodes_available(const int32_t* meta, int64_t capacity) {
+    const int64_t fresh = capacity - (int64_t)meta[kMetaCount];
+    return (int)(fresh > 0x3FFFFFFF ? 0x3FFFFFFF : fresh) + meta[kMetaFreeCount];
+}
+QTTT_HD int mcts_alloc(MctsNode* tree, int32_t* meta) {
+    int id;
+    if (meta[kMetaFree] >= 0) {
+        id = meta[kMetaFree];
+        meta[kMetaFree] = tree[id].child[0][0];        // the free list is threaded through child[0][0]
+        meta[kMetaFreeCount] -= 1;
+    } else {
+        id = meta[kMetaCount];
+        meta[kMetaCount] = id + 1;
+    }
+    const int live = meta[kMetaCount] - meta[kMetaFreeCount];
+    if (live > meta[kMetaPeak]) meta[kMetaPeak] = live;
+    return id;
+}
+
+// MCTS._prune (mcts.py:222-231): give the whole subtree under `c` back to the pool.  The nodes
+// still to visit are chained through `ntot` (their statistics are dead), so no stack is needed.
+QTTT_HD void mcts_free_subtree(MctsNode* tree, int32_t* meta, int c) {
+    int head = c;
+    tree[c].ntot = 0xFFFFFFFFu;
+    while (head >= 0) {
+        const int v = head;
+        head = (int)tree[v].ntot;
+        for (int a = 0; a < 36; ++a)
+            for (int k = 0; k < 2; ++k) {
+                const int ch = tree[v].child[a][k];
+                if (ch >= 0) { tree[ch].ntot = (uint32_t)head; head = ch; }
+            }
+        tree[v].child[0][0] = meta[kMetaFree];
+        meta[kMetaFree] = v;
+        meta[kMetaFreeCount] += 1;
+    }
 }
 
 // mcts.py:280-285: argmax_a Q[a] + c_puct * P[a] * sqrt(Ntot) / (1 + N[a]), first maximum wins
@@ -115,17 +161,17 @@ QTTT_HD bool mcts_expand(MctsNode* tree, int32_t* meta, int64_t capacity, int no
     State s0 = tree[node].state, s1 = s0;
     const StepResult r0 = step_core(s0, enew, 0u, L);
     const int need = r0.collapsed ? 2 : 1;
-    if ((int64_t)meta[kMetaCount] + need > capacity) { meta[kMetaError] |= kMctsErrPoolFull; return false; }
+    if (mcts_nodes_available(meta, capacity) < need) { meta[kMetaError] |= kMctsErrPoolFull; return false; }
     const bool turn = !tree[node].turn;
-    const int c0 = meta[kMetaCount];
+    const int c0 = mcts_alloc(tree, meta);
     mcts_init_node(tree[c0], s0, turn, L);
     tree[node].child[a][0] = c0;
     if (r0.collapsed) {
         step_core(s1, enew, 1u, L);
-        mcts_init_node(tree[c0 + 1], s1, turn, L);
-        tree[node].child[a][1] = c0 + 1;
+        const int c1 = mcts_alloc(tree, meta);
+        mcts_init_node(tree[c1], s1, turn, L);
+        tree[node].child[a][1] = c1;
     }
-    meta[kMetaCount] = c0 + need;
     return true;
 }
 
@@ -190,15 +236,27 @@ QTTT_HD int mcts_choose(const MctsNode& root) {
 QTTT_HD void mcts_sync(MctsNode* tree, int32_t* meta, int64_t capacity, int action, const State& now,
                        const Luts& L) {
     const int root = meta[kMetaRoot];
-    if (action < 0 || action >= 36 || !(tree[root].legal >> action & 1ull)) { meta[kMetaError] |= kMctsErrNoSuchChild; return; }
+    if (action >= 36) return;            // "no move was played" (a finished game's filler): keep the root
+    if (action < 0 || !(tree[root].legal >> action & 1ull)) { meta[kMetaError] |= kMctsErrNoSuchChild; return; }
     if (tree[root].child[action][0] < 0 && !mcts_expand(tree, meta, capacity, root, action, L)) return;
+    int keep = -1;
     for (int k = 0; k < 2; ++k) {
         const int c = tree[root].child[action][k];
         if (c < 0) continue;
         const State& s = tree[c].state;
-        if (s.x == now.x && s.y == now.y && s.z == now.z && s.w == now.w) { meta[kMetaRoot] = c; return; }
+        if (s.x == now.x && s.y == now.y && s.z == now.z && s.w == now.w) { keep = c; break; }
     }
-    meta[kMetaError] |= kMctsErrNoSuchChild;
+    if (keep < 0) { meta[kMetaError] |= kMctsErrNoSuchChild; return; }
+    // mcts.py:330-337: every other child of the old root is pruned with its subtree, the old
+    // root itself is dropped; their nodes go back to the pool
+    for (int a = 0; a < 36; ++a)
+        for (int k = 0; k < 2; ++k) {
+            const int c = tree[root].child[a][k];
+            if (c >= 0 && c != keep) mcts_free_subtree(tree, meta, c);
+            tree[root].child[a][k] = -1;
+        }
+    mcts_free_subtree(tree, meta, root);
+    meta[kMetaRoot] = keep;
 }
 
 }  // namespace qttt

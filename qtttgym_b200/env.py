@@ -146,6 +146,35 @@ class BatchedEnv:
                 _stream_ptr(self.device)))
         return self._result()
 
+    def step_features(self, actions, choices=None, autoreset=False, want_mask: bool = False, out=None):
+        """``step`` fused with the net-input encoding of the new states (``qttt_step_features``):
+        ``info["features"]`` float32[N,18,10] is ``GameState.to_vector`` (mcts.py:67-85) of every env
+        after the move and, with ``want_mask``, ``info["illegal_mask"]`` bool[N,36] is
+        ``nn.Model.get_mask`` (nn.py:44-61) -- written by the launch that steps the games, so the
+        policy/value net input costs no second pass over the state array.  ``out``: the ``info`` of
+        an earlier call, whose feature / mask tensors are reused."""
+        act, fmt = self._check_actions(actions)
+        coin = self._check_choices(choices)
+        flags = self._mode_flags(autoreset)
+        if flags:
+            self.epoch += 1
+        n, dev = self.num_envs, self.device
+        feats = out["features"] if out is not None else torch.empty((n, 18, 10), dtype=torch.float32, device=dev)
+        imask = None
+        if want_mask:
+            imask = out["illegal_mask"] if out is not None and "illegal_mask" in out else \
+                torch.empty((n, 36), dtype=torch.bool, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.qttt_step_features(
+                self.state.data_ptr(), act.data_ptr(), fmt, _lib.ptr(coin), self.seed, self.game_base,
+                self.epoch, flags, self.reward.data_ptr(), self.done.data_ptr(), self.mask.data_ptr(),
+                self.status.data_ptr(), feats.data_ptr(), _lib.ptr(imask), n, _stream_ptr(dev)))
+        res = self._result()
+        res[4]["features"] = feats
+        if imask is not None:
+            res[4]["illegal_mask"] = imask
+        return res
+
     def step_random(self, record: bool = False, autoreset=False, out=None):
         """One ply of the uniform-random policy of ``MCTS._simulate`` (mcts.py:185-198) for
         every env that is not terminated; terminated envs are left untouched
@@ -547,6 +576,18 @@ def to_vector(state):
     return out
 
 
+def get_mask(state):
+    """``nn.Model.get_mask`` (nn.py:44-61) for packed states int32[N,4] -> bool[N,36]: True where
+    the action touches a classical square (the logits the reference's policy head sets to -inf);
+    the complement of ``GameState.action_mask()`` (mcts.py:87-91)."""
+    lib = _lib.lib()
+    n, dev = state.shape[0], state.device
+    out = torch.empty((n, 36), dtype=torch.bool, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.qttt_get_mask(state.data_ptr(), out.data_ptr(), n, _stream_ptr(dev)))
+    return out
+
+
 def render_text(classical, moves, n_moves) -> str:
     """The 3x3-of-3x3 ASCII board of ``displayBoard`` (qtttgym/display.py:4-32) for ONE
     position given as reference-shaped lists: spooky mark of move i in sub-cell i of both its
@@ -593,24 +634,30 @@ def pack_states(classical, moves, n_moves, device="cuda"):
 
 class Env:
     """Single-env adapter with the reference's exact return types (qtttgym/env.py:15-66):
-    Python lists / tuples in ``obs``, a Python float reward (``-0.0`` / ``-1.0``), bools.
+    Python lists / tuples in ``obs``, a Python float reward (``-0.0`` / ``-1.0``), bools, and the
+    reference's ``action_space`` / ``observation_space`` attributes.
 
-    One ``step`` is two kernel launches (``qttt_step`` + ``qttt_observe``, all outputs written
-    into ONE 128-byte device record) and one device->host copy of that record: a single env
-    is latency-bound by construction (tens of microseconds per call); throughput comes from
-    ``BatchedEnv``.
+    One ``step`` is ONE kernel launch (``qttt_env1``): the action travels as kernel arguments, the
+    kernel steps the game, decodes everything ``step`` / ``observ`` / ``turn`` / ``_reward`` report
+    into a 128-byte record and writes it straight into mapped pinned host memory; the host spins
+    on the record's sequence word.  No copy engine, no stream synchronisation: the latency of a
+    step is launch + ~one PCIe write.  Throughput comes from ``BatchedEnv``.
 
     Deviations, all documented in DESIGN.md: ``obs["classical"]`` is a snapshot list, not an
-    alias of live state (Q5); the collapse coin comes from Philox ``(seed, 0, len(moves))``
-    unless ``coin`` is passed to ``step``; gymnasium spaces are not constructed (the reference's
-    ``observation_space`` is wrong anyway, Q6)."""
+    alias of live state (Q5); the collapse coin comes from Philox ``(seed, 0, len(moves), episode)``
+    unless ``coin`` is passed to ``step`` (``seed=None`` draws the seed from the OS like the
+    reference's unseeded ``random``); the classical range of ``observation_space`` is corrected
+    to -1..8 (Q6)."""
 
-    # byte offsets inside the record (state first: 16-byte aligned)
+    # byte offsets inside the record (include/qttt_b200.h: qttt_env1)
     _STATE, _MASK, _REWARD, _DONE, _STATUS, _TURN, _NMOVES = 0, 16, 24, 28, 29, 30, 31
-    _CLASSICAL, _Q1, _Q2, _ROUNDS, _WINNER, _REWARD_P1, _MOVES = 32, 48, 58, 66, 68, 72, 80
+    _CLASSICAL, _Q1, _Q2, _ROUNDS, _WINNER, _REWARD_P1, _MOVES, _SEQ = 32, 48, 58, 66, 68, 72, 80, 124
     _BYTES = 128
 
-    def __init__(self, device="cuda", seed: int = 0):
+    def __init__(self, device="cuda", seed=None):
+        import random as _random
+        import struct
+        from . import spaces as _spaces
         self.lib = _lib.lib()
         dev = torch.device(device)
         if dev.type != "cuda":
@@ -618,82 +665,79 @@ class Env:
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
         self._device = dev
-        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-        self._rec = torch.zeros(self._BYTES, dtype=torch.uint8, device=dev)
+        self.seed = (_random.SystemRandom().getrandbits(64) if seed is None else int(seed)) & 0xFFFFFFFFFFFFFFFF
+        self.epoch = 0
+        self.action_space = _spaces.action_space()              # env.py:19
+        self.observation_space = _spaces.observation_space()    # env.py:20-25 (Q6 corrected)
+        self._state = torch.zeros((1, 4), dtype=torch.int32, device=dev)
         self._host = torch.zeros(self._BYTES, dtype=torch.uint8).pin_memory()
         self._np = self._host.numpy()
-        self._d_act = torch.zeros(4, dtype=torch.int8, device=dev)       # (a, b) and the coin byte
-        self._h_act = torch.zeros(4, dtype=torch.int8).pin_memory()
-        self._h_act_np = self._h_act.numpy()
+        self._seq_view = self._np[self._SEQ:self._SEQ + 4].view("uint32")
+        self._mv = memoryview(self._np).cast("b")
+        self._unpack_f = struct.Struct("<f").unpack_from
+        self._seq = 0
         self._last_status = 0
+        self._first = True
         self.reset()
 
     # -- plumbing ---------------------------------------------------------------------------
-    def _p(self, off):
-        return self._rec.data_ptr() + off
-
-    def _refresh(self):
-        """qttt_observe into the record, one copy to the host, one synchronisation."""
-        st = _stream_ptr(self._device)
+    def _call(self, op, a=0, b=0, coin=-1):
+        self._seq = (self._seq + 1) & 0xFFFFFFFF or 1
+        seq = self._seq
         with torch.cuda.device(self._device):
-            _lib.check(self.lib.qttt_observe(self._p(self._STATE), self._p(self._CLASSICAL), self._p(self._MOVES),
-                                             self._p(self._NMOVES), self._p(self._Q1), self._p(self._Q2),
-                                             self._p(self._TURN), self._p(self._ROUNDS), self._p(self._REWARD_P1),
-                                             self._p(self._WINNER), None, 1, st))
-            self._host.copy_(self._rec, non_blocking=True)
-            torch.cuda.current_stream(self._device).synchronize()
+            _lib.check(self.lib.qttt_env1(self._state.data_ptr(), op, a, b, coin, self.seed, self.epoch,
+                                          self._host.data_ptr(), seq, _stream_ptr(self._device)))
+        view = self._seq_view
+        spins = 0
+        while view[0] != seq:                    # the kernel writes the sequence word last
+            spins += 1
+            if spins > 2_000_000:                # ~seconds: the launch failed asynchronously
+                torch.cuda.current_stream(self._device).synchronize()
+                if view[0] != seq:
+                    raise RuntimeError("qttt_env1: the record never arrived")
 
     def _observation(self):
-        r = self._np
-        i8 = r.view("int8")
-        q1 = i8[self._Q1:self._Q1 + 10].reshape(5, 2).tolist()
-        q2 = i8[self._Q2:self._Q2 + 8].reshape(4, 2).tolist()
-        return {"q_states_p1": [tuple(p) for p in q1 if p[0] >= 0],
-                "q_states_p2": [tuple(p) for p in q2 if p[0] >= 0],
-                "classical": i8[self._CLASSICAL:self._CLASSICAL + 9].tolist(),
-                "turn": int(r[self._TURN])}
+        mv = self._mv
+        q1, q2, cl = self._Q1, self._Q2, self._CLASSICAL
+        return {"q_states_p1": [(mv[q1 + 2 * k], mv[q1 + 2 * k + 1]) for k in range(5) if mv[q1 + 2 * k] >= 0],
+                "q_states_p2": [(mv[q2 + 2 * k], mv[q2 + 2 * k + 1]) for k in range(4) if mv[q2 + 2 * k] >= 0],
+                "classical": list(mv[cl:cl + 9]),
+                "turn": mv[self._TURN]}
 
     # -- the reference API ------------------------------------------------------------------
     def reset(self, *, seed=None, options=None):
-        """env.py:55-57 (seed / options ignored, Q4)."""
-        with torch.cuda.device(self._device):
-            _lib.check(self.lib.qttt_reset(self._p(self._STATE), self._p(self._MASK), 1,
-                                           _stream_ptr(self._device)))
-        self._refresh()
+        """env.py:55-57 (seed / options ignored, Q4).  A new episode: the Philox epoch advances, so
+        its collapses are independent of the previous episode's."""
+        if self._first:
+            self._first = False
+        else:
+            self.epoch += 1
+        self._call(1)
         return self._observation(), {}
 
     def step(self, action, verbose=False, coin=None):
         """env.py:34-53."""
         try:
             a, b = int(action[0]), int(action[1])
+            if not (0 <= a < 9 and 0 <= b < 9):
+                a = b = -1                  # IndexError path of the reference: a swallowed no-op
         except Exception as e:              # env.py:41: anything raised becomes a no-op
             if verbose:
                 print("noop (i.e. invalid) move...", e)
             a = b = -1
-        self._h_act_np[0] = a if -1 <= a <= 127 else -1
-        self._h_act_np[1] = b if -1 <= b <= 127 else -1
-        self._h_act_np[2] = 0 if coin is None else int(coin) & 1
-        with torch.cuda.device(self._device):
-            self._d_act.copy_(self._h_act, non_blocking=True)
-            coin_ptr = None if coin is None else self._d_act.data_ptr() + 2
-            _lib.check(self.lib.qttt_step(self._p(self._STATE), self._d_act.data_ptr(), _lib.ACT_PAIR, coin_ptr,
-                                          self.seed, 0, self._p(self._REWARD), self._p(self._DONE),
-                                          self._p(self._MASK), self._p(self._STATUS), 1,
-                                          _stream_ptr(self._device)))
-        self._refresh()
-        r = self._np
-        self._last_status = int(r[self._STATUS])
+        self._call(0, a, b, -1 if coin is None else int(coin) & 1)
+        mv = self._mv
+        self._last_status = mv[self._STATUS]
         if verbose and self._last_status == 1:
             print("noop (i.e. invalid) move...")
-        reward = float(r[self._REWARD:self._REWARD + 4].view("float32")[0])
-        return self._observation(), reward, bool(r[self._DONE]), False, {}
+        return self._observation(), self._unpack_f(self._np, self._REWARD)[0], bool(mv[self._DONE]), False, {}
 
     def observ(self):
         return self._observation()
 
     def turn(self):
         """env.py:65-66."""
-        return int(self._np[self._NMOVES])
+        return self._mv[self._NMOVES]
 
     def action_mask(self):
         """mcts.py:87-91: bool[36]."""
@@ -709,17 +753,17 @@ class Env:
 
     def _reward(self):
         """env.py:87-112."""
-        return float(self._np[self._REWARD_P1:self._REWARD_P1 + 4].view("float32")[0])
+        return self._unpack_f(self._np, self._REWARD_P1)[0]
 
     def winner(self):
         """0 none / draw, 1 X, 2 O (mcts.py:52-65)."""
-        return int(self._np[self._WINNER])
+        return self._mv[self._WINNER]
 
     @property
     def state(self):
-        """the packed state as an int32[1,4] device tensor (a view of the record)"""
-        return self._rec[:16].view(torch.int32).view(1, 4)
+        """the packed state as an int32[1,4] device tensor"""
+        return self._state
 
 
 __all__ = ["BatchedEnv", "Env", "observe_states", "pack_states", "pack_actions", "unpack_result",
-           "to_vector", "render_text", "PAIRS"]
+           "to_vector", "get_mask", "render_text", "PAIRS"]

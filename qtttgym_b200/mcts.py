@@ -37,12 +37,22 @@ class BatchedMCTS:
         self.pool = self.meta = None
         self.n_roots = 0
 
-    def reset(self, states, total_rollouts: int | None = None):
-        """mcts.py:139-164 for packed roots int32[R,4].  ``total_rollouts`` sizes the node pool
-        (default: ``rollouts`` per contemplate x (max_syncs + 1))."""
+    def reset(self, states, total_rollouts: int | None = None, capacity: int | None = None):
+        """mcts.py:139-164 for packed roots int32[R,4].
+
+        The node pool holds ``capacity`` nodes per root.  A rollout adds at most 2 nodes, and
+        ``sync`` gives the pruned subtrees back to the pool (``MCTS._prune``, mcts.py:222-231),
+        so what has to fit is the LIVE tree: the subtree kept by the last sync plus the rollouts
+        since.  Default: ``total_rollouts`` (when given: the whole budget of a search without
+        syncs) or three contemplates' worth of rollouts, + 2 per sync.  If a tree ever outgrows
+        its pool it stops growing and ``errors()`` reports bit 1; ``live_counts()`` /
+        ``peak_counts()`` show the occupancy."""
         self.n_roots = int(states.shape[0])
-        budget = total_rollouts if total_rollouts is not None else self.num_rollouts * (self.max_syncs + 1)
-        self.capacity = 1 + 2 * int(budget) + 2 * self.max_syncs
+        if capacity is not None:
+            self.capacity = int(capacity)
+        else:
+            budget = total_rollouts if total_rollouts is not None else 3 * self.num_rollouts
+            self.capacity = 1 + 2 * int(budget) + 2 * self.max_syncs
         need = self.n_roots * self.capacity * self.node_bytes
         if self.pool is None or self.pool.numel() < need:
             self.pool = torch.empty(need, dtype=torch.uint8, device=self.device)
@@ -94,4 +104,13 @@ class BatchedMCTS:
         return self.meta[:, 3]
 
     def node_counts(self):
+        """nodes ever taken from the fresh end of each root's pool (high-water mark)"""
         return self.meta[:, 1]
+
+    def live_counts(self):
+        """nodes alive in each tree now (taken minus reclaimed by ``sync``)"""
+        return self.meta[:, 1] - self.meta[:, 5]
+
+    def peak_counts(self):
+        """most nodes alive at once in each tree since ``reset``"""
+        return self.meta[:, 6]

@@ -36,8 +36,9 @@ class EmuBackend:
             out_dir = os.path.join(HERE, "hostemu", "_build")
             os.makedirs(out_dir, exist_ok=True)
             out = os.path.join(out_dir, "libqttt_hostemu.so")
-            if (not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src),
-                                                                        os.path.getmtime(core))):
+            mcts = os.path.join(ROOT, "qtttgym_b200", "csrc", "qttt_mcts.cuh")
+            if (not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(core),
+                                                                        os.path.getmtime(mcts))):
                 subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++",
                                 "-o", out, src], check=True)
             cls._lib = C.CDLL(out)
@@ -84,6 +85,12 @@ class EmuMCTS:
 
     def errors(self):
         return self.meta[:, 3].copy()
+
+    def taken(self):
+        return self.meta[:, 1].copy()
+
+    def live(self):
+        return (self.meta[:, 1] - self.meta[:, 5]).copy()
 
 
 class EmuGames:
@@ -169,6 +176,17 @@ class EmuGames:
         self.lib.emu_features(_p(self.state), _p(out), C.c_int64(self.n))
         return out
 
+    def get_mask(self):
+        out = np.empty((self.n, 36), np.uint8)
+        self.lib.emu_get_mask(_p(self.state), _p(out), C.c_int64(self.n))
+        return out.astype(bool)
+
+    def step_features(self, actions, coins=None, epoch=0, flags=0):
+        """host emulation: the step, then the two encoders on the new state"""
+        o = self.step_ex(actions, coins, epoch=epoch, flags=flags)
+        o["features"], o["illegal_mask"] = self.features(), self.get_mask()
+        return o
+
     def load(self, classical, moves, n_moves):
         cl = np.ascontiguousarray(classical, np.int8)
         mv = np.ascontiguousarray(moves, np.int8)
@@ -244,6 +262,12 @@ class CudaMCTS:
 
     def errors(self):
         return self.m.errors().cpu().numpy()
+
+    def taken(self):
+        return self.m.node_counts().cpu().numpy()
+
+    def live(self):
+        return self.m.live_counts().cpu().numpy()
 
 
 class CudaGames:
@@ -331,6 +355,22 @@ class CudaGames:
 
     def features(self):
         return self.Q.to_vector(self.env.state).cpu().numpy()
+
+    def get_mask(self):
+        return self.Q.get_mask(self.env.state).cpu().numpy()
+
+    def step_features(self, actions, coins=None, epoch=0, flags=0):
+        """the fused kernel: qttt_step_features"""
+        t = self.torch
+        env = self.env
+        ac = t.from_numpy(np.ascontiguousarray(actions, np.uint8)).cuda()
+        co = None if coins is None else t.from_numpy(np.ascontiguousarray(coins, np.uint8)).cuda()
+        env.epoch = epoch - (1 if flags else 0)
+        res = env.step_features(ac, co, autoreset=self._AUTORESET[flags], want_mask=True)
+        o = self._outs(res)
+        o["features"] = res[4]["features"].cpu().numpy()
+        o["illegal_mask"] = res[4]["illegal_mask"].cpu().numpy()
+        return o
 
     def load(self, classical, moves, n_moves):
         self.env.load_positions(np.asarray(classical, np.int8), np.asarray(moves, np.int8),

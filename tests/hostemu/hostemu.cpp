@@ -114,6 +114,15 @@ int emu_features(const State* state, float* out, int64_t n) {
     return 0;
 }
 
+int emu_get_mask(const State* state, uint8_t* illegal_mask, int64_t n) {
+    const Luts L = luts();
+    for (int64_t i = 0; i < n; ++i) {
+        const uint64_t legal = L.legal[~classical(state[i]) & M9];
+        for (int k = 0; k < 36; ++k) illegal_mask[36 * i + k] = (uint8_t)(((legal >> k) & 1ull) ^ 1ull);
+    }
+    return 0;
+}
+
 int emu_pack(State* state, const int8_t* classical_in, const int8_t* moves, const uint8_t* nmoves,
              int64_t n) {
     for (int64_t i = 0; i < n; ++i) state[i] = pack_game(classical_in, moves, nmoves, i);

@@ -518,6 +518,58 @@ def check_golden_features(backend):
     assert ((got != 0) == (want != 0)).all()
 
 
+def check_golden_getmask(backend):
+    """nn.Model.get_mask (nn.py:44-61) recorded from the live reference (oracle/make_golden_getmask.py),
+    next to the reference's own GameState.action_mask() of the same nodes."""
+    recs = load_golden("getmask_v1.json.gz")
+    n = len(recs)
+    classical = np.array([r["board"] for r in recs], np.int8)
+    moves = np.full((n, 9, 2), -1, np.int8)
+    n_moves = np.array([len(r["moves"]) for r in recs], np.uint8)
+    for i, r in enumerate(recs):
+        for m in r["moves"]:
+            moves[i, m[2]] = m[:2]
+    games = backend.games(n).load(classical, moves, n_moves)
+    got = games.get_mask()
+    want = np.array([r["get_mask"] for r in recs], bool)
+    assert got.shape == (n, 36) and np.array_equal(got, want)
+    legal = games.observe()["mask_bool"].astype(bool)
+    assert np.array_equal(legal, np.array([r["action_mask"] for r in recs], bool))
+
+
+def check_step_features(backend, n_games=3000, seed=41):
+    """qttt_step_features == qttt_step followed by to_vector / get_mask of the new state, on a
+    desynchronised (auto-resetting) batch with some illegal actions; the step outputs against the
+    oracle, the encodings against the stand-alone encoders of the same backend (which the golden
+    tests pin to the reference)."""
+    rng = np.random.default_rng(seed)
+    ref = CO.Games(n_games)
+    fresh = CO.Games(1).raw[0].copy()
+    full_mask = np.uint64((1 << 36) - 1)
+    dut = backend.games(n_games)
+    mask = np.full(n_games, full_mask, np.uint64)
+    over = np.zeros(n_games, bool)
+    for t in range(24):
+        legal = expand_mask(np.where(over, full_mask, mask))
+        k = (rng.random((n_games, 36)) * legal).argmax(1).astype(np.uint8)
+        bad = rng.random(n_games) < 0.05
+        k[bad] = rng.integers(0, 64, int(bad.sum())).astype(np.uint8)
+        coins = rng.integers(0, 2, n_games).astype(np.uint8)
+        ref.raw[over] = fresh
+        pairs = np.full((n_games, 2), -1, np.int8)
+        pairs[k < 36] = PAIRS[k[k < 36]]
+        r = ref.step(pairs, coins)
+        o = dut.step_features(k, coins, epoch=t + 1, flags=2)
+        where = f"{backend.name} step_features step {t}"
+        assert np.array_equal(o["reward"].view(np.uint32), r["reward"].view(np.uint32)), where
+        assert np.array_equal(o["done"], r["done"]) and np.array_equal(o["mask"], r["mask"]), where
+        assert_same_obs(dut.observe(), ref.observe(), where)
+        assert np.array_equal(o["features"], dut.features()), where
+        assert np.array_equal(o["illegal_mask"], dut.get_mask()), where
+        assert np.array_equal(o["illegal_mask"], ~expand_mask(r["mask"]).astype(bool)), where
+        mask, over = r["mask"], r["done"].astype(bool)
+
+
 def _pack_oracle_games(backend, games):
     """oracle Game objects -> packed states via the backend's pack."""
     n = len(games)
@@ -541,8 +593,11 @@ def check_golden_mcts_search(backend):
         budget = sum(st["rollouts"] for st in case["stages"])
         s = backend.mcts(_pack_oracle_games(backend, [g]), case["num_simulations"], case["seed"],
                          case["root_index"], budget)
+        created, syncs = 1, 0
         for st in case["stages"]:
+            before = int(s.live()[0])
             s.contemplate(st["rollouts"])
+            created += int(s.live()[0]) - before
             n, q, ntot, ch = s.stats()
             assert n[0].tolist() == st["N"], case["root_index"]
             assert q[0].tolist() == st["Q"], case["root_index"]          # float64, exact
@@ -552,8 +607,16 @@ def check_golden_mcts_search(backend):
             act, c = st["move"]
             a, b = O.PAIRS[act]
             g.place(a, b, lambda: c)
+            before = int(s.live()[0])
             s.sync(np.array([act], np.uint8), _pack_oracle_games(backend, [g]))
+            syncs += 1
+            # MCTS._prune (mcts.py:222-231, 330-337): the old root and the siblings' subtrees are gone
+            assert int(s.live()[0]) < before, case["root_index"]
         assert int(s.errors()[0]) == 0
+        # nodes reclaimed by sync are reused: the pool's high-water mark stays below the number of
+        # nodes ever created (and the statistics above stayed bit-identical all the same)
+        if syncs >= 2:
+            assert int(s.taken()[0]) < created, (case["root_index"], int(s.taken()[0]), created)
 
 
 def check_mcts_batch_vs_oracle(backend, n_roots=24, rollouts=80, sims=8, seed=4242, root_base=100):

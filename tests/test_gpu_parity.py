@@ -152,6 +152,78 @@ def test_single_env_adapter_reference_types(cuda):
             assert env.turn() == len(rec["moves"]) and env._reward() == rec["reward_p1"]
 
 
+def test_reference_user_code_runs_unchanged(cuda):
+    """A loop written against qtttgym.Env -- including env.action_space / observation_space --
+    runs unchanged on the drop-in adapter, and two Env instances do not share collapse coins."""
+    import qtttgym_b200 as Q
+
+    def user_code(env, episodes):
+        total, boards = 0, []
+        for _ in range(episodes):
+            obs, info = env.reset()
+            assert env.observation_space.contains({k: (np.asarray(v, np.int32) if k == "classical" else v)
+                                                   for k, v in obs.items()})
+            terminated = False
+            while not terminated:
+                action = env.action_space.sample()
+                assert env.action_space.contains(action) and action in env.action_space
+                obs, r, terminated, truncated, info = env.step(action)
+                assert isinstance(obs["classical"], list) and isinstance(r, float) and not truncated
+                total += 1
+            boards.append(tuple(obs["classical"]))
+        return total, boards
+
+    env = Q.Env()
+    steps, _ = user_code(env, 20)
+    assert steps >= 100
+    assert len(env.action_space) == 2 and env.action_space[0].n == 9
+    # same actions, consecutive episodes and independent instances: the collapses differ
+    outcomes = set()
+    for inst in range(6):
+        e = Q.Env()
+        for _ in range(2):
+            e.reset()
+            for a in [(0, 1), (1, 0), (2, 3), (3, 2), (4, 5), (5, 4)]:
+                obs, *_ = e.step(a)
+            outcomes.add(tuple(obs["classical"]))
+    assert len(outcomes) > 3
+    # a fixed seed reproduces the first episode
+    a, b = Q.Env(seed=5), Q.Env(seed=5)
+    for mv in [(0, 1), (1, 0), (2, 3), (3, 2)]:
+        assert a.step(mv)[0] == b.step(mv)[0]
+
+
+def test_vector_env_next_step_autoreset(cuda):
+    """gymnasium.vector conventions: spaces, (obs, info) / 5-tuple shapes, next-step autoreset."""
+    import torch
+    import qtttgym_b200 as Q
+    n = 4096
+    venv = Q.VectorEnv(n, seed=3, reward="p1")
+    assert venv.num_envs == n and venv.single_action_space.contains((0, 8))
+    obs, info = venv.reset(seed=1)
+    assert obs["classical"].shape == (n, 9) and obs["q_states_p1"].shape == (n, 5, 2) and obs["turn"].shape == (n,)
+    assert bool((obs["classical"] == -1).all())
+    episodes = torch.zeros(n, dtype=torch.int64, device="cuda")
+    prev_term = torch.zeros(n, dtype=torch.bool, device="cuda")
+    returns = torch.zeros(3, dtype=torch.int64, device="cuda")
+    for t in range(60):
+        actions = venv.sample_actions()
+        obs, reward, terminated, truncated, info = venv.step(actions)
+        # envs that terminated at the previous step were reset by this call: fresh board, no reward
+        assert bool(((obs["classical"][prev_term] == -1).all(1)).all())
+        assert bool((obs["turn"][prev_term] == 0).all()) and not bool(terminated[prev_term].any())
+        assert bool((reward[prev_term] == 0).all()) and bool(info["reset"][prev_term].all())
+        assert not bool(info["reset"][~prev_term].any()) and not bool(truncated.any())
+        assert not bool(info["invalid"][~prev_term].any())              # sampled actions are legal
+        episodes += terminated
+        returns += torch.bincount((reward[terminated] + 1).long(), minlength=3)
+        prev_term = terminated.clone()
+    assert int(episodes.min()) >= 4                                     # every env played several episodes
+    tot = int(returns.sum())
+    x, o, d = int(returns[2]) / tot, int(returns[0]) / tot, int(returns[1]) / tot
+    assert abs(x - 0.5816) < 0.02 and abs(o - 0.2914) < 0.02 and abs(d - 0.1271) < 0.02   # SURVEY 8(d) population
+
+
 def test_qeval_plugin_seam(cuda):
     """QEvalB200.eval is a drop-in for QEvalClassic.eval (board.py:51 -> qeval.py:5)."""
     import qtttgym_b200 as Q
@@ -326,6 +398,16 @@ def test_episode_cuda_graph(cuda):
 
 def test_golden_features(cuda):
     S.check_golden_features(cuda)
+
+
+def test_golden_getmask(cuda):
+    S.check_golden_getmask(cuda)
+
+
+@pytest.mark.parametrize("n", [1, 33, 5000, 70_001])
+def test_fused_step_features(cuda, n):
+    """qttt_step_features: ragged sizes (partial warps, many blocks)"""
+    S.check_step_features(cuda, n)
 
 
 def test_features_ragged_and_large(cuda):

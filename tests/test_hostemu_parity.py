@@ -100,3 +100,11 @@ def test_autoreset_random(emu):
 
 def test_epoch_coin(emu):
     S.check_epoch_coin(emu, 600)
+
+
+def test_golden_getmask(emu):
+    S.check_golden_getmask(emu)
+
+
+def test_step_features(emu):
+    S.check_step_features(emu, 1000)
