@@ -582,10 +582,20 @@ def run_b200(args):
 
     def roll():
         Q.rollout_eval(roots, 256, seed, out=box["r"])
-    ms = timed(roll, 50)
+    ms_call = timed(roll, 50)
     rsteps = int(box["r"][2].item())
+    rgraph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(rgraph):
+        for _ in range(10):
+            roll()
+    ms = timed(rgraph.replay, 20) / 10
     extra["config4_rollout_1024x256"] = {"playouts_per_s": 1024 * 256 / (ms * 1e-3) * world,
-                                         "env_steps_per_s": rsteps / (ms * 1e-3) * world, "ms": ms}
+                                         "env_steps_per_s": rsteps / (ms * 1e-3) * world, "ms": ms,
+                                         "ms_per_python_call": ms_call,
+                                         "env_steps_per_s_python_calls": rsteps / (ms_call * 1e-3) * world,
+                                         "note": "device time per launch (10 launches + their counter resets per "
+                                                 "CUDA-graph replay); one launch is 20 us of GPU work, so bare "
+                                                 "Python calls (ms_per_python_call) are launch-latency bound"}
     # config 1 through the drop-in single-env adapter (qtttgym_b200.Env): the reference's own loop
     if rank == 0:
         import random as _random

@@ -518,6 +518,53 @@ QTTT_HD uint32_t commit_outcome(State& out, uint32_t xa, uint32_t ya, uint32_t z
     return Cn;
 }
 
+// Board.make_move for a game whose len(moves) is the compile-time constant N (playouts that walk
+// the plies of a game in order, all lanes of a warp at the same ply): no table row, no warp vote,
+// no switch -- the slot offsets and plane patterns of move N are immediates and sweep<N> is called
+// directly.  `enew` must be a legal pair of this state or 0 (no-op); C = classical(s).
+template <int N>
+QTTT_HD StepResult step_fixed(State& s, uint32_t enew, uint32_t coin, uint32_t C) {
+    static_assert(N >= 0 && N <= 8, "a move needs a free slot");
+    constexpr uint32_t v = N + 1;
+    constexpr uint32_t kp = (v & 1u) | ((v & 2u) << 8) | ((v & 4u) << 16);
+    const uint32_t x = s.x, y = s.y, z = s.z, w = s.w;
+    const uint32_t lo = enew & (0u - enew);
+    const uint32_t t = coin ? (enew ^ lo) : lo;
+    const uint32_t o = enew ^ t;
+    uint32_t R = t, W = t * kp, A3 = 0u;
+    sweep<N, false>(x, y, z, R, W, A3, nullptr, N == 8 ? (~C & M9) : ~0u);
+    const uint32_t colf = (R & o) != 0u ? 1u : 0u;                         // board.py:42
+    uint32_t wn = w + W * colf;
+    uint32_t Cn = C | (R * colf);
+    constexpr uint32_t sh = 9u * (N % 3);
+    uint32_t xn = x + (N < 3 ? (enew << sh) : 0u);                         // board.py:19
+    uint32_t yn = y + ((N >= 3 && N < 6) ? (enew << sh) : 0u);
+    uint32_t zn = z + (N >= 6 ? (enew << sh) : 0u);
+    uint32_t inc = enew ? 1u : 0u;
+    if (N >= 7) {                                                          // plane 3 and the autofill
+        A3 += t;
+        A3 *= colf;
+        const uint32_t fr = ~Cn & M9;
+        const bool fill = (colf != 0u) & (popc32(fr) == 1);                // board.py:21-25
+        const uint32_t fs = fill ? fr : 0u;
+        zn += fs << 18;
+        wn += fs;
+        A3 += fs;
+        Cn |= fs;
+        inc += fill ? 1u : 0u;
+        yn += A3 << 27;
+        zn += (A3 >> 5) << 27;
+    }
+    xn += inc << 27;
+    s.x = xn; s.y = yn; s.z = zn; s.w = wn;
+    StepResult out;
+    out.illegal = enew ? 0u : 1u;
+    out.collapsed = colf;
+    out.classical = Cn;
+    out.n = (uint32_t)N + inc;
+    return out;
+}
+
 // Both measurement outcomes of one move in ONE sweep (board.py:42-56 with qeval.py:35 taking
 // either value; what MCTS._step enumerates by rejection sampling, mcts.py:233-267).  The two
 // outcomes are the rootings of the same tree at the closing move's two squares; sweep2 grows
@@ -804,11 +851,32 @@ QTTT_HD uint32_t finished_winner(const State& s, const Luts& L, bool& terminal) 
 
 // One ply of MCTS._simulate (mcts.py:188-196): action ~ U(legal), coin ~ U{0,1}.
 // Needs the policy tables (kLutPolicyBytes staged).
+template <int N>
+QTTT_HD StepResult playout_ply_fixed(State& s, uint32_t C, uint64_t seed, uint64_t game, uint32_t domain,
+                                     const Luts& L, DrawCache& cache) {
+    uint32_t word, coin;
+    ply_draw_cached(seed, game, (uint32_t)N, domain, cache, word, coin);
+    return step_fixed<N>(s, policy_edge(~C & M9, word, L), coin, C);
+}
+// The same for a run-time len(moves): one jump to the specialised ply (uniform across a warp whose
+// lanes play from the same root; correct, if slower, when it is not).
 QTTT_HD StepResult playout_ply(State& s, uint32_t C, uint64_t seed, uint64_t game, uint32_t domain,
                                const Luts& L, DrawCache& cache) {
-    uint32_t word, coin;
-    ply_draw_cached(seed, game, n_moves(s), domain, cache, word, coin);
-    return step_core<false, true>(s, policy_edge(~C & M9, word, L), coin, L, nullptr, C);
+    switch (n_moves(s)) {
+        case 0: return playout_ply_fixed<0>(s, C, seed, game, domain, L, cache);
+        case 1: return playout_ply_fixed<1>(s, C, seed, game, domain, L, cache);
+        case 2: return playout_ply_fixed<2>(s, C, seed, game, domain, L, cache);
+        case 3: return playout_ply_fixed<3>(s, C, seed, game, domain, L, cache);
+        case 4: return playout_ply_fixed<4>(s, C, seed, game, domain, L, cache);
+        case 5: return playout_ply_fixed<5>(s, C, seed, game, domain, L, cache);
+        case 6: return playout_ply_fixed<6>(s, C, seed, game, domain, L, cache);
+        case 7: return playout_ply_fixed<7>(s, C, seed, game, domain, L, cache);
+        case 8: return playout_ply_fixed<8>(s, C, seed, game, domain, L, cache);
+        default: break;
+    }
+    StepResult r;                       // 9 entries in moves: nothing can be played
+    r.illegal = 1u; r.collapsed = 0u; r.classical = C; r.n = n_moves(s);
+    return r;
 }
 
 QTTT_HD int board_value(uint32_t P0, uint32_t P1, uint32_t P2, uint32_t P3, int sq) {

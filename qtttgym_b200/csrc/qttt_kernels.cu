@@ -654,9 +654,27 @@ k_rollout(const qttt_state* __restrict__ roots, int64_t n_roots, int32_t n_rollo
 }
 
 // K5: self-play sweep from the empty board, entirely in registers.  The 32 games of a warp are
-// played in lock-step (ply p of all of them together), so len(moves) is uniform across the
-// active lanes and the transition's switch on it never diverges; lanes whose game ended
-// earlier (mean 8.29 of 9 plies) idle until the warp's last game ends.
+// played in lock-step (ply p of all of them together), so len(moves) == p in every active lane:
+// the nine plies are nine compile-time specialisations (playout_ply_fixed<p>: immediates instead
+// of table rows, sweep<p> called directly, the even / odd halves of the shared Philox block
+// resolved at compile time).  Lanes whose game ended earlier (mean 8.29 of 9 plies) idle until
+// the warp's last game ends.
+template <int PLY>
+__device__ __forceinline__ void sweep_from_ply(State& s, uint32_t& C, bool& active, uint32_t& len, uint32_t& co,
+                                               uint64_t seed, uint64_t g, const Luts& L, DrawCache& cache) {
+    if constexpr (PLY < 9) {
+        if (!__any_sync(0xFFFFFFFFu, active)) return;
+        if (active) {
+            const StepResult r = playout_ply_fixed<PLY>(s, C, seed, g, 0u, L, cache);
+            C = r.classical;
+            co += r.collapsed;
+            len = PLY + 1;
+            active = !((any_line(s, C, L) != 0u) | (r.n >= 9u));              // mcts.py:52-65
+        }
+        sweep_from_ply<PLY + 1>(s, C, active, len, co, seed, g, L, cache);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, unsigned long long* __restrict__ stats) {
     __shared__ __align__(16) uint8_t smem[kLutPolicyBytes];
@@ -677,17 +695,7 @@ k_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, unsigned long long* __r
         DrawCache cache = empty_draw_cache();
         const bool mine = active;
         games += active;
-#pragma unroll 1
-        for (uint32_t ply = 0; ply < 9u; ++ply) {
-            if (!__any_sync(0xFFFFFFFFu, active)) break;
-            if (active) {
-                const StepResult r = playout_ply(s, C, seed, (uint64_t)g, 0u, L, cache);
-                C = r.classical;
-                co += r.collapsed;
-                len = ply + 1u;
-                active = !((any_line(s, C, L) != 0u) | (r.n >= 9u));          // mcts.py:52-65
-            }
-        }
+        sweep_from_ply<0>(s, C, active, len, co, seed, (uint64_t)g, L, cache);
         // every lane's game is over: who has the earlier line (mcts.py:52-65), once, undiverged
         bool t2;
         const uint32_t w = finished_winner(s, L, t2);

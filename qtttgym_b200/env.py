@@ -678,21 +678,33 @@ class Env:
         self._seq = 0
         self._last_status = 0
         self._first = True
+        # everything a call needs, resolved once: a step is latency-bound, and looking these up
+        # through torch on every call costs more than the kernel does
+        self._fn = self.lib.qttt_env1
+        self._state_ptr = self._state.data_ptr()
+        self._host_ptr = self._host.data_ptr()
+        self._dev_index = dev.index
+        self._stream = _stream_ptr(dev)          # the stream that is current now (the default stream)
         self.reset()
 
     # -- plumbing ---------------------------------------------------------------------------
     def _call(self, op, a=0, b=0, coin=-1):
-        self._seq = (self._seq + 1) & 0xFFFFFFFF or 1
-        seq = self._seq
-        with torch.cuda.device(self._device):
-            _lib.check(self.lib.qttt_env1(self._state.data_ptr(), op, a, b, coin, self.seed, self.epoch,
-                                          self._host.data_ptr(), seq, _stream_ptr(self._device)))
+        seq = self._seq = (self._seq % 0xFFFFFFFE) + 1
+        if torch.cuda.current_device() == self._dev_index:
+            rc = self._fn(self._state_ptr, op, a, b, coin, self.seed, self.epoch, self._host_ptr, seq, self._stream)
+        else:
+            with torch.cuda.device(self._device):
+                rc = self._fn(self._state_ptr, op, a, b, coin, self.seed, self.epoch, self._host_ptr, seq,
+                              self._stream)
+        if rc:
+            _lib.check(rc)
+        _lib.LAUNCHES += 1
         view = self._seq_view
         spins = 0
         while view[0] != seq:                    # the kernel writes the sequence word last
             spins += 1
-            if spins > 2_000_000:                # ~seconds: the launch failed asynchronously
-                torch.cuda.current_stream(self._device).synchronize()
+            if spins > 5_000_000:                # ~seconds: the launch failed asynchronously
+                torch.cuda.synchronize(self._device)
                 if view[0] != seq:
                     raise RuntimeError("qttt_env1: the record never arrived")
 
