@@ -471,7 +471,9 @@ def run_b200(args):
         return total_steps_pass * e2e_K / (ms * 1e-3), ms / e2e_K
 
     def link_floor_ms(b_in, b_out):
-        return 1e3 * max(b_in / (ceiling["h2d_concurrent_gbs"] * 1e9), b_out / (ceiling["d2h_concurrent_gbs"] * 1e9))
+        # the traffic is lopsided (1 B in, 2 or 18 B out per env-step), so each direction is held against
+        # what the link gave that direction ALONE: the most favourable ceiling, frac <= 1
+        return 1e3 * max(b_in / (ceiling["h2d_alone_gbs"] * 1e9), b_out / (ceiling["d2h_alone_gbs"] * 1e9))
 
     variants = {}
     for name, kw, b_in, b_out in (
@@ -506,8 +508,10 @@ def run_b200(args):
                         "ms_per_pass": variants[best_obs]["ms_per_pass"],
                         "h2d_bytes_per_pass": 1 * E * PLIES, "d2h_bytes_per_pass": 18 * E * PLIES},
            "variants": variants, "pcie_ceiling": ceiling,
-           "note": "frac_of_link_ceiling = (bytes that must cross the link / measured pinned-copy bandwidth of the same "
-                   "direction with both directions busy) / measured time"}
+           "note": "frac_of_link_ceiling = (bytes that must cross the link / pinned cudaMemcpyAsync bandwidth measured "
+                   "in this run for that direction alone, all ranks copying at once) / measured time.  With several "
+                   "ranks the per-rank ceiling itself drops (one host, one NUMA node feeds every GPU): that, not "
+                   "the kernels, is what bounds multi-GPU e2e"}
     del h_obs
 
     # ---- extras: the other configs of BASELINE.json

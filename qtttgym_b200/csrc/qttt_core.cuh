@@ -84,18 +84,22 @@ QTTT_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 
 // Largest value among the lanes of the warp that are executing this call together (the value
 // itself on the host).
+// kFullWarp: the caller guarantees that all 32 lanes execute the call together (no __activemask
+// query needed).
+template <bool kFullWarp = false>
 QTTT_HD uint32_t warp_max_u32(uint32_t v) {
 #if defined(__CUDA_ARCH__)
-    return __reduce_max_sync(__activemask(), v);
+    return __reduce_max_sync(kFullWarp ? 0xFFFFFFFFu : __activemask(), v);
 #else
     return v;
 #endif
 }
 
 // true if the predicate holds in any lane executing this call together (the value on the host)
+template <bool kFullWarp = false>
 QTTT_HD bool warp_any(bool p) {
 #if defined(__CUDA_ARCH__)
-    return __any_sync(__activemask(), p) != 0;
+    return __any_sync(kFullWarp ? 0xFFFFFFFFu : __activemask(), p) != 0;
 #else
     return p;
 #endif
@@ -403,7 +407,7 @@ QTTT_HD void sweep2(uint32_t x, uint32_t y, uint32_t z, uint32_t& Ra, uint32_t& 
 //
 // kKnownC: the caller already holds the classical set of `s` (playouts carry it from the
 // previous step's result) and passes it as `known_c`.
-template <bool kTargets = false, bool kKnownC = false>
+template <bool kTargets = false, bool kKnownC = false, bool kFullWarp = false>
 QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, const Luts& L, uint32_t* tgt = nullptr,
                              uint32_t known_c = 0u) {
     const uint32_t x = s.x, y = s.y, z = s.z, w = s.w;
@@ -430,7 +434,7 @@ QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, const Luts&
     // slots hold E = 0 and can never touch R, which makes sweep<N> exact for every n <= N.  A
     // batch stepped in lock-step pays exactly its own n; a desynchronised batch (envs at
     // different plies in one warp) pays one sweep<max n> instead of one case per distinct n.
-    switch (warp_max_u32(legal ? n : 0u)) {
+    switch (warp_max_u32<kFullWarp>(legal ? n : 0u)) {
         case 1: sweep<1, kTargets>(x, y, z, R, W, A3, T); break;
         case 2: sweep<2, kTargets>(x, y, z, R, W, A3, T); break;
         case 3: sweep<3, kTargets>(x, y, z, R, W, A3, T); break;
@@ -458,7 +462,7 @@ QTTT_HD StepResult step_core(State& s, uint32_t enew, uint32_t coin, const Luts&
 
     // Plane 3 (move indices 7 and 8) and the autofill exist only once 7 moves are on the board:
     // a branch on the WARP's largest len(moves), so earlier plies do not pay for them.
-    if (warp_any(n >= 7u)) {
+    if (warp_any<kFullWarp>(n >= 7u)) {
         A3 += (n >= 7u) ? t : 0u;       // the closing move itself: v = n + 1 in {8, 9}
         A3 *= colf;
         // Autofill (board.py:21-25): one free square left.  Only reachable right after the
@@ -795,7 +799,7 @@ struct StepOut {
     uint32_t action, coin; // the random policy's choice (kRandom), 255 / 0 when nothing was played
 };
 
-template <bool kRandom, int kMode>
+template <bool kRandom, int kMode, bool kFullWarp = false>
 QTTT_HD StepOut step_game(State& s, uint32_t enew, bool have_coin, uint32_t coin, uint64_t seed, uint64_t game,
                           uint32_t dword, const Luts& L) {
     StepOut o;
@@ -830,7 +834,7 @@ QTTT_HD StepOut step_game(State& s, uint32_t enew, bool have_coin, uint32_t coin
         }
         if (kMode == kStepAutoNext && was_reset) enew = 0u;
     }
-    const StepResult r = step_core(s, enew, coin, L);
+    const StepResult r = step_core<false, false, kFullWarp>(s, enew, coin, L);
     o.win = any_line(s, r.classical, L);
     o.done = (o.win != 0u) | (r.n > 8u);
     o.classical = r.classical;

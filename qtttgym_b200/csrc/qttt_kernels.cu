@@ -131,14 +131,18 @@ __global__ void __launch_bounds__(kThreads, kPrefetch ? 6 : 8) k_step(const Step
         }
         return in;
     };
+    // Lanes past the end of the batch run the step on an empty game with an illegal action and
+    // store nothing, so that all 32 lanes of every warp execute step_game together (full-mask
+    // warp votes, no __activemask query).
     auto run = [&](uint32_t i, const StepIn& in) {
-        if (i >= a.n) return;
+        const bool valid = i < a.n;
         State s{in.sv.x, in.sv.y, in.sv.z, in.sv.w};
         uint32_t enew = 0u;
         if (!kRandom)
             enew = kFmt == QTTT_ACT_INDEX ? (uint32_t)L.pair[in.act] : pair_to_edge(in.act & 255u, in.act >> 8);
-        const StepOut o = step_game<kRandom, kMode>(s, enew, kFull || a.coin != nullptr, in.coin & 1u, a.seed,
-                                                    a.game_base + (uint64_t)i, a.dword, L);
+        const StepOut o = step_game<kRandom, kMode, true>(s, enew, kFull || a.coin != nullptr, in.coin & 1u, a.seed,
+                                                          a.game_base + (uint64_t)i, a.dword, L);
+        if (!valid) return;
         if (o.write_state) *reinterpret_cast<uint4*>(a.state + i) = make_uint4(s.x, s.y, s.z, s.w);
         // the reward is stored through an integer pointer: its two values differ only in bit
         // patterns (-0.0f / -1.0f), and a float-typed select gets "simplified" by the compiler
