@@ -59,6 +59,18 @@ def main():
         env.step(actions[ply], coins[ply])
     mid = env.state.clone()
     qa = torch.where(actions[4] < 36, actions[4], torch.zeros_like(actions[4]))
+    if want("desync"):
+        mix = Q.BatchedEnv(E, device=dev, seed=seed + 1)
+        for _ in range(31):
+            mix.step_random(autoreset=True)
+        da = torch.empty(E, dtype=torch.uint8, device=dev)
+        dc = torch.empty(E, dtype=torch.uint8, device=dev)
+        start = mix.state.clone()
+        mix.step_random(autoreset=True, out=(da, dc))
+        for rep in range(2):
+            mix.state.copy_(start)
+            timed(f"k_step desync autoreset (rep {rep})", lambda: mix.step(da, dc, autoreset=True))
+        del mix, start
     if want("packed"):
         ac = Q.pack_actions(actions[4], coins[4])
         res = torch.empty(E, dtype=torch.int16, device=dev)
@@ -68,6 +80,15 @@ def main():
             Q._lib.check(env.lib.qttt_step_packed(st.data_ptr(), ac.data_ptr(), res.data_ptr(), E,
                                                   torch.cuda.current_stream().cuda_stream))
         timed("k_step_packed ply 4", packed)
+        timed("k_step_packed ply 4 (again)", packed)
+        h_ac = ac.cpu().pin_memory()
+        h_res = torch.empty(E, dtype=torch.int16).pin_memory()
+
+        def mapped():
+            Q._lib.check(env.lib.qttt_step_packed_mapped(st.data_ptr(), h_ac.data_ptr(), h_res.data_ptr(), None, E,
+                                                         torch.cuda.current_stream().cuda_stream))
+        timed("k_step_packed_zc ply 4 (mapped pinned host buffers)", mapped)
+        timed("k_step_packed_zc ply 4 (again)", mapped)
     if want("observe"):
         buf = Q.observe_states(mid, extras=True)
         timed("k_observe all outputs", lambda: Q.observe_states(mid, extras=True, out=buf))
@@ -76,6 +97,16 @@ def main():
         del buf, buf2
     if want("features"):
         timed("k_features 2^20", lambda: Q.to_vector(mid[:1 << 20]))
+        timed("k_features 2^20 (again)", lambda: Q.to_vector(mid[:1 << 20]))
+        timed("k_get_mask 2^24", lambda: Q.get_mask(mid))
+        nf = 1 << 20
+        fenv = Q.BatchedEnv(nf, device=dev, seed=seed)
+        fenv.state.copy_(mid[:nf])
+        info = fenv.step_features(actions[4, :nf], coins[4, :nf], want_mask=True)[4]
+        fenv.state.copy_(mid[:nf])
+        timed("k_step_features 2^20 (step + to_vector + get_mask)",
+              lambda: fenv.step_features(actions[4, :nf], coins[4, :nf], want_mask=True, out=info))
+        del fenv, info
     if want("qeval"):
         out_big = Q.qeval_both(mid, qa, want_states=False, want_probs=False)
         timed("k_qeval_both 2^24 boards", lambda: Q.qeval_both(mid, qa, out=out_big))
@@ -95,6 +126,9 @@ def main():
         mc = Q.BatchedMCTS(rollouts=500, num_simulations=10, seed=seed, device=dev)
         mc.reset(roots, total_rollouts=500)
         timed("k_mcts_run 1024 roots 500x10", lambda: mc.contemplate(500))
+    if want("env1"):
+        single = Q.Env(device=dev, seed=1)
+        timed("k_env1 (single-env step, record to mapped host memory)", lambda: single.step((0, 1)), reps=20)
     torch.cuda.synchronize()
     print("drive_kernels done", flush=True)
 
