@@ -43,10 +43,13 @@ def main():
     env = Q.BatchedEnv(E, device=dev, seed=seed)
     actions = torch.empty((9, E), dtype=torch.uint8, device=dev)
     coins = torch.empty((9, E), dtype=torch.uint8, device=dev)
+    accepted = []
     for ply in range(9):                                  # trace generation: k_step<0,1,...>
         _, _, _, _, info = env.step_random(record=True)
         actions[ply].copy_(info["action"])
         coins[ply].copy_(info["coin"])
+        accepted.append(int((info["status"] == 0).sum().item()))
+    print("accepted by ply:", accepted, flush=True)
 
     if want("step"):
         for rep in range(2):                              # pass 0 warms up, pass 1 is the one to read

@@ -500,6 +500,7 @@ __global__ void __launch_bounds__(kFeatThreads) k_step_features(const StepFeatAr
         const bool valid = i < a.n;
         const int games_here = (int)((a.n - base) < 32u ? (a.n - base) : 32u);
         State s = empty_state();
+        uint64_t legal_of_mine = 0ull;
         if (valid) {
             if (kMode != kStepFresh) {
                 const uint4 sv = *reinterpret_cast<const uint4*>(a.state + i);
@@ -521,22 +522,42 @@ __global__ void __launch_bounds__(kFeatThreads) k_step_features(const StepFeatAr
             if (a.done) a.done[i] = (uint8_t)o.done;
             if (a.mask) a.mask[i] = legal;
             if (a.status) a.status[i] = (uint8_t)o.status;
-            if (fa.illegal_mask) store_illegal_mask(fa.illegal_mask + 36ull * i, legal);
+            legal_of_mine = legal;
         }
         emit_features(warp_buf, lane, s, valid, fa.features + (size_t)base * 180, games_here);
+        if (fa.illegal_mask) {
+            // the warp's 32 masks (1,152 contiguous bytes of the output) go through the feature
+            // buffer, which is free again, and out as lane-contiguous words
+            uint8_t* mbuf = reinterpret_cast<uint8_t*>(warp_buf);
+            store_illegal_mask(mbuf + 36 * lane, legal_of_mine);
+            __syncwarp();
+            uint32_t* dst = reinterpret_cast<uint32_t*>(fa.illegal_mask + 36ull * base);
+            for (int q = lane; q < games_here * 9; q += 32) dst[q] = reinterpret_cast<const uint32_t*>(mbuf)[q];
+            __syncwarp();
+        }
     }
 }
 
-// nn.Model.get_mask for packed states (one thread per game, 9 word stores).
+// nn.Model.get_mask for packed states.  36 bytes per game at a 36-byte stride: each block decodes
+// its 256 games into shared memory and writes the 9,216 bytes out as coalesced 16-byte stores
+// (per-thread word stores at that stride ran at 18 % of the DRAM peak: 569 us per 2^24 games).
 __global__ void __launch_bounds__(kThreads)
 k_get_mask(const qttt_state* __restrict__ state, uint8_t* __restrict__ illegal_mask, int64_t n) {
     __shared__ __align__(16) uint8_t smem[kLutStepBytes];
+    __shared__ __align__(16) uint8_t st_mask[kThreads * 36];
     stage_luts(smem, kLutStepBytes);
     const Luts L = luts_from_image(smem);
     const int64_t stride = (int64_t)gridDim.x * kThreads;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-        const State s = load_state(state, i);
-        store_illegal_mask(illegal_mask + 36 * i, L.legal[~classical(s) & M9]);
+    for (int64_t block_start = (int64_t)blockIdx.x * kThreads; block_start < n; block_start += stride) {
+        const int valid = (int)((n - block_start) < kThreads ? (n - block_start) : kThreads);
+        const int t = threadIdx.x;
+        if (t < valid) {
+            const State s = load_state(state, block_start + t);
+            store_illegal_mask(st_mask + 36 * t, L.legal[~classical(s) & M9]);
+        }
+        __syncthreads();
+        copy_out<36>(st_mask, illegal_mask, block_start, valid);
+        __syncthreads();
     }
 }
 
@@ -609,6 +630,27 @@ k_qeval_both(const qttt_state* __restrict__ state, const uint8_t* __restrict__ a
                    reinterpret_cast<State*>(next1), board0, board1, sq0, sq1, closes, result_prob, i);
 }
 
+// The config-3 shape of K3 -- both outcome boards and the closes flag, nothing else: the same
+// per-game function with the optional outputs known to be absent at compile time, so the
+// successor states are never assembled and no pointer is tested per game.
+__global__ void __launch_bounds__(kThreads, 8)
+k_qeval_boards(const qttt_state* __restrict__ state, const uint8_t* __restrict__ action,
+               uint64_t* __restrict__ board0, uint64_t* __restrict__ board1, uint8_t* __restrict__ closes,
+               int64_t n) {
+    __shared__ __align__(16) uint8_t smem[kLutQevalBytes];
+    stage_luts(smem, kLutQevalBytes);
+    const Luts L = luts_from_image(smem);
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+        const State s = load_state(state, i);
+        State t0, t1;
+        const BothResult r = step_both(s, (uint32_t)L.pair[action[i]], L, t0, t1);
+        board0[i] = board_nibbles(t0, L);
+        board1[i] = board_nibbles(t1, L);
+        closes[i] = (uint8_t)r.collapsed;
+    }
+}
+
 // ------------------------------------------------------------------------------ playouts
 // K4: a block works on one root at a time (rollouts strided over its threads).
 __global__ void __launch_bounds__(kThreads)
@@ -679,7 +721,10 @@ __device__ __forceinline__ void sweep_from_ply(State& s, uint32_t& C, bool& acti
     }
 }
 
-__global__ void __launch_bounds__(kThreads)
+#ifndef QTTT_SWEEP_BLOCKS
+#define QTTT_SWEEP_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(kThreads, QTTT_SWEEP_BLOCKS)
 k_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, unsigned long long* __restrict__ stats) {
     __shared__ __align__(16) uint8_t smem[kLutPolicyBytes];
     __shared__ unsigned long long sh[16];
@@ -1336,6 +1381,10 @@ int qttt_qeval_both(const qttt_state* state, const uint8_t* action, qttt_state* 
         misaligned(board0, 8) || misaligned(board1, 8) || misaligned(result_prob, 4))
         return QTTT_ERR_ALIGN;
     if (n == 0) return QTTT_OK;
+    if (board0 && board1 && closes && !next0 && !next1 && !sq0 && !sq1 && !result_prob) {
+        k_qeval_boards<<<chunk_grid(n, iters_for(n, 8)), kThreads, 0, (cudaStream_t)stream>>>(state, action, board0, board1, closes, n);
+        return check_launch();
+    }
     if (sq0 || sq1)
         k_qeval_both<true><<<chunk_grid(n, iters_for(n, 4)), kThreads, 0, (cudaStream_t)stream>>>(state, action, next0, next1, board0, board1, sq0, sq1, closes, result_prob, n);
     else

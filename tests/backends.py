@@ -194,8 +194,9 @@ class EmuGames:
         self.lib.emu_pack(_p(self.state), _p(cl), _p(mv), _p(nm), C.c_int64(self.n))
         return self
 
-    def qeval_both(self, actions, squares=True):
+    def qeval_both(self, actions, squares=True, boards_only=False):
         """squares=False takes the one-sweep path (no per-move squares), like the library."""
+        squares = squares and not boards_only
         n = self.n
         ac = np.ascontiguousarray(actions, np.uint8)
         o = dict(next0=np.empty((n, 4), np.uint32), next1=np.empty((n, 4), np.uint32),
@@ -381,13 +382,17 @@ class CudaGames:
     def state(self):
         return self.env.state.cpu().numpy().view(np.uint32)
 
-    def qeval_both(self, actions, squares=True):
+    def qeval_both(self, actions, squares=True, boards_only=False):
         t = self.torch
         ac = t.from_numpy(np.ascontiguousarray(actions, np.uint8)).cuda()
-        res = self.Q.qeval_both(self.env.state, ac, want_squares=squares)
+        if boards_only:      # the config-3 shape: its own kernel (k_qeval_boards)
+            res = self.Q.qeval_both(self.env.state, ac, want_states=False, want_probs=False)
+        else:
+            res = self.Q.qeval_both(self.env.state, ac, want_squares=squares)
         out = {k: v.cpu().numpy() for k, v in res.items()}
         for k in ("next0", "next1"):
-            out[k] = out[k].view(np.uint32)
+            if k in out:
+                out[k] = out[k].view(np.uint32)
         for k in ("board0", "board1"):
             out[k] = out[k].astype(np.uint64)
         return out

@@ -235,6 +235,9 @@ def check_qeval_both(backend, n_boards, seed):
         fast = dut.qeval_both(act, squares=False)
         for k in ("closes", "next0", "next1", "board0", "board1", "result_prob"):
             assert np.array_equal(fast[k], res[k]), f"{backend.name} qeval {want} one-sweep: {k}"
+        lean = dut.qeval_both(act, boards_only=True)      # boards + closes only (config 3's shape)
+        for k in ("closes", "board0", "board1"):
+            assert np.array_equal(lean[k], res[k]), f"{backend.name} qeval {want} boards-only: {k}"
         assert np.array_equal(res["board0"], want_res["out0"]) and np.array_equal(res["board1"], want_res["out1"])
         probs = np.zeros((len(act), 3), np.float64)
         for c in (0, 1):
