@@ -328,8 +328,7 @@ QTTT_HD void sweep(uint32_t x, uint32_t y, uint32_t z, uint32_t& R, uint32_t& W,
     const uint32_t E2 = N > 2 ? slot<2>(x, y, z) : 0u, E3 = N > 3 ? slot<3>(x, y, z) : 0u;
     const uint32_t E4 = N > 4 ? slot<4>(x, y, z) : 0u, E5 = N > 5 ? slot<5>(x, y, z) : 0u;
     const uint32_t E6 = N > 6 ? slot<6>(x, y, z) : 0u, E7 = N > 7 ? slot<7>(x, y, z) : 0u;
-    uint32_t before, passes = 0u;
-    (void)passes;
+    uint32_t before;
 #if QTTT_ABSORB == 2
     uint64_t acc = (uint64_t)R + ((uint64_t)W << 9);
     do {
@@ -356,19 +355,6 @@ QTTT_HD void sweep(uint32_t x, uint32_t y, uint32_t z, uint32_t& R, uint32_t& W,
         if (N > 5) absorb<5>(E5, R, W, A3);
         if (N > 6) absorb<6>(E6, R, W, A3);
         if (N > 7) absorb<7>(E7, R, W, A3);
-        if (N >= 5 && N <= 7) {
-            // From the third pass on, a pass that still grew R is followed by an exact test for
-            // "nothing left to absorb" instead of a whole pass that finds nothing.  R spans a tree
-            // of popc(R) - 1 absorbed edges (both squares in R); an edge still to absorb has exactly
-            // one square in R; every other move has none (dead moves sit on classical squares).
-            // So the squares-in-R count over all move slots is 2 (popc(R) - 1) exactly when the
-            // sweep is complete.  ~12 instructions against the ~4 N + 4 of a pass.
-            if (++passes >= 3u && R != before) {
-                const uint32_t R3 = R * 0x40201u;
-                const int inside = popc32(x & R3) + popc32(y & R3) + popc32(z & R3);
-                if (inside == 2 * (popc32(R) - 1)) break;
-            }
-        }
     } while (N > 1 && R != before && (N < 8 || R != stop));
 #endif
     if (kTargets) {
