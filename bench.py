@@ -49,6 +49,16 @@ WORKLOAD = ("step API (K1): reset + 9 steps per pass (the reset is fused into th
             "(config 2 of BASELINE.json scaled to fill the GPU)")
 
 
+def bench_config(envs_per_gpu, world):
+    """The workload description both arms print (identical for `--impl b200` and `--impl reference`)."""
+    return {"workload": WORKLOAD, "envs_per_gpu": envs_per_gpu, "global_envs": envs_per_gpu * world,
+            "plies_per_pass": PLIES,
+            "l2": ("inputs exceed L2: 16 B x E state + 2 B x E actions/coins + 13 B x E outputs per launch "
+                   f"= {31 * envs_per_gpu / 1e6:.0f} MB vs 126 MB L2" if 31 * envs_per_gpu > 126e6
+                   else "inputs fit in L2 (small E)"),
+            "parallelism": f"dp{world} (independent games per rank, no data-path collective)"}
+
+
 def profiled_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per k_step launch from the committed
     `ncu --set full` capture (profiles/k_step_traffic.json, written by profiles/summarize.py)."""
@@ -174,11 +184,11 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "python-int", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs,
-                   "reference_sample": "the same workload (random-vs-random games from the empty board to "
-                                       "termination through Env.reset/step) on the CPU: one env per process, "
-                                       f"{cores} processes x {games_per_proc} games per step",
-                   "envs_per_process": 1, "processes": cores},
+        "config": bench_config(args.envs, args.gpus),
+        "reference_sample": {"what": "the same workload (random-vs-random games from the empty board to "
+                                     "termination through Env.reset/step) on the CPU: one env per process, "
+                                     f"{cores} processes x {games_per_proc} games per step",
+                             "envs_per_process": 1, "processes": cores},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -648,6 +658,62 @@ def run_b200(args):
     ms = timed(lambda: Q.to_vector(qenv.state), 20)
     extra["to_vector_1M_states"] = {"ms": ms, "states_per_s": nb / (ms * 1e-3) * world,
                                     "gb_per_s": nb * 736 / (ms * 1e-3) / 1e9}
+    # the net-input path: step fused with to_vector + get_mask (one launch) next to step, then encoders
+    nf = 1 << 20
+    fenv = Q.BatchedEnv(nf, device=dev, seed=seed, game_base=rank * E)
+    fa, fc = actions[4, :nf].contiguous(), coins[4, :nf].contiguous()
+    fstart = qenv.state.clone()
+
+    def fused():
+        fenv.state.copy_(fstart)
+        return fenv.step_features(fa, fc, want_mask=True, out=fbox.get("info"))
+    fbox = {}
+    fbox["info"] = fused()[4]
+    ms_copy = timed(lambda: fenv.state.copy_(fstart), 20)
+    ms_fused = timed(fused, 20) - ms_copy
+
+    def separate():
+        fenv.state.copy_(fstart)
+        fenv.step(fa, fc)
+        Q.to_vector(fenv.state)
+        Q.get_mask(fenv.state)
+    ms_sep = timed(separate, 20) - ms_copy
+    extra["step_features_1M_envs"] = {
+        "ms_fused": ms_fused, "ms_step_then_to_vector_then_get_mask": ms_sep,
+        "gb_per_s_fused": nf * (47 + 720 + 36) / (ms_fused * 1e-3) / 1e9,
+        "note": "qttt_step_features (Env.step + GameState.to_vector + nn.Model.get_mask of the new state in one "
+                "launch, 803 B per env) against the three separate launches (which also allocate their outputs)"}
+    del fenv, fbox
+    ms = timed(lambda: Q.get_mask(qenv.state), 20)
+    extra["get_mask_1M_states"] = {"ms": ms, "gb_per_s": nb * 52 / (ms * 1e-3) / 1e9}
+
+    # MCTS node-pool occupancy with pruning (MCTS._prune): 256 games, 200 rollouts per move, both players
+    # searching; peak live nodes per tree vs nodes that would have been needed without reclamation
+    if rank == 0:
+        ar_env = Q.BatchedEnv(256, device=dev, seed=seed)
+        mx, mo = Q.MCTSStrategy(rollouts=200, num_simulations=10, seed=1), Q.MCTSStrategy(rollouts=200, num_simulations=10, seed=2)
+        mx.reset(ar_env)
+        mo.reset(ar_env)
+        created = torch.zeros(256, dtype=torch.int64, device=dev)
+        for ply in range(9):
+            mover = mx if ply % 2 == 0 else mo
+            before = mover.search.live_counts().clone()
+            mover.contemplate()
+            created += (mover.search.live_counts() - before) if mover is mx else 0
+            a_ = mover.choose()
+            ar_env.step(a_)
+            mx.sync(a_)
+            mo.sync(a_)
+        extra["mcts_pool_with_prune"] = {
+            "peak_live_nodes_per_tree_mean": float(mx.search.peak_counts().float().mean().item()),
+            "peak_live_nodes_per_tree_max": int(mx.search.peak_counts().max().item()),
+            "pool_high_water_mean": float(mx.search.node_counts().float().mean().item()),
+            "nodes_created_mean": float(created.float().mean().item()) + 1.0,
+            "capacity_per_tree": mx.search.capacity, "node_bytes": mx.search.node_bytes,
+            "errors": int(mx.search.errors().max().item()),
+            "note": "X's search over a 9-ply game against an MCTS opponent, 200 rollouts x 10 playouts per move, "
+                    "sync() after every ply (own and opponent's): nodes of pruned subtrees return to the pool"}
+
     # the rollout kernel at a size that fills the GPU: 65,536 roots x 256 playouts
     big_roots = big.state[:65536].clone()
     box["rb"] = Q.rollout_eval(big_roots, 256, seed)
@@ -668,13 +734,11 @@ def run_b200(args):
             "metric": METRIC, "value": value_graph, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": graph_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "envs_per_gpu": E, "global_envs": E * world, "plies_per_pass": PLIES,
-                       "passes_per_step": P, "timed_region_s": graph_ms * 1e-3,
-                       "env_steps_per_pass_per_gpu": steps_per_pass,
-                       "l2": "inputs exceed L2: 16 B x E state + 2 B x E actions/coins + 13 B x E outputs per launch "
-                             f"= {31 * E / 1e6:.0f} MB vs 126 MB L2" if 31 * E > 126e6 else "inputs fit in L2 (small E)",
-                       "parallelism": f"dp{world} (independent games per rank, no data-path collective)"},
+            "config": bench_config(E, world),
+            "run": {"passes_per_step": P, "timed_region_s": graph_ms * 1e-3,
+                    "env_steps_per_pass_per_gpu": steps_per_pass, "accepted_steps_by_ply": accepted,
+                    "step": "one bench step = passes_per_step passes; a pass = reset + 9 steps over all envs, "
+                            "replayed as one CUDA graph of 9 kernel launches"},
             "value_eager": {"value": value_eager, "ms_per_pass": t_ms / Ke,
                             "note": "the same pass issued as 9 separate BatchedEnv.reset_step/step calls per pass "
                                     "(the loop the per-launch events are recorded in)"},

@@ -1,6 +1,6 @@
 import json,sys
 d=json.loads([l for l in open(sys.argv[1]).read().splitlines() if l.startswith("{")][-1])
-print("value", round(d["value"]/1e9,2), "ms/step", round(d["ms_per_step"],2), "region_s", round(d["config"]["timed_region_s"],3))
+print("value", round(d["value"]/1e9,2), "ms/step", round(d["ms_per_step"],2), "region_s", round(d["run"]["timed_region_s"],3))
 r=d["roofline"]; print("roofline", round(r["frac"],4), "events", round(r["per_launch_events"]["frac"],4), [round(x*1e3,1) for x in r["per_launch_events"]["launch_ms_by_ply"]])
 e=d["e2e"]; print("e2e", round(e["value"]/1e9,2), e["variant"], {k:(round(v["value"]/1e9,2), round(v["frac_of_link_ceiling"],3)) for k,v in e["variants"].items()})
 print("ceiling", {k:(round(v,1) if isinstance(v,float) else v) for k,v in e["pcie_ceiling"].items() if k!="how"})

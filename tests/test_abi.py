@@ -98,3 +98,23 @@ def test_cpu_device_is_refused():
     import qtttgym_b200 as Q
     with pytest.raises(RuntimeError):
         Q.BatchedEnv(4, device="cpu")
+
+
+def test_spaces_mirror_the_reference_env():
+    """qtttgym/env.py:19-25: action_space = Tuple(Discrete(9), Discrete(9)); the observation Dict
+    (classical range corrected to -1..8, quirk Q6)."""
+    import numpy as np
+    from qtttgym_b200 import spaces as S
+    a = S.action_space()
+    assert len(a) == 2 and a[0].n == 9 and a[1].n == 9
+    for _ in range(50):
+        x = a.sample()
+        assert a.contains(x) and x in a
+    assert not a.contains((9, 0)) and not a.contains((0,))
+    o = S.observation_space()
+    obs = {"q_states_p1": [(0, 1)], "q_states_p2": [], "classical": np.array([-1, 8, 0, 1, 2, 3, 4, 5, 6], np.int32),
+           "turn": 1}
+    if not S.HAVE_GYMNASIUM:
+        assert o.contains(obs)
+        assert o["q_states_p1"].max_len == 5 and o["q_states_p2"].max_len == 4
+        assert not o["classical"].contains(np.full(9, 9, np.int32))
