@@ -217,6 +217,15 @@ QTTT_API int qttt_features(const qttt_state* state, float* features, int64_t n, 
 QTTT_API int qttt_env1(qttt_state* state, int op, int a, int b, int coin, uint64_t seed, uint64_t epoch,
                        void* record_host, uint32_t seq, void* stream);
 
+/* QEvalClassic.eval (qeval.py:5-51) for ONE measurement at minimum latency -- the evaluator
+ * plugin Board(qevaluator) calls at board.py:51.  state_host is read on the HOST (the packed
+ * position travels as kernel arguments); record_host is 32 bytes of MAPPED PINNED HOST memory
+ * (16-byte aligned): sq0 int8[9] | sq1 int8[9] (the square each move index collapses into for
+ * coin 0 / 1, -1 = not measured) | closes at byte 18 | seq u32 at byte 28, written last after a
+ * system-scope fence (spin on it). */
+QTTT_API int qttt_qeval1(const qttt_state* state_host, int action, void* record_host, uint32_t seq,
+                         void* stream);
+
 /* nn.Model.get_mask (nn.py:44-61) for packed states: illegal_mask uint8[n][36] (bool bytes,
  * 4-byte aligned), entry [g][a] = 1 when action a touches a classical square of game g
  * (occupied[i] or occupied[j]) -- the logits the reference's policy head sets to -inf.  It is

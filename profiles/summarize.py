@@ -73,7 +73,7 @@ def kernels(tag):
     E, acc = labels_from_drive(tag)
     lines = []
     traffic = []
-    for part in ("step", "io", "qeval", "play", "mcts"):
+    for part in ("step", "desync", "packed", "io", "qeval", "play", "mcts"):
         path = os.path.join(GP, f"raw_{part}_{tag}.csv")
         if not os.path.exists(path):
             continue
@@ -98,7 +98,12 @@ def kernels(tag):
                     st[s] = num(r[hdr.index(key)])
             top = sorted(st.items(), key=lambda kv: -kv[1])[:3]
             what, alg = name, None
-            if part == "step" and name.startswith("k_step<"):
+            if part == "desync":
+                what, alg = "k_step DESYNC batch (autoreset, forced actions, plies 1-9 mixed in every warp)", 47 * E
+            elif part == "packed":
+                what, alg = (("k_step_packed ply 4", 35 * (acc[4] if acc else E)) if "zc" not in name else
+                             ("k_step_packed_zc ply 4 (kernel reads/writes mapped pinned host memory)", None))
+            elif part == "step" and name.startswith("k_step<"):
                 if ", 1, 0>" in name.replace(" ", "").replace(",", ", ") and "k_step<0, 0, 1, 1" in name:
                     what, alg = "k_step ply 0 (reset fused in)", (31 * acc[0] if acc else None)
                 elif "k_step<0, 0, 1, 0" in name:
@@ -118,7 +123,7 @@ def kernels(tag):
                 what, alg = "k_step_packed ply 4", 35 * (acc[4] if acc else E)
             elif name.startswith("k_qeval"):
                 n = E if k < 2 else (1 << 20)
-                what, alg = f"k_qeval_both {n} boards", 33 * n
+                what, alg = f"{name.split(chr(60))[0]} {n} boards", 33 * n
             elif name.startswith("k_observe"):
                 what, alg = ("k_observe all outputs" if k < 2 else "k_observe env.py outputs"), E * (16 + (90 if k < 2 else 28))
             elif name.startswith("k_features"):

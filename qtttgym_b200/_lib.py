@@ -34,6 +34,7 @@ _SIGNATURES = {
     "qttt_observe": ([_vp] * 11 + [_i64, _vp], _int),
     "qttt_features": ([_vp, _vp, _i64, _vp], _int),
     "qttt_env1": ([_vp, _int, _int, _int, _int, _u64, _u64, _vp, _u32, _vp], _int),
+    "qttt_qeval1": ([_vp, _int, _vp, _u32, _vp], _int),
     "qttt_get_mask": ([_vp, _vp, _i64, _vp], _int),
     "qttt_step_features": ([_vp, _vp, _int, _vp, _u64, _u64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp], _int),
     "qttt_pack": ([_vp, _vp, _vp, _vp, _i64, _vp], _int),

@@ -613,6 +613,29 @@ k_env1(qttt_state* __restrict__ state, int a, int b, int coin, int op, uint64_t 
     }
 }
 
+// QEvalClassic.eval for ONE measurement at minimum latency (the plugin seam, board.py:51): the
+// component's moves travel as a packed state in the kernel arguments, both outcomes' per-move
+// squares come back through mapped pinned host memory (32-byte record: sq0[9], sq1[9], closes,
+// ..., seq at byte 28), the host spins on the sequence word.
+__global__ void __launch_bounds__(32)
+k_qeval1(uint32_t x, uint32_t y, uint32_t z, uint32_t w, uint32_t action, uint8_t* __restrict__ rec_host,
+         uint32_t seq) {
+    __shared__ __align__(16) uint8_t smem[kLutStepBytes];
+    __shared__ __align__(16) int8_t rec[32];
+    stage_luts(smem, kLutStepBytes);
+    const Luts L = luts_from_image(smem);
+    if (threadIdx.x == 0) {
+        const State s{x, y, z, w};
+        uint8_t closes = 0;
+        qeval_game<true>(s, action, L, nullptr, nullptr, nullptr, nullptr, rec, rec + 9, &closes, nullptr, 0);
+        rec[18] = (int8_t)closes;
+        reinterpret_cast<uint4*>(rec_host)[0] = reinterpret_cast<const uint4*>(rec)[0];
+        reinterpret_cast<uint2*>(rec_host)[2] = reinterpret_cast<const uint2*>(rec)[2];
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t*>(rec_host + 28) = seq;
+    }
+}
+
 // ------------------------------------------------------------------------------ K3 qeval
 template <bool kSquares>
 __global__ void __launch_bounds__(kThreads, kSquares ? 4 : 8)
@@ -1266,6 +1289,15 @@ int qttt_env1(qttt_state* state, int op, int a, int b, int coin, uint64_t seed, 
     if (const int rc = device_ok()) return rc;
     k_env1<<<1, 32, 0, (cudaStream_t)stream>>>(state, a, b, coin, op, seed, domain_word(0u, epoch),
                                                static_cast<uint8_t*>(record_host), seq);
+    return check_launch();
+}
+
+int qttt_qeval1(const qttt_state* state_host, int action, void* record_host, uint32_t seq, void* stream) {
+    if (!state_host || !record_host || action < 0 || action > 255) return QTTT_ERR_ARG;
+    if (misaligned(record_host, 16)) return QTTT_ERR_ALIGN;
+    if (const int rc = device_ok()) return rc;
+    k_qeval1<<<1, 32, 0, (cudaStream_t)stream>>>(state_host->w[0], state_host->w[1], state_host->w[2], state_host->w[3],
+                                                 (uint32_t)action, static_cast<uint8_t*>(record_host), seq);
     return check_launch();
 }
 

@@ -82,14 +82,28 @@ class QEvalB200:
     one having closed the cycle, and returns the square each collapses into.  The coin is one
     call to ``rng.choice((0, 1))`` -- the stdlib ``random`` module by default, which is what
     the reference consumes (qeval.py:35) -- or a forced bit via ``force``.
+
+    One call is one kernel launch (``qttt_qeval1``): the component is packed on the host (a few
+    shifts), travels as kernel arguments, and both outcomes come back through mapped pinned host
+    memory; the host spins on the record's sequence word.  No tensors are created per call.
     """
 
     def __init__(self, device="cuda", rng=None):
+        import ctypes as C
+        self.lib = _lib.lib()
         self.device = torch.device(device)
-        if self.device.type == "cuda" and self.device.index is None:
+        if self.device.type != "cuda":
+            raise RuntimeError("qtttgym_b200 runs on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.rng = rng if rng is not None else _random
         self.forced: list[int] = []
+        self._host = torch.zeros(32, dtype=torch.uint8).pin_memory()
+        self._np = self._host.numpy()
+        self._seq_view = self._np[28:32].view("uint32")
+        self._mv = memoryview(self._np).cast("b")
+        self._state = (C.c_uint32 * 4)()
+        self._seq = 0
 
     def force(self, *bits):
         self.forced.extend(int(b) & 1 for b in bits)
@@ -98,17 +112,32 @@ class QEvalB200:
         k = len(entangled_moves)
         if not 2 <= k <= 9:
             raise ValueError("a measured component has 2..9 moves")
-        classical = torch.full((1, 9), -1, dtype=torch.int8)
-        moves = torch.full((1, 9, 2), -1, dtype=torch.int8)
+        # pack the k - 1 earlier moves as an all-quantum position (csrc/qttt_core.cuh: E fields of 9
+        # bits, three per word, len(moves) in bits 27..30 of word 0); the last move is the action
+        words = [0, 0, 0, 0]
         for r, m in enumerate(entangled_moves[:-1]):
-            moves[0, r, 0], moves[0, r, 1] = int(m[0]), int(m[1])
-        state = pack_states(classical, moves, torch.tensor([k - 1], dtype=torch.uint8), self.device)
+            a, b = int(m[0]), int(m[1])
+            if not (0 <= a < 9 and 0 <= b < 9 and a != b):
+                raise ValueError("moves are pairs of distinct squares 0..8")
+            words[r // 3] |= ((1 << a) | (1 << b)) << (9 * (r % 3))
+        words[0] |= (k - 1) << 27
+        st = self._state
+        st[0], st[1], st[2], st[3] = words
         last = entangled_moves[-1]
-        act = torch.tensor([move2ind(int(last[0]), int(last[1]))], dtype=torch.uint8,
-                           device=self.device)
-        res = qeval_both(state, act, want_states=False, want_boards=False, want_squares=True,
-                         want_probs=False)
-        if int(res["closes"][0].item()) != 1:
+        self._seq = seq = (self._seq % 0xFFFFFFFE) + 1
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.qttt_qeval1(st, move2ind(int(last[0]), int(last[1])), self._host.data_ptr(), seq,
+                                            _stream_ptr(self.device)))
+        view, spins = self._seq_view, 0
+        while view[0] != seq:
+            spins += 1
+            if spins > 5_000_000:
+                torch.cuda.synchronize(self.device)
+                if view[0] != seq:
+                    raise RuntimeError("qttt_qeval1: the record never arrived")
+        mv = self._mv
+        if mv[18] != 1:
             raise ValueError("the last move does not close a cycle in this component")
         coin = self.forced.pop(0) if self.forced else self.rng.choice((0, 1))
-        return res["sq1" if coin else "sq0"][0, :k].tolist()
+        off = 9 if coin else 0
+        return list(mv[off:off + k])
