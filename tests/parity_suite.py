@@ -465,6 +465,25 @@ def check_epoch_coin(backend, n_games=2000, seed=99, game_base=7):
     del rng
 
 
+def check_exhaustive_openings(backend, depth=3, stride=1):
+    """EVERY action-index sequence of `depth` plies from the empty board (36^depth of them, legal or
+    not) under every assignment of the forced coins, against the oracle after every ply: all
+    placements, all 2- and 3-cycles, all illegal repeats of an opening.  `stride` thins the set."""
+    idx = np.arange(0, 36 ** depth, stride, dtype=np.int64)
+    acts = np.stack([(idx // 36 ** p) % 36 for p in range(depth)], 0).astype(np.uint8)      # [depth, n]
+    n0 = acts.shape[1]
+    for coin_bits in range(1 << depth):
+        coins = np.stack([np.full(n0, (coin_bits >> p) & 1, np.uint8) for p in range(depth)], 0)
+        ref = CO.Games(n0)
+        dut = backend.games(n0)
+        for p in range(depth):
+            r = ref.step(PAIRS[acts[p]], coins[p])
+            o = dut.step_index(acts[p], coins[p])
+            assert_same_step(o, r, f"{backend.name} exhaustive coins={coin_bits:b} ply {p}")
+        assert_same_obs(dut.observe(), ref.observe(), f"{backend.name} exhaustive coins={coin_bits:b}")
+    return n0 * (1 << depth)
+
+
 def check_packed_step(backend, n_games=5000, seed=31, variant=None):
     """qttt_step_packed: one byte in (action | coin << 7), one 16-bit word out (free squares |
     terminated << 9 | line << 10 | status << 11) -- same transition as the oracle, bit for bit."""

@@ -296,6 +296,13 @@ def test_step_host_equals_step(cuda):
         assert torch.equal(a.state, b.state) and torch.equal(a.state, gen.state)
 
 
+def test_exhaustive_openings(cuda):
+    """all 36^3 three-ply openings x all 8 coin assignments (373,248 games) and a thinned set of the
+    36^4 four-ply ones x 16 coin assignments, every output after every ply"""
+    assert S.check_exhaustive_openings(cuda, depth=3) == 36 ** 3 * 8
+    assert S.check_exhaustive_openings(cuda, depth=4, stride=5) > 5_000_000
+
+
 def test_packed_step_host(cuda):
     S.check_packed_step(cuda, 40_001)
 

@@ -108,3 +108,7 @@ def test_golden_getmask(emu):
 
 def test_step_features(emu):
     S.check_step_features(emu, 1000)
+
+
+def test_exhaustive_openings(emu):
+    assert S.check_exhaustive_openings(emu, depth=3, stride=7) > 50000
