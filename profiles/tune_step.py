@@ -1,8 +1,8 @@
 """Times the step kernel (K1) ply by ply for a lock-step pass and for a desynchronised batch,
-under the tuning knobs of csrc/qttt_kernels.cu (QTTT_STEP_ITERS, QTTT_STEP_PREFETCH), one
-subprocess per setting (the knobs are read once per process).
+under the tuning knob of csrc/qttt_kernels.cu (QTTT_STEP_ITERS: chunks of 256 games per block), one
+subprocess per setting (the knob is read once per process).
 
-    python profiles/tune_step.py [--envs 16777216] [--reps 5] [--grid "4:0,4:1,8:0"]
+    python profiles/tune_step.py [--envs 16777216] [--reps 5] [--grid "4,8,16"]
 """
 from __future__ import annotations
 
@@ -75,7 +75,7 @@ def child(args):
     assert torch.equal(mix.state, final), "desync replay diverged"
     d_ms = [sum(dv[k][2 * p].elapsed_time(dv[k][2 * p + 1]) for k in range(reps)) / reps for p in range(9)]
     d_frac = BYTES_PER_STEP * E * 9 / (sum(d_ms) * 1e-3) / 1e9 / peak
-    print(json.dumps({"iters": os.environ.get("QTTT_STEP_ITERS"), "prefetch": os.environ.get("QTTT_STEP_PREFETCH"),
+    print(json.dumps({"iters": os.environ.get("QTTT_STEP_ITERS"),
                       "pass_ms": round(sum(per_ply), 4), "frac": round(frac, 4),
                       "ply_us": [round(1e3 * x, 1) for x in per_ply],
                       "desync_ms_per_launch": round(sum(d_ms) / 9, 4), "desync_frac": round(d_frac, 4),
@@ -86,14 +86,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=1 << 24)
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--grid", default="4:0")
+    ap.add_argument("--grid", default="8")
     ap.add_argument("--child", action="store_true")
     args = ap.parse_args()
     if args.child:
         return child(args)
     for cfg in args.grid.split(","):
-        it, pf = cfg.split(":")
-        env = dict(os.environ, QTTT_STEP_ITERS=it, QTTT_STEP_PREFETCH=pf)
+        env = dict(os.environ, QTTT_STEP_ITERS=cfg.split(":")[0])
         subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "--envs", str(args.envs),
                         "--reps", str(args.reps)], env=env, check=False)
 

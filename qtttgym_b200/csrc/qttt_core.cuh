@@ -237,39 +237,19 @@ template <int I> struct PlanePattern {
     static constexpr uint32_t value = (v & 1u) | ((v & 2u) << 8) | ((v & 4u) << 16);
 };
 
-#ifndef QTTT_ABSORB
-#define QTTT_ABSORB 1
-#endif
-
 template <int I>
 QTTT_HD void absorb(uint32_t E, uint32_t& R, uint32_t& W, uint32_t& A3) {
 #if defined(__CUDA_ARCH__)
-    // PTX pins the shape.  The integer ALU pipe (LOP3 / SHF / ISETP / SEL: one warp instruction
-    // per TWO cycles) is the binding resource of these kernels, the FMA pipe (IMAD: one per
-    // cycle) is mostly idle, so everything that can be a multiply-add is one:
+    // PTX pins the shape.  The integer ALU pipe (LOP3 / SHF / ISETP / SEL) issues one warp
+    // instruction per TWO cycles, the FMA pipe (IMAD) one per cycle, so everything that can be a
+    // multiply-add is one:
     //   h = E & R, p = (h != 0)      one LOP3 with a predicate output            (ALU pipe)
     //   c = E - h                    the endpoint not yet reached: IMAD h * -1 + E (FMA pipe)
     //   @p W += c * pattern(I)       books c as owned by move I in the plane word  (FMA pipe)
     //   @p R += c                                                                 (FMA pipe)
-#if QTTT_ABSORB == 0
-    if (I < 7) {
-        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 h, c;\n\t"
-            "and.b32 h, %2, %1;\n\t"
-            "setp.ne.u32 p, h, 0;\n\t"
-            "lop3.b32 c, %2, %1, 0, 0x30;\n\t"
-            "@p mad.lo.u32 %0, c, %3, %0;\n\t"
-            "@p add.u32 %1, %1, c;\n\t}"
-            : "+r"(W), "+r"(R) : "r"(E), "n"(PlanePattern<I>::value));
-    } else {
-        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 h, c;\n\t"
-            "and.b32 h, %2, %1;\n\t"
-            "setp.ne.u32 p, h, 0;\n\t"
-            "lop3.b32 c, %2, %1, 0, 0x30;\n\t"
-            "@p add.u32 %0, %0, c;\n\t"
-            "@p add.u32 %1, %1, c;\n\t}"
-            : "+r"(A3), "+r"(R) : "r"(E));
-    }
-#else
+    // (Measured alternatives, DESIGN.md section 9: c as a second LOP3 -- the same speed, the kernel is
+    // issue-bound, not ALU-pipe-bound; R and W in one 64-bit accumulator updated by a single
+    // predicated IMAD.WIDE -- three instructions per slot but 9 % slower.)
     if (I < 7) {
         asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 h, c;\n\t"
             "and.b32 h, %2, %1;\n\t"
@@ -287,7 +267,6 @@ QTTT_HD void absorb(uint32_t E, uint32_t& R, uint32_t& W, uint32_t& A3) {
             "@p mad.lo.u32 %1, c, 1, %1;\n\t}"
             : "+r"(A3), "+r"(R) : "r"(E));
     }
-#endif
 #else
     if (E & R) {
         const uint32_t c = E & ~R;
@@ -295,20 +274,6 @@ QTTT_HD void absorb(uint32_t E, uint32_t& R, uint32_t& W, uint32_t& A3) {
         R |= c;
     }
 #endif
-}
-
-// The 64-bit form: acc = R (bits 0..8) | W << 9, so that ONE wide multiply-add books both the
-// reached square and its owner: acc += c * (1 | pattern(I) << 9).
-template <int I>
-QTTT_HD void absorb_wide(uint32_t E, uint64_t& acc, uint32_t& A3) {
-    // plain C++: ptxas turns this into LOP3 (h and the predicate), @p IMAD.IADD (c), @p IMAD.WIDE
-    const uint32_t h = E & (uint32_t)acc;       // E < 512, so only the R bits of acc matter
-    const uint32_t c = E - h;
-    if (I < 7) {
-        if (h) acc = (uint64_t)c * (uint64_t)(1u | (PlanePattern<I>::value << 9)) + acc;
-    } else {
-        if (h) { acc += c; A3 += c; }
-    }
 }
 
 template <int I> QTTT_HD uint32_t slot(uint32_t x, uint32_t y, uint32_t z) {
@@ -329,22 +294,6 @@ QTTT_HD void sweep(uint32_t x, uint32_t y, uint32_t z, uint32_t& R, uint32_t& W,
     const uint32_t E4 = N > 4 ? slot<4>(x, y, z) : 0u, E5 = N > 5 ? slot<5>(x, y, z) : 0u;
     const uint32_t E6 = N > 6 ? slot<6>(x, y, z) : 0u, E7 = N > 7 ? slot<7>(x, y, z) : 0u;
     uint32_t before;
-#if QTTT_ABSORB == 2
-    uint64_t acc = (uint64_t)R + ((uint64_t)W << 9);
-    do {
-        before = (uint32_t)acc;
-        if (N > 0) absorb_wide<0>(E0, acc, A3);
-        if (N > 1) absorb_wide<1>(E1, acc, A3);
-        if (N > 2) absorb_wide<2>(E2, acc, A3);
-        if (N > 3) absorb_wide<3>(E3, acc, A3);
-        if (N > 4) absorb_wide<4>(E4, acc, A3);
-        if (N > 5) absorb_wide<5>(E5, acc, A3);
-        if (N > 6) absorb_wide<6>(E6, acc, A3);
-        if (N > 7) absorb_wide<7>(E7, acc, A3);
-    } while (N > 1 && (uint32_t)acc != before && (N < 8 || ((uint32_t)acc & M9) != stop));
-    R = (uint32_t)acc & M9;
-    W = (uint32_t)(acc >> 9);
-#else
     do {
         before = R;
         if (N > 0) absorb<0>(E0, R, W, A3);
@@ -356,7 +305,6 @@ QTTT_HD void sweep(uint32_t x, uint32_t y, uint32_t z, uint32_t& R, uint32_t& W,
         if (N > 6) absorb<6>(E6, R, W, A3);
         if (N > 7) absorb<7>(E7, R, W, A3);
     } while (N > 1 && R != before && (N < 8 || R != stop));
-#endif
     if (kTargets) {
         // Which square did each absorbed edge bring in?  Only the qeval kernel asks: replay
         // the rooting from the start square (T[8]) with plain code.

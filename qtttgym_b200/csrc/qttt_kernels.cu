@@ -104,10 +104,11 @@ struct StepIn { uint4 sv; uint32_t act, coin; };
 
 // kFmt: QTTT_ACT_INDEX / QTTT_ACT_PAIR; kRandom: Philox policy instead of given actions;
 // kFull: reward, done, mask and status are all requested and coins are given (no NULL tests);
-// kMode: kStepPlain / kStepFresh / kStepAuto / kStepAutoNext (qttt_core.cuh);
-// kPrefetch: the next chunk's inputs are loaded before the current chunk is computed.
-template <int kFmt, bool kRandom, bool kFull, int kMode, bool kPrefetch>
-__global__ void __launch_bounds__(kThreads, kPrefetch ? 6 : 8) k_step(const StepArgs a) {   // 8 blocks/SM: 32 registers
+// kMode: kStepPlain / kStepFresh / kStepAuto / kStepAutoNext (qttt_core.cuh).
+// (Loading the next chunk's inputs before computing the current one was measured: 39 registers,
+// 6 blocks per SM, 2 % slower overall.)
+template <int kFmt, bool kRandom, bool kFull, int kMode>
+__global__ void __launch_bounds__(kThreads, 8) k_step(const StepArgs a) {   // 8 blocks/SM: 32 registers
     __shared__ __align__(16) uint8_t smem[kLutStepBytes];
     stage_luts(smem, kLutStepBytes);
     const Luts L = luts_from_image(smem);
@@ -158,20 +159,9 @@ __global__ void __launch_bounds__(kThreads, kPrefetch ? 6 : 8) k_step(const Step
     };
 
     const uint32_t first = (blockIdx.x * (uint32_t)a.iters) * kThreads + threadIdx.x;
-    if (kPrefetch) {
-        StepIn cur = load(first);
-        for (int it = 0; it < a.iters; ++it) {
-            const uint32_t i = first + (uint32_t)it * kThreads;
-            StepIn nxt = cur;
-            if (it + 1 < a.iters) nxt = load(i + kThreads);
-            run(i, cur);
-            cur = nxt;
-        }
-    } else {
-        for (int it = 0; it < a.iters; ++it) {
-            const uint32_t i = first + (uint32_t)it * kThreads;
-            run(i, load(i));
-        }
+    for (int it = 0; it < a.iters; ++it) {
+        const uint32_t i = first + (uint32_t)it * kThreads;
+        run(i, load(i));
     }
 }
 
@@ -744,10 +734,7 @@ __device__ __forceinline__ void sweep_from_ply(State& s, uint32_t& C, bool& acti
     }
 }
 
-#ifndef QTTT_SWEEP_BLOCKS
-#define QTTT_SWEEP_BLOCKS 6
-#endif
-__global__ void __launch_bounds__(kThreads, QTTT_SWEEP_BLOCKS)
+__global__ void __launch_bounds__(kThreads, 6)      // 39 registers; 7 or 8 blocks per SM spill and measured 2 % slower
 k_sweep(int64_t game_lo, int64_t game_hi, uint64_t seed, unsigned long long* __restrict__ stats) {
     __shared__ __align__(16) uint8_t smem[kLutPolicyBytes];
     __shared__ unsigned long long sh[16];
@@ -993,8 +980,8 @@ static int device_ok() {
     return verdict[dev] == 1 ? QTTT_OK : QTTT_ERR_NO_DEVICE;
 }
 
-// Tuning knobs of the step kernels, read once from the environment (experiments only; the
-// defaults are what the numbers in DESIGN.md were measured with).
+// Tuning knob of the step kernels, read once from the environment (experiments only; the default
+// is what the numbers in DESIGN.md were measured with).
 static int step_iters() {
     static const int v = []() {
         const char* e = getenv("QTTT_STEP_ITERS");
@@ -1010,14 +997,6 @@ static int iters_for(int64_t n, int tuned) {
     const int64_t it = chunks / (148 * 16);
     return (int)(it < 1 ? 1 : (it > tuned ? tuned : it));
 }
-static bool step_prefetch() {
-    static const bool v = []() {
-        const char* e = getenv("QTTT_STEP_PREFETCH");
-        return e ? atoi(e) != 0 : false;
-    }();
-    return v;
-}
-
 }  // namespace qttt
 
 using namespace qttt;
@@ -1059,7 +1038,6 @@ template <int kFmt, bool kRandom, int kMode>
 static int launch_step_mode(StepArgs a, int64_t n, cudaStream_t st) {
     const int64_t kSlice = 1ll << 31;
     const bool full = !kRandom && a.coin && a.reward && a.done && a.mask && a.status;
-    const bool pf = step_prefetch();
     const int act_bytes = kFmt == QTTT_ACT_PAIR ? 2 : 1;
     for (int64_t lo = 0; lo < n; lo += kSlice) {
         const int64_t m = n - lo < kSlice ? n - lo : kSlice;
@@ -1081,12 +1059,11 @@ static int launch_step_mode(StepArgs a, int64_t n, cudaStream_t st) {
         bool launched = false;
         if constexpr (kFmt == QTTT_ACT_INDEX && !kRandom && kMode != kStepAutoNext) {
             if (full) {                           // the headline shape gets the specialised variants
-                if (pf) k_step<kFmt, false, true, kMode, true><<<grid, kThreads, 0, st>>>(b);
-                else    k_step<kFmt, false, true, kMode, false><<<grid, kThreads, 0, st>>>(b);
+                k_step<kFmt, false, true, kMode><<<grid, kThreads, 0, st>>>(b);
                 launched = true;
             }
         }
-        if (!launched) k_step<kFmt, kRandom, false, kMode, false><<<grid, kThreads, 0, st>>>(b);
+        if (!launched) k_step<kFmt, kRandom, false, kMode><<<grid, kThreads, 0, st>>>(b);
         const int rc = check_launch();
         if (rc != QTTT_OK) return rc;
     }
