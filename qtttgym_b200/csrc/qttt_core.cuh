@@ -281,6 +281,8 @@ template <int I> QTTT_HD uint32_t slot(uint32_t x, uint32_t y, uint32_t z) {
     return (I % 3 == 0) ? (word & M9) : ((word >> (9 * (I % 3))) & M9);
 }
 
+constexpr int kFixedSweepMax = 5;   // up to this many slots the sweep runs a fixed schedule (below)
+
 // Forward sweeps over move slots 0..N-1 until the reached set stops growing.
 // `stop`: a set R cannot grow beyond, or ~0 when none is known.  With 8 moves on the board the
 // live edges form ONE spanning tree of the free squares (every measured component of k squares
@@ -293,18 +295,34 @@ QTTT_HD void sweep(uint32_t x, uint32_t y, uint32_t z, uint32_t& R, uint32_t& W,
     const uint32_t E2 = N > 2 ? slot<2>(x, y, z) : 0u, E3 = N > 3 ? slot<3>(x, y, z) : 0u;
     const uint32_t E4 = N > 4 ? slot<4>(x, y, z) : 0u, E5 = N > 5 ? slot<5>(x, y, z) : 0u;
     const uint32_t E6 = N > 6 ? slot<6>(x, y, z) : 0u, E7 = N > 7 ? slot<7>(x, y, z) : 0u;
-    uint32_t before;
-    do {
-        before = R;
+    if (N <= kFixedSweepMax) {
+        // Few slots: a fixed schedule with no convergence test.  A slot is absorbed in pass p when the
+        // tree path from the start square to it turns back to a lower slot p - 1 times, so N passes
+        // always suffice and the last one can only still absorb slot 0.  A warp of 32 games needs
+        // (nearly) that many passes anyway, and the per-pass test is gone.
+#pragma unroll
+        for (int p = 0; p < N - 1; ++p) {
+            if (N > 0) absorb<0>(E0, R, W, A3);
+            if (N > 1) absorb<1>(E1, R, W, A3);
+            if (N > 2) absorb<2>(E2, R, W, A3);
+            if (N > 3) absorb<3>(E3, R, W, A3);
+            if (N > 4) absorb<4>(E4, R, W, A3);
+        }
         if (N > 0) absorb<0>(E0, R, W, A3);
-        if (N > 1) absorb<1>(E1, R, W, A3);
-        if (N > 2) absorb<2>(E2, R, W, A3);
-        if (N > 3) absorb<3>(E3, R, W, A3);
-        if (N > 4) absorb<4>(E4, R, W, A3);
-        if (N > 5) absorb<5>(E5, R, W, A3);
-        if (N > 6) absorb<6>(E6, R, W, A3);
-        if (N > 7) absorb<7>(E7, R, W, A3);
-    } while (N > 1 && R != before && (N < 8 || R != stop));
+    } else {
+        uint32_t before;
+        do {
+            before = R;
+            if (N > 0) absorb<0>(E0, R, W, A3);
+            if (N > 1) absorb<1>(E1, R, W, A3);
+            if (N > 2) absorb<2>(E2, R, W, A3);
+            if (N > 3) absorb<3>(E3, R, W, A3);
+            if (N > 4) absorb<4>(E4, R, W, A3);
+            if (N > 5) absorb<5>(E5, R, W, A3);
+            if (N > 6) absorb<6>(E6, R, W, A3);
+            if (N > 7) absorb<7>(E7, R, W, A3);
+        } while (N > 1 && R != before && (N < 8 || R != stop));
+    }
     if (kTargets) {
         // Which square did each absorbed edge bring in?  Only the qeval kernel asks: replay
         // the rooting from the start square (T[8]) with plain code.
@@ -328,18 +346,30 @@ QTTT_HD void sweep2(uint32_t x, uint32_t y, uint32_t z, uint32_t& Ra, uint32_t& 
     const uint32_t E2 = N > 2 ? slot<2>(x, y, z) : 0u, E3 = N > 3 ? slot<3>(x, y, z) : 0u;
     const uint32_t E4 = N > 4 ? slot<4>(x, y, z) : 0u, E5 = N > 5 ? slot<5>(x, y, z) : 0u;
     const uint32_t E6 = N > 6 ? slot<6>(x, y, z) : 0u, E7 = N > 7 ? slot<7>(x, y, z) : 0u;
-    uint32_t before;
-    do {
-        before = Ra + (Rb << 9);
+    if (N <= kFixedSweepMax) {      // the fixed schedule of sweep<N>
+#pragma unroll
+        for (int p = 0; p < N - 1; ++p) {
+            if (N > 0) { absorb<0>(E0, Ra, Wa, A3a); absorb<0>(E0, Rb, Wb, A3b); }
+            if (N > 1) { absorb<1>(E1, Ra, Wa, A3a); absorb<1>(E1, Rb, Wb, A3b); }
+            if (N > 2) { absorb<2>(E2, Ra, Wa, A3a); absorb<2>(E2, Rb, Wb, A3b); }
+            if (N > 3) { absorb<3>(E3, Ra, Wa, A3a); absorb<3>(E3, Rb, Wb, A3b); }
+            if (N > 4) { absorb<4>(E4, Ra, Wa, A3a); absorb<4>(E4, Rb, Wb, A3b); }
+        }
         if (N > 0) { absorb<0>(E0, Ra, Wa, A3a); absorb<0>(E0, Rb, Wb, A3b); }
-        if (N > 1) { absorb<1>(E1, Ra, Wa, A3a); absorb<1>(E1, Rb, Wb, A3b); }
-        if (N > 2) { absorb<2>(E2, Ra, Wa, A3a); absorb<2>(E2, Rb, Wb, A3b); }
-        if (N > 3) { absorb<3>(E3, Ra, Wa, A3a); absorb<3>(E3, Rb, Wb, A3b); }
-        if (N > 4) { absorb<4>(E4, Ra, Wa, A3a); absorb<4>(E4, Rb, Wb, A3b); }
-        if (N > 5) { absorb<5>(E5, Ra, Wa, A3a); absorb<5>(E5, Rb, Wb, A3b); }
-        if (N > 6) { absorb<6>(E6, Ra, Wa, A3a); absorb<6>(E6, Rb, Wb, A3b); }
-        if (N > 7) { absorb<7>(E7, Ra, Wa, A3a); absorb<7>(E7, Rb, Wb, A3b); }
-    } while (N > 1 && (Ra + (Rb << 9)) != before && (N < 8 || (Ra & Rb) != stop));
+    } else {
+        uint32_t before;
+        do {
+            before = Ra + (Rb << 9);
+            if (N > 0) { absorb<0>(E0, Ra, Wa, A3a); absorb<0>(E0, Rb, Wb, A3b); }
+            if (N > 1) { absorb<1>(E1, Ra, Wa, A3a); absorb<1>(E1, Rb, Wb, A3b); }
+            if (N > 2) { absorb<2>(E2, Ra, Wa, A3a); absorb<2>(E2, Rb, Wb, A3b); }
+            if (N > 3) { absorb<3>(E3, Ra, Wa, A3a); absorb<3>(E3, Rb, Wb, A3b); }
+            if (N > 4) { absorb<4>(E4, Ra, Wa, A3a); absorb<4>(E4, Rb, Wb, A3b); }
+            if (N > 5) { absorb<5>(E5, Ra, Wa, A3a); absorb<5>(E5, Rb, Wb, A3b); }
+            if (N > 6) { absorb<6>(E6, Ra, Wa, A3a); absorb<6>(E6, Rb, Wb, A3b); }
+            if (N > 7) { absorb<7>(E7, Ra, Wa, A3a); absorb<7>(E7, Rb, Wb, A3b); }
+        } while ((Ra + (Rb << 9)) != before && (N < 8 || (Ra & Rb) != stop));
+    }
 }
 
 // Board.make_move for one game.  `enew`: E mask of the requested pair (0 = malformed);
@@ -526,18 +556,26 @@ struct BothResult {
     uint32_t classical0, classical1;   // classical squares of the two successors
     uint32_t n0, n1;                   // len(moves) of the two successors
 };
-QTTT_HD BothResult step_both(const State& s, uint32_t enew, const Luts& L, State& s0, State& s1) {
-    const uint32_t x = s.x, y = s.y, z = s.z, w = s.w;
-    const uint32_t n = (x >> 27) & 15u;
-    const NRow row = L.nrow[n];
-    const uint32_t C = classical(s);
-    const bool legal = (enew != 0u) & ((enew & C) == 0u) & (n < 9u);   // board.py:10-15
+// The sweep both callers share: the two rootings of the closing move's component.
+struct BothSweep {
+    uint32_t n, C, enew, legal, colf;
+    uint32_t Ra, Wa, A3a, Rb, Wb, A3b;
+    NRow row;
+};
+template <bool kFullWarp = false>
+QTTT_HD BothSweep sweep_both(const State& s, uint32_t enew, const Luts& L) {
+    const uint32_t x = s.x, y = s.y, z = s.z;
+    BothSweep r;
+    r.n = (x >> 27) & 15u;
+    r.row = L.nrow[r.n];
+    r.C = classical(s);
+    const bool legal = (enew != 0u) & ((enew & r.C) == 0u) & (r.n < 9u);   // board.py:10-15
     enew = legal ? enew : 0u;
     const uint32_t a = enew & (0u - enew), b = enew ^ a;                // coin 0 -> a, coin 1 -> b
     uint32_t Ra = a, Rb = b;
-    uint32_t Wa = a * row.kp, Wb = b * row.kp;
-    uint32_t A3a = (n >= 7u) ? a : 0u, A3b = (n >= 7u) ? b : 0u;
-    switch (warp_max_u32(legal ? n : 0u)) {
+    uint32_t Wa = a * r.row.kp, Wb = b * r.row.kp;
+    uint32_t A3a = (r.n >= 7u) ? a : 0u, A3b = (r.n >= 7u) ? b : 0u;
+    switch (warp_max_u32<kFullWarp>(legal ? r.n : 0u)) {
         case 1: sweep2<1>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b); break;
         case 2: sweep2<2>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b); break;
         case 3: sweep2<3>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b); break;
@@ -545,20 +583,74 @@ QTTT_HD BothResult step_both(const State& s, uint32_t enew, const Luts& L, State
         case 5: sweep2<5>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b); break;
         case 6: sweep2<6>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b); break;
         case 7: sweep2<7>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b); break;
-        case 8: sweep2<8>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b, n == 8u ? (~C & M9) : ~0u); break;
+        case 8: sweep2<8>(x, y, z, Ra, Wa, A3a, Rb, Wb, A3b, r.n == 8u ? (~r.C & M9) : ~0u); break;
         default: break;
     }
-    const uint32_t colf = (Ra & b) != 0u ? 1u : 0u;                     // board.py:42
-    const uint32_t xa = x + enew * row.mx, ya = y + enew * row.my, za = z + enew * row.mz;   // board.py:19
-    const uint32_t inc = legal ? 1u : 0u;
+    r.colf = (Ra & b) != 0u ? 1u : 0u;                                  // board.py:42
+    r.enew = enew;
+    r.legal = legal ? 1u : 0u;
+    r.Ra = Ra; r.Wa = Wa; r.A3a = A3a; r.Rb = Rb; r.Wb = Wb; r.A3b = A3b;
+    return r;
+}
+
+QTTT_HD BothResult step_both(const State& s, uint32_t enew, const Luts& L, State& s0, State& s1) {
+    const BothSweep k = sweep_both<false>(s, enew, L);
+    const uint32_t xa = s.x + k.enew * k.row.mx, ya = s.y + k.enew * k.row.my, za = s.z + k.enew * k.row.mz;   // board.py:19
     BothResult r;
     uint32_t i0, i1;
-    r.classical0 = commit_outcome(s0, xa, ya, za, w, C, Ra, Wa, A3a, colf, inc, i0);
-    r.classical1 = commit_outcome(s1, xa, ya, za, w, C, Rb, Wb, A3b, colf, inc, i1);
-    r.n0 = n + i0;
-    r.n1 = n + i1;
-    r.illegal = legal ? 0u : 1u;
-    r.collapsed = colf;
+    r.classical0 = commit_outcome(s0, xa, ya, za, s.w, k.C, k.Ra, k.Wa, k.A3a, k.colf, k.legal, i0);
+    r.classical1 = commit_outcome(s1, xa, ya, za, s.w, k.C, k.Rb, k.Wb, k.A3b, k.colf, k.legal, i1);
+    r.n0 = k.n + i0;
+    r.n1 = k.n + i1;
+    r.illegal = k.legal ^ 1u;
+    r.collapsed = k.colf;
+    return r;
+}
+
+// One outcome's board as 9 nibbles (square s at bits 4s..4s+3; 0 = free, else move index + 1)
+// from its plane words: the sum over planes of spread(plane) << plane.  Nibbles never carry into
+// each other, so the two 32-bit halves are combined separately with multiply-adds (FMA pipe).
+struct alignas(8) Halves { uint32_t lo, hi; };
+template <bool kPlane3 = true>
+QTTT_HD uint64_t nibbles_of_planes(uint32_t p012, uint32_t p3, const Luts& L) {
+    const Halves* sp = reinterpret_cast<const Halves*>(L.spread);
+    const Halves s0 = sp[p012 & M9], s1 = sp[(p012 >> 9) & M9], s2 = sp[(p012 >> 18) & M9];
+    uint32_t lo = s0.lo + 2u * s1.lo + 4u * s2.lo;
+    uint32_t hi = s0.hi + 2u * s1.hi + 4u * s2.hi;
+    if (kPlane3) {
+        const Halves s3 = sp[p3 & M9];
+        lo += 8u * s3.lo;
+        hi += 8u * s3.hi;
+    }
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+
+// Both outcome BOARDS of one move and nothing else (config 3's shape): the successor states are
+// never assembled -- the plane words go straight from the sweep's accumulators to the nibble form.
+// Marks 8 and 9 (plane 3) and the autofill exist only from the eighth move on, so that part runs
+// only in warps holding such a game.
+struct BoardsBoth { uint64_t board0, board1; uint32_t collapsed; };
+template <bool kFullWarp = false>
+QTTT_HD BoardsBoth boards_both(const State& s, uint32_t enew, const Luts& L) {
+    const BothSweep k = sweep_both<kFullWarp>(s, enew, L);
+    BoardsBoth r;
+    r.collapsed = k.colf;
+    uint32_t cf = k.colf;
+#if defined(__CUDA_ARCH__)
+    asm("" : "+r"(cf));      // keep `x + y * cf` a multiply-add (FMA pipe) instead of a select and an add (ALU pipe)
+#endif
+    if (warp_any<kFullWarp>(k.n >= 7u)) {
+        const uint32_t p3 = plane3(s);
+        // the autofill (board.py:21-25) can only be the ninth mark: planes 0 and 3
+        const uint32_t fr0 = ~(k.C | k.Ra) & M9, fr1 = ~(k.C | k.Rb) & M9;
+        const uint32_t fs0 = ((k.colf != 0u) & (popc32(fr0) == 1)) ? fr0 : 0u;
+        const uint32_t fs1 = ((k.colf != 0u) & (popc32(fr1) == 1)) ? fr1 : 0u;
+        r.board0 = nibbles_of_planes<true>(s.w + k.Wa * cf + fs0, p3 + k.A3a * cf + fs0, L);
+        r.board1 = nibbles_of_planes<true>(s.w + k.Wb * cf + fs1, p3 + k.A3b * cf + fs1, L);
+    } else {
+        r.board0 = nibbles_of_planes<false>(s.w + k.Wa * cf, 0u, L);
+        r.board1 = nibbles_of_planes<false>(s.w + k.Wb * cf, 0u, L);
+    }
     return r;
 }
 
@@ -898,8 +990,7 @@ QTTT_HD State pack_game(const int8_t* classical_in, const int8_t* moves, const u
 }
 
 QTTT_HD uint64_t board_nibbles(const State& s, const Luts& L) {
-    return L.spread[plane0(s)] | (L.spread[plane1(s)] << 1) | (L.spread[plane2(s)] << 2) |
-           (L.spread[plane3(s)] << 3);
+    return nibbles_of_planes<true>(s.w, plane3(s), L);
 }
 
 // Both measurement outcomes of one (position, action): board.py:42-56 + qeval.py:5-51 twice,

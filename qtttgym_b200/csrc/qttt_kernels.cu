@@ -643,24 +643,30 @@ k_qeval_both(const qttt_state* __restrict__ state, const uint8_t* __restrict__ a
                    reinterpret_cast<State*>(next1), board0, board1, sq0, sq1, closes, result_prob, i);
 }
 
-// The config-3 shape of K3 -- both outcome boards and the closes flag, nothing else: the same
-// per-game function with the optional outputs known to be absent at compile time, so the
-// successor states are never assembled and no pointer is tested per game.
+// The config-3 shape of K3 -- both outcome boards and the closes flag, nothing else: the sweep's
+// plane accumulators go straight to the nibble boards (boards_both), the successor states are
+// never assembled.
 __global__ void __launch_bounds__(kThreads, 8)
 k_qeval_boards(const qttt_state* __restrict__ state, const uint8_t* __restrict__ action,
                uint64_t* __restrict__ board0, uint64_t* __restrict__ board1, uint8_t* __restrict__ closes,
-               int64_t n) {
+               uint32_t n, int iters) {
     __shared__ __align__(16) uint8_t smem[kLutQevalBytes];
     stage_luts(smem, kLutQevalBytes);
     const Luts L = luts_from_image(smem);
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-        const State s = load_state(state, i);
-        State t0, t1;
-        const BothResult r = step_both(s, (uint32_t)L.pair[action[i]], L, t0, t1);
-        board0[i] = board_nibbles(t0, L);
-        board1[i] = board_nibbles(t1, L);
-        closes[i] = (uint8_t)r.collapsed;
+    // a block owns `iters` consecutive chunks of 256 boards (32-bit indices: the host splits larger batches)
+    const uint32_t first = (blockIdx.x * (uint32_t)iters) * kThreads + threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+        const uint32_t i = first + (uint32_t)it * kThreads;
+        const bool valid = i < n;
+        // out-of-range lanes run on an empty game so that the warp votes inside stay full
+        const State s = valid ? load_state(state, i) : State{0u, 0u, 0u, 0u};
+        const uint32_t act = valid ? (uint32_t)action[i] : 255u;
+        const BoardsBoth r = boards_both<true>(s, (uint32_t)L.pair[act], L);
+        if (valid) {
+            board0[i] = r.board0;
+            board1[i] = r.board1;
+            closes[i] = (uint8_t)r.collapsed;
+        }
     }
 }
 
@@ -1391,7 +1397,14 @@ int qttt_qeval_both(const qttt_state* state, const uint8_t* action, qttt_state* 
         return QTTT_ERR_ALIGN;
     if (n == 0) return QTTT_OK;
     if (board0 && board1 && closes && !next0 && !next1 && !sq0 && !sq1 && !result_prob) {
-        k_qeval_boards<<<chunk_grid(n, iters_for(n, 8)), kThreads, 0, (cudaStream_t)stream>>>(state, action, board0, board1, closes, n);
+        // 32-bit indices inside the kernel: batches beyond 2^31 boards go slice by slice
+        const int64_t slice = (int64_t)1 << 30;
+        for (int64_t at = 0; at < n; at += slice) {
+            const int64_t m = n - at < slice ? n - at : slice;
+            const int iters = iters_for(m, 8);
+            k_qeval_boards<<<chunk_grid(m, iters), kThreads, 0, (cudaStream_t)stream>>>(
+                state + at, action + at, board0 + at, board1 + at, closes + at, (uint32_t)m, iters);
+        }
         return check_launch();
     }
     if (sq0 || sq1)

@@ -202,11 +202,13 @@ class EmuGames:
         o = dict(next0=np.empty((n, 4), np.uint32), next1=np.empty((n, 4), np.uint32),
                  board0=np.empty(n, np.uint64), board1=np.empty(n, np.uint64),
                  closes=np.empty(n, np.uint8), result_prob=np.empty((n, 3), np.float32))
+        if boards_only:
+            o = {k: o[k] for k in ("board0", "board1", "closes")}
         if squares:
             o.update(sq0=np.empty((n, 9), np.int8), sq1=np.empty((n, 9), np.int8))
-        self.lib.emu_qeval_both(_p(self.state), _p(ac), _p(o["next0"]), _p(o["next1"]),
+        self.lib.emu_qeval_both(_p(self.state), _p(ac), _p(o.get("next0")), _p(o.get("next1")),
                                 _p(o["board0"]), _p(o["board1"]), _p(o.get("sq0")), _p(o.get("sq1")),
-                                _p(o["closes"]), _p(o["result_prob"]), C.c_int64(n))
+                                _p(o["closes"]), _p(o.get("result_prob")), C.c_int64(n))
         return o
 
     def rollout(self, n_rollouts, seed):

@@ -133,8 +133,18 @@ int emu_qeval_both(const State* state, const uint8_t* action, State* next0, Stat
                    uint64_t* board0, uint64_t* board1, int8_t* sq0, int8_t* sq1, uint8_t* closes,
                    float* result_prob, int64_t n) {
     const Luts L = luts();
+    // the same dispatch as qttt_qeval_both: boards only / per-move squares wanted or not
+    if (board0 && board1 && closes && !next0 && !next1 && !sq0 && !sq1 && !result_prob) {
+        for (int64_t i = 0; i < n; ++i) {
+            const BoardsBoth r = boards_both(state[i], (uint32_t)L.pair[action[i]], L);
+            board0[i] = r.board0;
+            board1[i] = r.board1;
+            closes[i] = (uint8_t)r.collapsed;
+        }
+        return 0;
+    }
     for (int64_t i = 0; i < n; ++i) {
-        if (sq0 || sq1)      // the same dispatch as qttt_qeval_both: per-move squares wanted or not
+        if (sq0 || sq1)
             qeval_game<true>(state[i], action[i], L, next0, next1, board0, board1, sq0, sq1, closes,
                              result_prob, i);
         else
