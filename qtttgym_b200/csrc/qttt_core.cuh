@@ -310,6 +310,20 @@ QTTT_HD void sweep(uint32_t x, uint32_t y, uint32_t z, uint32_t& R, uint32_t& W,
         }
         if (N > 0) absorb<0>(E0, R, W, A3);
     } else {
+        // More slots: passes until nothing changes.  32 games together practically never finish in
+        // fewer than 4 passes with 6 or 7 slots (2 with 8, where the spanning-tree stop applies), so
+        // the first passes run without the test.
+#pragma unroll
+        for (int p = 0; p < (N == 8 ? 1 : 3); ++p) {
+            absorb<0>(E0, R, W, A3);
+            absorb<1>(E1, R, W, A3);
+            absorb<2>(E2, R, W, A3);
+            absorb<3>(E3, R, W, A3);
+            absorb<4>(E4, R, W, A3);
+            absorb<5>(E5, R, W, A3);
+            if (N > 6) absorb<6>(E6, R, W, A3);
+            if (N > 7) absorb<7>(E7, R, W, A3);
+        }
         uint32_t before;
         do {
             before = R;
@@ -357,6 +371,7 @@ QTTT_HD void sweep2(uint32_t x, uint32_t y, uint32_t z, uint32_t& Ra, uint32_t& 
         }
         if (N > 0) { absorb<0>(E0, Ra, Wa, A3a); absorb<0>(E0, Rb, Wb, A3b); }
     } else {
+        // (running the first passes without the test, as sweep<N> does, measured 5-12 % slower here)
         uint32_t before;
         do {
             before = Ra + (Rb << 9);
