@@ -16,6 +16,53 @@ namespace qttt {
 
 __device__ __align__(128) const LutImage g_lut = make_lut_image();
 
+// Tables of the observation kernel only (k_observe): byte selectors that compact the codes of
+// the uncollapsed move slots of one player into q_states_p1 / q_states_p2 (env.py:73-78).
+struct ObsLutImage {
+    uint32_t q1sel[32][4];   // which of the slots 0,2,4,6,8 are uncollapsed -> selA0, selB0, selA1, selB1
+    uint32_t q2sel[16][4];   // the same for slots 1,3,5,7: two selectors and two padding masks
+};
+constexpr int kObsLutBytes = (int)sizeof(ObsLutImage);
+static_assert(kObsLutBytes == 768, "ObsLutImage layout");
+constexpr ObsLutImage make_obs_lut() {
+    ObsLutImage t{};
+    // q_states_p1: five candidate codes k0..k4 live in bytes 0..9 of (S0, S1, S2) and bytes 10..11
+    // of S2 hold the (-1, -1) padding.  Word w of the list is PRMT(PRMT(S0, S1, selA), S2, selB).
+    for (uint32_t m = 0; m < 32; ++m) {
+        int idx[5] = {5, 5, 5, 5, 5}, cnt = 0;            // 5 = the padding entry
+        for (int j = 0; j < 5; ++j)
+            if (m >> j & 1u) idx[cnt++] = j;
+        for (int w = 0; w < 2; ++w) {
+            uint32_t selA = 0, selB = 0;
+            for (int p = 0; p < 4; ++p) {
+                const int src = 2 * idx[2 * w + p / 2] + (p & 1);          // byte 0..11
+                if (src < 8) { selA |= (uint32_t)src << (4 * p); selB |= (uint32_t)p << (4 * p); }
+                else selB |= (uint32_t)(src - 8 + 4) << (4 * p);
+            }
+            t.q1sel[m][2 * w] = selA;
+            t.q1sel[m][2 * w + 1] = selB;
+        }
+    }
+    // q_states_p2: four candidates in (S0, S1); word w = PRMT(S0, S1, sel[w]) | pad[w]
+    for (uint32_t m = 0; m < 16; ++m) {
+        int idx[4] = {4, 4, 4, 4}, cnt = 0;
+        for (int j = 0; j < 4; ++j)
+            if (m >> j & 1u) idx[cnt++] = j;
+        for (int w = 0; w < 2; ++w) {
+            uint32_t sel = 0, pad = 0;
+            for (int p = 0; p < 4; ++p) {
+                const int e = idx[2 * w + p / 2];
+                if (e < 4) sel |= (uint32_t)(2 * e + (p & 1)) << (4 * p);
+                else pad |= 0xFFu << (8 * p);
+            }
+            t.q2sel[m][w] = sel;
+            t.q2sel[m][2 + w] = pad;
+        }
+    }
+    return t;
+}
+__device__ __align__(128) const ObsLutImage g_obs_lut = make_obs_lut();
+
 constexpr int kThreads = 256;
 
 // Stage the first `bytes` of the table image into shared memory: ONE bulk asynchronous copy
@@ -23,16 +70,22 @@ constexpr int kThreads = 256;
 // mbarrier) issued by thread 0, instead of every thread looping over 16-byte loads and stores.
 // With blocks that live for only a few chunks of games the staging is paid often, and as a
 // loop it was ~90 instructions per thread per block.
-__device__ __forceinline__ void stage_luts(uint8_t* smem, int bytes) {
+__device__ __forceinline__ void stage_luts(uint8_t* smem, int bytes, uint8_t* smem2 = nullptr,
+                                           const void* src2 = nullptr, int bytes2 = 0) {
     __shared__ __align__(8) uint64_t bar;
     const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
     const uint32_t dst_a = (uint32_t)__cvta_generic_to_shared(smem);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes + bytes2) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(dst_a), "l"(&g_lut), "r"(bytes), "r"(bar_a) : "memory");
+        if (smem2) {      // a second table image on the same barrier
+            const uint32_t dst2_a = (uint32_t)__cvta_generic_to_shared(smem2);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst2_a), "l"(src2), "r"(bytes2), "r"(bar_a) : "memory");
+        }
     }
     __syncthreads();                  // the barrier object is initialised for everybody
     uint32_t done = 0;                // every thread observes the completion itself: that is what
@@ -261,114 +314,184 @@ __device__ __forceinline__ void copy_out(const uint8_t* sm, void* dst, int64_t b
     }
 }
 
-// One move slot of the observation: Board.moves[T] and, when the move is uncollapsed, its entry
-// in q_states_p1 / q_states_p2 (env.py:73-78).  T is a compile-time slot.
-template <int T>
-__device__ __forceinline__ void observe_move(const State& s, uint32_t nm, uint32_t C, int8_t* moves,
-                                             int8_t* q1, int8_t* q2, int& c1, int& c2) {
-    const uint32_t E = edge<T>(s);
-    const bool present = ((uint32_t)T < nm) & (E != 0u);
-    const int a = present ? ctz32(E) : -1, b = present ? flo32(E) : -1;
-    if (moves) { moves[2 * T] = (int8_t)a; moves[2 * T + 1] = (int8_t)b; }
-    if (present && !(E & C)) {
-        if (T & 1) { if (q2 && c2 < 4) { q2[2 * c2] = (int8_t)a; q2[2 * c2 + 1] = (int8_t)b; } ++c2; }
-        else       { if (q1 && c1 < 5) { q1[2 * c1] = (int8_t)a; q1[2 * c1 + 1] = (int8_t)b; } ++c1; }
-    }
+// Env._observation & co. (env.py:68-85, mcts.py:52-65,87-91) for one game.  The kernel moves a
+// few odd-sized rows per game through shared memory, so shared-memory wavefronts are its scarce
+// resource (ncu: the LSU data pipe at 90 % with table-driven decoding): the decode below is
+// arithmetic, the only tables are two tiny selector tables.
+//   classical      the four 8-bit planes are transposed into eight 4-bit values with two delta
+//                  swaps, widened to bytes, and 1 is subtracted bytewise (free -> -1)
+//   moves          per slot a 16-bit code a | b << 8 from two find-first-set instructions
+//                  (both give -1 on an empty slot; the autofill entry has a == b)
+//   q_states_p1/2  the codes of the uncollapsed slots of each player, compacted by PRMT with
+//                  selectors looked up from the 5-bit / 4-bit "which slots are live" mask
+// Outputs whose per-game size keeps them aligned (q_states_p2, rounds, reward, the one-byte ones)
+// go straight to global memory, coalesced; the odd-sized rows (9, 18, 10, 36 bytes) are staged in
+// shared memory and written out with 16-byte stores.  A slot at or beyond len(moves) is empty in
+// every state this library produces, so len(moves) is not consulted per slot.  (The host emulation
+// keeps the plain form, observe_game; the GPU tests diff this one against the oracle on every
+// output after every ply.)
+struct ObsOut {
+    int8_t* classical; int8_t* moves; uint8_t* nmoves; int8_t* q1; int8_t* q2; uint8_t* turn;
+    int8_t* rounds; float* reward_p1; uint8_t* winner; uint8_t* mask_bool;
+};
+// Which outputs a launch writes, known at compile time for the two common requests so that no
+// pointer is tested per game: the env.py observation (classical, q_states_p1/2, turn), everything,
+// or (kObsAny) whatever is non-null.
+enum { kObsAny = 0, kObsEnv = 1, kObsAll = 2 };
+template <int kSet> __device__ __forceinline__ bool obs_has(const void* p, bool in_env_set) {
+    return kSet == kObsAny ? p != nullptr : (kSet == kObsAll || in_env_set);
 }
-
-// Device form of observe_game (qttt_core.cuh) writing one game's rows of the staging buffers:
-// same values, with compile-time move slots, word stores for the bool mask and the q-list
-// padding.  (The host emulation keeps the plain form; GPU tests diff this one against the
-// oracle on every output after every ply.)
-__device__ __forceinline__ void observe_row(const State& s, const Luts& L, int8_t* cl, int8_t* moves,
-                                            uint8_t* nmoves, int8_t* q1, int8_t* q2, uint8_t* turn,
-                                            int8_t* rounds, float* reward_p1, uint8_t* winner,
-                                            uint8_t* mask_bool) {
-    const uint32_t P0 = plane0(s), P1 = plane1(s), P2 = plane2(s), P3 = plane3(s);
-    const uint32_t C = P0 | P1 | P2 | P3;
+__device__ __forceinline__ uint32_t bfind32(uint32_t v) {      // index of the highest set bit, 0xFFFFFFFF for 0
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {   // PRMT, selector used as is
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+// bytes (a, b, ?, ?) of one move slot: a = lowest, b = highest square of E, both -1 when E == 0
+__device__ __forceinline__ uint32_t move_code(uint32_t E) {
+    return prmt(bfind32(E & (0u - E)), bfind32(E), 0x0040u);
+}
+// m += bit when the slot still has a free square, i.e. the move is uncollapsed (env.py:73-78):
+// one LOP3 with a predicate output and one predicated add
+__device__ __forceinline__ void add_if_live(uint32_t& m, uint32_t E, uint32_t free_sq, uint32_t bit) {
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 h;\n\t"
+        "and.b32 h, %1, %2;\n\t"
+        "setp.ne.u32 p, h, 0;\n\t"
+        "@p add.u32 %0, %0, %3;\n\t}"
+        : "+r"(m) : "r"(E), "r"(free_sq), "r"(bit));
+}
+template <int kSet>
+__device__ __forceinline__ void observe_row(const State& s, const Luts& L, const ObsLutImage* O, const ObsOut& o,
+                                            int64_t i, int t, uint8_t* st_cl, uint8_t* st_moves,
+                                            uint8_t* st_q1, uint8_t* st_mask) {
+    const uint32_t P3 = plane3(s);
+    const uint32_t C = plane0(s) | plane1(s) | plane2(s) | P3;
     const uint32_t nm = n_moves(s);
-    if (cl) {
-#pragma unroll
-        for (int sq = 0; sq < 9; ++sq) cl[sq] = (int8_t)board_value(P0, P1, P2, P3, sq);
+    if (obs_has<kSet>(o.nmoves, false)) o.nmoves[i] = (uint8_t)nm;
+    if (obs_has<kSet>(o.turn, true)) o.turn[i] = (uint8_t)(nm & 1u);          // env.py:83
+    if (obs_has<kSet>(o.classical, true)) {
+        // M: byte r = squares 0..7 of plane r.  Swapping index bits (0 <-> 3) and (1 <-> 4) leaves
+        // square k in the low nibble of byte k (k < 4) and square k + 4 in its high nibble.
+        uint32_t M = prmt(prmt(s.w, s.w >> 9, 0x0040u), prmt(s.w >> 18, P3, 0x0040u), 0x5410u);
+        uint32_t d = ((M >> 7) ^ M) & 0x00AA00AAu;
+        M ^= d ^ (d << 7);
+        d = ((M >> 14) ^ M) & 0x0000CCCCu;
+        M ^= d ^ (d << 14);
+        // value = move index + 1, 0 = free; byte = value - 1: add 0x7F and flip the top bit (no carries)
+        const uint32_t w0 = ((M & 0x0F0F0F0Fu) + 0x7F7F7F7Fu) ^ 0x80808080u;
+        const uint32_t w1 = (((M >> 4) & 0x0F0F0F0Fu) + 0x7F7F7F7Fu) ^ 0x80808080u;
+        const uint32_t v8 = ((s.w >> 8) & 1u) | ((s.w >> 16) & 2u) | ((s.w >> 24) & 4u) | ((P3 >> 5) & 8u);
+        uint8_t* r = st_cl + 9 * t;
+        r[0] = (uint8_t)w0; r[1] = (uint8_t)(w0 >> 8); r[2] = (uint8_t)(w0 >> 16); r[3] = (uint8_t)(w0 >> 24);
+        r[4] = (uint8_t)w1; r[5] = (uint8_t)(w1 >> 8); r[6] = (uint8_t)(w1 >> 16); r[7] = (uint8_t)(w1 >> 24);
+        r[8] = (uint8_t)(v8 - 1u);
     }
-    if (nmoves) *nmoves = (uint8_t)nm;
-    if (turn) *turn = (uint8_t)(nm & 1u);                                     // env.py:83
-    if (q1) {
+    const bool has_moves = obs_has<kSet>(o.moves, false), has_q1 = obs_has<kSet>(o.q1, true);
+    const bool has_q2 = obs_has<kSet>(o.q2, true);
+    if (has_moves || has_q1 || has_q2) {
+        const uint32_t free_sq = ~C;
+        uint32_t k[9], m1 = 0u, m2 = 0u;
+#define QTTT_OBS_SLOT(T)                                                                 \
+        {                                                                                \
+            const uint32_t E = slot<T>(s.x, s.y, s.z);                                   \
+            k[T] = move_code(E);                                                         \
+            add_if_live(((T) & 1) ? m2 : m1, E, free_sq, 1u << ((T) >> 1));              \
+        }
+        QTTT_OBS_SLOT(0) QTTT_OBS_SLOT(1) QTTT_OBS_SLOT(2) QTTT_OBS_SLOT(3) QTTT_OBS_SLOT(4)
+        QTTT_OBS_SLOT(5) QTTT_OBS_SLOT(6) QTTT_OBS_SLOT(7) QTTT_OBS_SLOT(8)
+#undef QTTT_OBS_SLOT
+        if (has_moves) {
+            uint16_t* r = reinterpret_cast<uint16_t*>(st_moves + 18 * t);
 #pragma unroll
-        for (int k = 0; k < 5; ++k) reinterpret_cast<uint16_t*>(q1)[k] = 0xFFFFu;   // (-1, -1) padding
+            for (int T = 0; T < 9; ++T) r[T] = (uint16_t)k[T];
+        }
+        if (has_q1) {
+            const uint32_t S0 = prmt(k[0], k[2], 0x5410u), S1 = prmt(k[4], k[6], 0x5410u);
+            const uint32_t S2 = prmt(k[8], 0xFFFFFFFFu, 0x7610u);               // the last code, then the padding
+            const uint4 sel = *reinterpret_cast<const uint4*>(O->q1sel[m1]);
+            const uint32_t w0 = prmt(prmt(S0, S1, sel.x), S2, sel.y);
+            const uint32_t w1 = prmt(prmt(S0, S1, sel.z), S2, sel.w);
+            uint16_t* r = reinterpret_cast<uint16_t*>(st_q1 + 10 * t);
+            r[0] = (uint16_t)w0; r[1] = (uint16_t)(w0 >> 16);
+            r[2] = (uint16_t)w1; r[3] = (uint16_t)(w1 >> 16);
+            r[4] = (uint16_t)(m1 == 31u ? k[8] : 0xFFFFu);
+        }
+        if (has_q2) {
+            const uint32_t S0 = prmt(k[1], k[3], 0x5410u), S1 = prmt(k[5], k[7], 0x5410u);
+            const uint4 sel = *reinterpret_cast<const uint4*>(O->q2sel[m2]);
+            reinterpret_cast<uint2*>(o.q2)[i] =
+                make_uint2(prmt(S0, S1, sel.x) | sel.z, prmt(S0, S1, sel.y) | sel.w);
+        }
     }
-    if (q2) *reinterpret_cast<uint2*>(q2) = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-    int c1 = 0, c2 = 0;
-    observe_move<0>(s, nm, C, moves, q1, q2, c1, c2); observe_move<1>(s, nm, C, moves, q1, q2, c1, c2);
-    observe_move<2>(s, nm, C, moves, q1, q2, c1, c2); observe_move<3>(s, nm, C, moves, q1, q2, c1, c2);
-    observe_move<4>(s, nm, C, moves, q1, q2, c1, c2); observe_move<5>(s, nm, C, moves, q1, q2, c1, c2);
-    observe_move<6>(s, nm, C, moves, q1, q2, c1, c2); observe_move<7>(s, nm, C, moves, q1, q2, c1, c2);
-    observe_move<8>(s, nm, C, moves, q1, q2, c1, c2);
-    if (rounds || reward_p1 || winner) {
+    const bool has_rounds = obs_has<kSet>(o.rounds, false), has_reward = obs_has<kSet>(o.reward_p1, false);
+    const bool has_winner = obs_has<kSet>(o.winner, false);
+    if (has_rounds || has_reward || has_winner) {
         int px, po;
         win_rounds(s, L, px, po);
-        if (rounds) { rounds[0] = (int8_t)px; rounds[1] = (int8_t)po; }
-        if (reward_p1) {                                                      // env.py:87-112
+        if (has_rounds) reinterpret_cast<uint16_t*>(o.rounds)[i] = (uint16_t)((uint32_t)(px & 255) | ((uint32_t)(po & 255) << 8));
+        if (has_reward) {                                                       // env.py:87-112
             const int a = px < 0 ? 10 : px, b = po < 0 ? 10 : po;
-            *reward_p1 = a < b ? 1.0f : (b < a ? -1.0f : 0.0f);
+            o.reward_p1[i] = a < b ? 1.0f : (b < a ? -1.0f : 0.0f);
         }
-        if (winner) *winner = (uint8_t)winner_of(px, po);                     // mcts.py:52-65
+        if (has_winner) o.winner[i] = (uint8_t)winner_of(px, po);               // mcts.py:52-65
     }
-    if (mask_bool) {                                                          // mcts.py:87-91
+    if (obs_has<kSet>(o.mask_bool, false)) {                                    // mcts.py:87-91
         const uint64_t lm = L.legal[~C & M9];
-        uint32_t* w = reinterpret_cast<uint32_t*>(mask_bool);
+        uint32_t* w = reinterpret_cast<uint32_t*>(st_mask + 36 * t);
 #pragma unroll
-        for (int k = 0; k < 9; ++k)       // 4 mask bits -> 4 bool bytes: (bits * 0x204081) & 0x01010101
-            w[k] = (((uint32_t)(lm >> (4 * k)) & 15u) * 0x00204081u) & 0x01010101u;
+        for (int q = 0; q < 9; ++q)       // 4 mask bits -> 4 bool bytes: (bits * 0x204081) & 0x01010101
+            w[q] = (((uint32_t)(lm >> (4 * q)) & 15u) * 0x00204081u) & 0x01010101u;
     }
 }
 
-// Env._observation & co. for n games.  Every output is a few BYTES per game at an odd stride
-// (9, 18, 10, 8, 36 ...), so each block of 256 games is decoded into shared memory first and
-// then written out with coalesced 16-byte stores.
+// A full chunk of 256 staged rows to global memory, 16 bytes per store (the destination of a
+// full chunk is 16-byte aligned when the array is: 256 * kBytesPerGame is a multiple of 16).
+template <int kBytesPerGame>
+__device__ __forceinline__ void copy_out_full(const uint8_t* sm, void* dst, int64_t block_start) {
+    const uint4* s16 = reinterpret_cast<const uint4*>(sm);
+    uint4* g16 = reinterpret_cast<uint4*>(static_cast<uint8_t*>(dst) + block_start * kBytesPerGame);
+#pragma unroll
+    for (int v = 0; v < (kBytesPerGame + 15) / 16; ++v) {
+        const int at = v * kThreads + (int)threadIdx.x;
+        if (kBytesPerGame % 16 == 0 || at < kThreads * kBytesPerGame / 16) g16[at] = s16[at];
+    }
+}
+
+template <int kSet>
 __global__ void __launch_bounds__(kThreads)
-k_observe(const qttt_state* __restrict__ state, int8_t* __restrict__ classical_out,
-          int8_t* __restrict__ moves, uint8_t* __restrict__ nmoves, int8_t* __restrict__ q1,
-          int8_t* __restrict__ q2, uint8_t* __restrict__ turn, int8_t* __restrict__ rounds,
-          float* __restrict__ reward_p1, uint8_t* __restrict__ winner,
-          uint8_t* __restrict__ mask_bool, int64_t n) {
+k_observe(const qttt_state* __restrict__ state, const ObsOut o, int64_t n, bool aligned16) {
     __shared__ __align__(16) uint8_t smem[kLutStepBytes];
+    __shared__ __align__(16) uint8_t smem_obs[kObsLutBytes];
     __shared__ __align__(16) uint8_t st_classical[kThreads * 9];
-    __shared__ __align__(16) uint8_t st_moves[kThreads * 18];
+    __shared__ __align__(16) uint8_t st_moves[kSet == kObsEnv ? 16 : kThreads * 18];
     __shared__ __align__(16) uint8_t st_q1[kThreads * 10];
-    __shared__ __align__(16) uint8_t st_q2[kThreads * 8];
-    __shared__ __align__(16) uint8_t st_mask[kThreads * 36];
-    __shared__ __align__(16) uint8_t st_rounds[kThreads * 2];
-    __shared__ __align__(16) float   st_reward[kThreads];
-    __shared__ __align__(16) uint8_t st_n[kThreads], st_turn[kThreads], st_winner[kThreads];
-    stage_luts(smem, kLutStepBytes);
+    __shared__ __align__(16) uint8_t st_mask[kSet == kObsEnv ? 16 : kThreads * 36];
+    stage_luts(smem, kLutStepBytes, smem_obs, &g_obs_lut, kObsLutBytes);
     const Luts L = luts_from_image(smem);
+    const ObsLutImage* O = reinterpret_cast<const ObsLutImage*>(smem_obs);
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     for (int64_t block_start = (int64_t)blockIdx.x * kThreads; block_start < n; block_start += stride) {
         const int valid = (int)((n - block_start) < kThreads ? (n - block_start) : kThreads);
         const int t = threadIdx.x;
         if (t < valid)
-            observe_row(load_state(state, block_start + t), L,
-                        classical_out ? reinterpret_cast<int8_t*>(st_classical) + 9 * t : nullptr,
-                        moves ? reinterpret_cast<int8_t*>(st_moves) + 18 * t : nullptr,
-                        nmoves ? st_n + t : nullptr,
-                        q1 ? reinterpret_cast<int8_t*>(st_q1) + 10 * t : nullptr,
-                        q2 ? reinterpret_cast<int8_t*>(st_q2) + 8 * t : nullptr,
-                        turn ? st_turn + t : nullptr,
-                        rounds ? reinterpret_cast<int8_t*>(st_rounds) + 2 * t : nullptr,
-                        reward_p1 ? st_reward + t : nullptr, winner ? st_winner + t : nullptr,
-                        mask_bool ? st_mask + 36 * t : nullptr);
+            observe_row<kSet>(load_state(state, block_start + t), L, O, o, block_start + t, t,
+                              st_classical, st_moves, st_q1, st_mask);
         __syncthreads();
-        copy_out<9>(st_classical, classical_out, block_start, valid);
-        copy_out<18>(st_moves, moves, block_start, valid);
-        copy_out<1>(st_n, nmoves, block_start, valid);
-        copy_out<10>(st_q1, q1, block_start, valid);
-        copy_out<8>(st_q2, q2, block_start, valid);
-        copy_out<1>(st_turn, turn, block_start, valid);
-        copy_out<2>(st_rounds, rounds, block_start, valid);
-        copy_out<4>(reinterpret_cast<const uint8_t*>(st_reward), reward_p1, block_start, valid);
-        copy_out<1>(st_winner, winner, block_start, valid);
-        copy_out<36>(st_mask, mask_bool, block_start, valid);
+        if (valid == kThreads && aligned16) {
+            if (obs_has<kSet>(o.classical, true)) copy_out_full<9>(st_classical, o.classical, block_start);
+            if (obs_has<kSet>(o.moves, false)) copy_out_full<18>(st_moves, o.moves, block_start);
+            if (obs_has<kSet>(o.q1, true)) copy_out_full<10>(st_q1, o.q1, block_start);
+            if (obs_has<kSet>(o.mask_bool, false)) copy_out_full<36>(st_mask, o.mask_bool, block_start);
+        } else {
+            copy_out<9>(st_classical, o.classical, block_start, valid);
+            if (kSet != kObsEnv) copy_out<18>(st_moves, o.moves, block_start, valid);
+            copy_out<10>(st_q1, o.q1, block_start, valid);
+            if (kSet != kObsEnv) copy_out<36>(st_mask, o.mask_bool, block_start, valid);
+        }
         __syncthreads();
     }
 }
@@ -1245,9 +1368,22 @@ int qttt_observe(const qttt_state* state, int8_t* classical, int8_t* moves, uint
                  uint8_t* winner, uint8_t* mask_bool, int64_t n, void* stream) {
     if (n == 0) return QTTT_OK;
     if (!state || n < 0) return QTTT_ERR_ARG;
-    if (misaligned(state, 16) || misaligned(reward_p1, 4)) return QTTT_ERR_ALIGN;
-    if (n == 0) return QTTT_OK;
-    k_observe<<<chunk_grid(n, iters_for(n, 4)), kThreads, 0, (cudaStream_t)stream>>>(state, classical, moves, n_moves, q_p1, q_p2, turn, rounds, reward_p1, winner, mask_bool, n);
+    if (misaligned(state, 16) || misaligned(reward_p1, 4) || misaligned(q_p2, 8) || misaligned(rounds, 2))
+        return QTTT_ERR_ALIGN;
+    const ObsOut o{classical, moves, n_moves, q_p1, q_p2, turn, rounds, reward_p1, winner, mask_bool};
+    // the staged rows leave with 16-byte stores when every staged array starts on a 16-byte boundary
+    const bool aligned16 = !(misaligned(classical, 16) || misaligned(moves, 16) || misaligned(q_p1, 16) ||
+                             misaligned(mask_bool, 16));
+    const bool env_set = classical && q_p1 && q_p2 && turn;
+    const bool extras = moves || n_moves || rounds || reward_p1 || winner || mask_bool;
+    const bool all_set = env_set && moves && n_moves && rounds && reward_p1 && winner && mask_bool;
+    const int grid = chunk_grid(n, iters_for(n, 4));
+    if (all_set)
+        k_observe<kObsAll><<<grid, kThreads, 0, (cudaStream_t)stream>>>(state, o, n, aligned16);
+    else if (env_set && !extras)
+        k_observe<kObsEnv><<<grid, kThreads, 0, (cudaStream_t)stream>>>(state, o, n, aligned16);
+    else
+        k_observe<kObsAny><<<grid, kThreads, 0, (cudaStream_t)stream>>>(state, o, n, aligned16);
     return check_launch();
 }
 
