@@ -104,7 +104,7 @@ def kernels(tag):
                 what, alg = (("k_step_packed ply 4", 35 * (acc[4] if acc else E)) if "zc" not in name else
                              ("k_step_packed_zc ply 4 (kernel reads/writes mapped pinned host memory)", None))
             elif part == "step" and name.startswith("k_step<"):
-                if ", 1, 0>" in name.replace(" ", "").replace(",", ", ") and "k_step<0, 0, 1, 1" in name:
+                if "k_step<0, 0, 1, 1" in name:
                     what, alg = "k_step ply 0 (reset fused in)", (31 * acc[0] if acc else None)
                 elif "k_step<0, 0, 1, 0" in name:
                     ply = k + 1
@@ -125,7 +125,8 @@ def kernels(tag):
                 n = E if k < 2 else (1 << 20)
                 what, alg = f"{name.split(chr(60))[0]} {n} boards", 33 * n
             elif name.startswith("k_observe"):
-                what, alg = ("k_observe all outputs" if k < 2 else "k_observe env.py outputs"), E * (16 + (90 if k < 2 else 28))
+                everything = "<2>" in name or (chr(60) not in name and k < 2)
+                what, alg = ("k_observe all outputs" if everything else "k_observe env.py outputs"), E * (16 + (90 if everything else 28))
             elif name.startswith("k_features"):
                 what, alg = "k_features 2^20", (1 << 20) * 736
             elif name.startswith("k_get_mask"):
