@@ -191,7 +191,10 @@ QTTT_API int qttt_step_random_ex(qttt_state* state, uint64_t seed, uint64_t game
  *   rounds    int8[n][2]    check_win() -> (p1_round, p2_round)
  *   reward_p1 float[n]      Env._reward()
  *   winner    uint8[n]      0 none/draw, 1 X, 2 O (mcts.py:52-65)
- *   mask_bool uint8[n][36]  GameState.action_mask() */
+ *   mask_bool uint8[n][36]  GameState.action_mask()
+ * Alignment: q_p2 8 bytes, reward_p1 4, rounds 2 (QTTT_ERR_ALIGN otherwise); the other arrays any,
+ * 16 bytes for the fast path.  Three specialisations are dispatched on which outputs are non-NULL:
+ * exactly {classical, q_p1, q_p2, turn} (the env.py observation), every output, anything else. */
 QTTT_API int qttt_observe(const qttt_state* state, int8_t* classical, int8_t* moves, uint8_t* n_moves,
                  int8_t* q_p1, int8_t* q_p2, uint8_t* turn, int8_t* rounds, float* reward_p1,
                  uint8_t* winner, uint8_t* mask_bool, int64_t n, void* stream);

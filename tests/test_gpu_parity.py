@@ -274,6 +274,45 @@ def test_error_codes(cuda):
     torch.cuda.synchronize()
 
 
+def test_observe_output_subsets_and_alignment(cuda):
+    """qttt_observe dispatches on the set of outputs and on their alignment: every path gives
+    the same bytes (mid-game states incl. collapses, a size that is not a multiple of 256)."""
+    import torch
+    import qtttgym_b200 as Q
+    import qtttgym_b200._lib as L
+    n = 3 * 256 + 77
+    env = Q.BatchedEnv(n, seed=17)
+    for _ in range(6):
+        env.step_random()
+    full = Q.observe_states(env.state, extras=True)                # every output, aligned
+    lean = Q.observe_states(env.state)                             # the env.py set
+    for k in lean:
+        assert torch.equal(lean[k], full[k]), k
+    # outputs that start one row late: odd byte offsets, the byte-granular copy-out
+    off = {k: torch.zeros((n + 1,) + tuple(v.shape[1:]), dtype=torch.uint8 if v.dtype == torch.bool else v.dtype,
+                          device=v.device)[1:] for k, v in full.items()}
+    got = Q.observe_states(env.state, extras=True, out=off)
+    for k, v in full.items():
+        assert torch.equal(got[k].to(v.dtype), v), k
+    off2 = {k: off[k] for k in lean}
+    got2 = Q.observe_states(env.state, out=off2)
+    for k in lean:
+        assert torch.equal(got2[k], full[k]), k
+    # single outputs (the generic specialisation)
+    assert torch.equal(env.turn(), full["n_moves"])
+    assert torch.equal(env.action_mask(), full["action_mask"])
+    assert torch.equal(env.reward_p1(), full["reward_p1"])
+    assert torch.equal(env.winner(), full["winner"])
+    # q_states_p2 and rounds are written with 8- / 2-byte stores
+    lib = L.lib()
+    buf = torch.zeros(16 * n + 64, dtype=torch.uint8, device="cuda")
+    none = [None] * 4
+    assert lib.qttt_observe(env.state.data_ptr(), None, None, None, None, buf.data_ptr() + 4, *none, None, n, None) == -2
+    assert lib.qttt_observe(env.state.data_ptr(), None, None, None, None, None, None, buf.data_ptr() + 1,
+                            None, None, None, n, None) == -2
+    torch.cuda.synchronize()
+
+
 def test_step_host_equals_step(cuda):
     """The end-to-end entry (pinned host buffers, chunk-pipelined) gives the same results."""
     import torch
