@@ -282,6 +282,7 @@ template <int I> QTTT_HD uint32_t slot(uint32_t x, uint32_t y, uint32_t z) {
 }
 
 constexpr int kFixedSweepMax = 5;   // up to this many slots the sweep runs a fixed schedule (below)
+static_assert(kFixedSweepMax <= 5, "the fixed schedules of sweep / sweep2 list slots 0..4");
 
 // Forward sweeps over move slots 0..N-1 until the reached set stops growing.
 // `stop`: a set R cannot grow beyond, or ~0 when none is known.  With 8 moves on the board the
