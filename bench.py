@@ -441,19 +441,27 @@ def run_b200(args):
                 "inside the launch, so every lane plays every step; 9 launches as one CUDA graph; 47 B per step"}
     del mix, dg, d_start, d_final, d_act, d_coin
 
-    # ---- step + full observation in the timed region (obs_mode='full': classical, q lists, turn)
+    # ---- step + full observation in the timed region (classical, q lists, turn after every ply):
+    #      the fused launch (qttt_step_obs) and, beside it, step followed by qttt_observe
     obs_env = Q.BatchedEnv(E, device=dev, seed=seed, game_base=rank * E)
     obs_buf = obs_env.observation()
 
-    def obs_pass():
+    def obs_pass_two_launches():
         for ply in range(PLIES):
             (obs_env.reset_step if ply == 0 else obs_env.step)(actions[ply], coins[ply])
             obs_env.observation(out=obs_buf)
+
+    def obs_pass():
+        for ply in range(PLIES):
+            obs_env.step_obs(actions[ply], coins[ply], out=obs_buf, fresh=(ply == 0))
+    ms2 = timed(obs_pass_two_launches, 3)
     ms = timed(obs_pass, 3)
     extra["value_with_observation"] = {
         "env_steps_per_s": total_steps_pass / (ms * 1e-3), "ms_per_pass": ms,
-        "note": "the same pass with qttt_observe (env.py:68-85 tensors: classical int8[N,9], q_states_p1/p2, turn) "
-                "after every step, i.e. what the reference's Env.step returns as obs, decoded on the device"}
+        "env_steps_per_s_step_then_observe": total_steps_pass / (ms2 * 1e-3), "ms_per_pass_step_then_observe": ms2,
+        "note": "the same pass through BatchedEnv.step_obs (qttt_step_obs: Env.step and the env.py:68-85 tensors "
+                "classical int8[N,9], q_states_p1/p2, turn of the new state from one launch), i.e. what the "
+                "reference's Env.step returns as obs, decoded on the device; beside it step + qttt_observe"}
     del obs_env, obs_buf
 
     # ---- e2e: host buffers through the public API, copies inside the timed region

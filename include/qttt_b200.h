@@ -247,6 +247,16 @@ QTTT_API int qttt_step_features(qttt_state* state, const void* action, int actio
                                 uint8_t* status, float* features, uint8_t* illegal_mask, int64_t n,
                                 void* stream);
 
+/* qttt_step_ex fused with the env.py observation of the NEW state (what Env.step returns as obs,
+ * qtttgym/env.py:34-53 with env.py:68-85): classical int8[n][9], q_p1 int8[n][5][2], q_p2
+ * int8[n][4][2] (8-byte aligned), turn uint8[n] -- all four required, laid out as in qttt_observe
+ * -- are written by the launch that steps the games, from the state it still holds in registers.
+ * All other arguments and outputs as in qttt_step_ex; reward / done / mask / status may be NULL. */
+QTTT_API int qttt_step_obs(qttt_state* state, const void* action, int action_format, const uint8_t* coin,
+                           uint64_t seed, uint64_t game_base, uint64_t epoch, uint32_t flags, float* reward,
+                           uint8_t* done, uint64_t* mask, uint8_t* status, int8_t* classical, int8_t* q_p1,
+                           int8_t* q_p2, uint8_t* turn, int64_t n, void* stream);
+
 /* Inverse of qttt_observe for (classical, moves, n_moves): builds packed states from
  * reference-shaped positions (what MCTS.reset does with game.board / game.moves,
  * mcts.py:139-164 -- but the entanglement is re-derived, so mid-game roots are handled

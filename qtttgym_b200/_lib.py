@@ -37,6 +37,7 @@ _SIGNATURES = {
     "qttt_qeval1": ([_vp, _int, _vp, _u32, _vp], _int),
     "qttt_get_mask": ([_vp, _vp, _i64, _vp], _int),
     "qttt_step_features": ([_vp, _vp, _int, _vp, _u64, _u64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp], _int),
+    "qttt_step_obs": ([_vp, _vp, _int, _vp, _u64, _u64, _u64, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp], _int),
     "qttt_pack": ([_vp, _vp, _vp, _vp, _i64, _vp], _int),
     "qttt_qeval_both": ([_vp] * 10 + [_i64, _vp], _int),
     "qttt_rollout": ([_vp, _i64, _i32, _u64, _vp, _vp, _vp, _vp], _int),

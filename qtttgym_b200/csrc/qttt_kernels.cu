@@ -509,6 +509,68 @@ k_observe(const qttt_state* __restrict__ state, const ObsOut o, int64_t n, bool 
     }
 }
 
+// Env.step returning the observation (env.py:34-53 with env.py:68-85) as ONE launch: K1 followed
+// by the env.py observation of the state it just produced, which is still in registers -- the
+// separate observe launch would read the 16-byte state back and pay a second launch.
+struct StepObsArgs {
+    StepArgs st;
+    ObsOut obs;            // classical, q1, q2, turn (all required); the rest unused
+    bool aligned16;        // classical and q1 start on 16-byte boundaries
+};
+template <int kFmt, int kMode>
+__global__ void __launch_bounds__(kThreads, 6) k_step_obs(const StepObsArgs fa) {
+    __shared__ __align__(16) uint8_t smem[kLutStepBytes];
+    __shared__ __align__(16) uint8_t smem_obs[kObsLutBytes];
+    __shared__ __align__(16) uint8_t st_classical[kThreads * 9];
+    __shared__ __align__(16) uint8_t st_q1[kThreads * 10];
+    stage_luts(smem, kLutStepBytes, smem_obs, &g_obs_lut, kObsLutBytes);
+    const Luts L = luts_from_image(smem);
+    const ObsLutImage* O = reinterpret_cast<const ObsLutImage*>(smem_obs);
+    const StepArgs& a = fa.st;
+    const uint32_t first_chunk = blockIdx.x * (uint32_t)a.iters;
+    for (int it = 0; it < a.iters; ++it) {
+        const uint32_t chunk_start = (first_chunk + (uint32_t)it) * kThreads;
+        if (chunk_start >= a.n) break;                              // the same for the whole block
+        const uint32_t i = chunk_start + threadIdx.x;
+        const bool valid = i < a.n;
+        // lanes past the end step an empty game with an illegal action (full-warp votes inside)
+        State s = empty_state();
+        uint32_t act = 255u, coin = 0u;
+        if (valid) {
+            if (kMode != kStepFresh) s = load_state(a.state, i);
+            if (kFmt == QTTT_ACT_INDEX) {
+                act = a.action[i];
+            } else {
+                const uchar2 ab = reinterpret_cast<const uchar2*>(a.action)[i];
+                act = (uint32_t)ab.x | ((uint32_t)ab.y << 8);
+            }
+            if (a.coin) coin = a.coin[i];
+        }
+        const uint32_t enew = kFmt == QTTT_ACT_INDEX ? (uint32_t)L.pair[act] : pair_to_edge(act & 255u, act >> 8);
+        const StepOut o = step_game<false, kMode, true>(s, enew, a.coin != nullptr, coin & 1u, a.seed,
+                                                        a.game_base + (uint64_t)i, a.dword, L);
+        if (valid) {
+            if (o.write_state) store_state(a.state, i, s);
+            if (a.reward) reinterpret_cast<uint32_t*>(a.reward)[i] = reward_bits(o.win);   // env.py:49
+            if (a.done) a.done[i] = (uint8_t)o.done;                                       // env.py:51
+            if (a.mask) a.mask[i] = L.legal[~o.classical & M9];                            // mcts.py:87-91
+            if (a.status) a.status[i] = (uint8_t)o.status;
+            observe_row<kObsEnv>(s, L, O, fa.obs, (int64_t)i, (int)threadIdx.x, st_classical, nullptr, st_q1, nullptr);
+        }
+        __syncthreads();
+        const uint32_t left = a.n - chunk_start;
+        if (left >= (uint32_t)kThreads && fa.aligned16) {
+            copy_out_full<9>(st_classical, fa.obs.classical, chunk_start);
+            copy_out_full<10>(st_q1, fa.obs.q1, chunk_start);
+        } else {
+            const int nvalid = left < (uint32_t)kThreads ? (int)left : kThreads;
+            copy_out<9>(st_classical, fa.obs.classical, chunk_start, nvalid);
+            copy_out<10>(st_q1, fa.obs.q1, chunk_start, nvalid);
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_pack(qttt_state* __restrict__ state, const int8_t* __restrict__ classical_in,
        const int8_t* __restrict__ moves, const uint8_t* __restrict__ nmoves, int64_t n) {
@@ -1524,6 +1586,81 @@ int qttt_step_features(qttt_state* state, const void* action, int action_format,
     if (action_format == QTTT_ACT_INDEX)
         return launch_step_features_fmt<QTTT_ACT_INDEX>(fa, flags, n, (cudaStream_t)stream);
     return launch_step_features_fmt<QTTT_ACT_PAIR>(fa, flags, n, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+template <int kFmt, int kMode>
+static int launch_step_obs(const StepObsArgs& fa, int64_t n, cudaStream_t st) {
+    const int64_t kSlice = 1ll << 31;
+    const int act_bytes = kFmt == QTTT_ACT_PAIR ? 2 : 1;
+    for (int64_t lo = 0; lo < n; lo += kSlice) {
+        const int64_t m = n - lo < kSlice ? n - lo : kSlice;
+        StepObsArgs b = fa;
+        b.st.state = fa.st.state + lo;
+        b.st.action = fa.st.action + act_bytes * lo;
+        b.st.coin = fa.st.coin ? fa.st.coin + lo : nullptr;
+        b.st.game_base = fa.st.game_base + (uint64_t)lo;
+        b.st.reward = fa.st.reward ? fa.st.reward + lo : nullptr;
+        b.st.done = fa.st.done ? fa.st.done + lo : nullptr;
+        b.st.mask = fa.st.mask ? fa.st.mask + lo : nullptr;
+        b.st.status = fa.st.status ? fa.st.status + lo : nullptr;
+        b.st.n = (uint32_t)m;
+        b.st.iters = iters_for(m, 4);
+        b.obs.classical = fa.obs.classical + 9 * lo;
+        b.obs.q1 = fa.obs.q1 + 10 * lo;
+        b.obs.q2 = fa.obs.q2 + 8 * lo;
+        b.obs.turn = fa.obs.turn + lo;
+        k_step_obs<kFmt, kMode><<<chunk_grid(m, b.st.iters), kThreads, 0, st>>>(b);
+        const int rc = check_launch();
+        if (rc != QTTT_OK) return rc;
+    }
+    return QTTT_OK;
+}
+
+template <int kFmt>
+static int launch_step_obs_fmt(const StepObsArgs& fa, uint32_t flags, int64_t n, cudaStream_t st) {
+    if (flags & QTTT_STEP_FRESH) return launch_step_obs<kFmt, kStepFresh>(fa, n, st);
+    if (flags & QTTT_STEP_AUTORESET) return launch_step_obs<kFmt, kStepAuto>(fa, n, st);
+    if (flags & QTTT_STEP_AUTORESET_NEXT) return launch_step_obs<kFmt, kStepAutoNext>(fa, n, st);
+    return launch_step_obs<kFmt, kStepPlain>(fa, n, st);
+}
+
+extern "C" {
+
+int qttt_step_obs(qttt_state* state, const void* action, int action_format, const uint8_t* coin,
+                  uint64_t seed, uint64_t game_base, uint64_t epoch, uint32_t flags, float* reward,
+                  uint8_t* done, uint64_t* mask, uint8_t* status, int8_t* classical, int8_t* q_p1,
+                  int8_t* q_p2, uint8_t* turn, int64_t n, void* stream) {
+    if (action_format != QTTT_ACT_INDEX && action_format != QTTT_ACT_PAIR) return QTTT_ERR_ARG;
+    const uint32_t modes = flags & (QTTT_STEP_FRESH | QTTT_STEP_AUTORESET | QTTT_STEP_AUTORESET_NEXT);
+    if ((flags & ~(QTTT_STEP_FRESH | QTTT_STEP_AUTORESET | QTTT_STEP_AUTORESET_NEXT)) || (modes & (modes - 1)))
+        return QTTT_ERR_ARG;
+    if (n == 0) return QTTT_OK;
+    if (!state || !action || !classical || !q_p1 || !q_p2 || !turn || n < 0) return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(mask, 8) || misaligned(reward, 4) || misaligned(q_p2, 8))
+        return QTTT_ERR_ALIGN;
+    if (action_format == QTTT_ACT_PAIR && misaligned(action, 2)) return QTTT_ERR_ALIGN;
+    if (const int rc = device_ok()) return rc;
+    StepObsArgs fa{};
+    fa.st.state = state;
+    fa.st.action = static_cast<const uint8_t*>(action);
+    fa.st.coin = coin;
+    fa.st.seed = seed;
+    fa.st.game_base = game_base;
+    fa.st.dword = domain_word(0u, epoch);
+    fa.st.reward = reward;
+    fa.st.done = done;
+    fa.st.mask = mask;
+    fa.st.status = status;
+    fa.obs.classical = classical;
+    fa.obs.q1 = q_p1;
+    fa.obs.q2 = q_p2;
+    fa.obs.turn = turn;
+    fa.aligned16 = !(misaligned(classical, 16) || misaligned(q_p1, 16));
+    if (action_format == QTTT_ACT_INDEX)
+        return launch_step_obs_fmt<QTTT_ACT_INDEX>(fa, flags, n, (cudaStream_t)stream);
+    return launch_step_obs_fmt<QTTT_ACT_PAIR>(fa, flags, n, (cudaStream_t)stream);
 }
 
 int qttt_pack(qttt_state* state, const int8_t* classical, const int8_t* moves,

@@ -109,6 +109,8 @@ class BatchedEnv:
         the reference's -1.0 / -0.0 (quirk Q1).  The returned tensors are views of buffers that
         the next ``step`` overwrites.
         """
+        if self.obs_mode == "full":          # the observation (fresh tensors) comes out of the same launch
+            return self.step_obs(actions, choices, autoreset)
         act, fmt = self._check_actions(actions)
         coin = self._check_choices(choices)
         flags = self._mode_flags(autoreset)
@@ -121,6 +123,34 @@ class BatchedEnv:
                 self.mask.data_ptr(), self.status.data_ptr(), self.num_envs,
                 _stream_ptr(self.device)))
         return self._result()
+
+    def step_obs(self, actions, choices=None, autoreset=False, out=None, fresh: bool = False):
+        """``step`` fused with the env.py observation of the new states (``qttt_step_obs``): one
+        launch steps the games and decodes ``classical`` int8[N,9], ``q_states_p1`` int8[N,5,2],
+        ``q_states_p2`` int8[N,4,2], ``turn`` uint8[N] (env.py:68-85) from the states it still holds
+        in registers.  ``out``: the observation dict of an earlier call, overwritten in place.
+        ``fresh``: ``reset()`` first, inside the same launch (like ``reset_step``).
+        Returns what ``step`` returns, with that dict as ``obs``."""
+        act, fmt = self._check_actions(actions)
+        coin = self._check_choices(choices)
+        flags = _lib.STEP_FRESH if fresh else self._mode_flags(autoreset)
+        if flags:
+            self.epoch += 1
+        n, dev = self.num_envs, self.device
+        if out is None:
+            out = {"classical": torch.empty((n, 9), dtype=torch.int8, device=dev),
+                   "q_states_p1": torch.empty((n, 5, 2), dtype=torch.int8, device=dev),
+                   "q_states_p2": torch.empty((n, 4, 2), dtype=torch.int8, device=dev),
+                   "turn": torch.empty(n, dtype=torch.uint8, device=dev)}
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.qttt_step_obs(
+                self.state.data_ptr(), act.data_ptr(), fmt, _lib.ptr(coin), self.seed,
+                self.game_base, self.epoch, flags, self.reward.data_ptr(), self.done.data_ptr(),
+                self.mask.data_ptr(), self.status.data_ptr(), out["classical"].data_ptr(),
+                out["q_states_p1"].data_ptr(), out["q_states_p2"].data_ptr(), out["turn"].data_ptr(),
+                n, _stream_ptr(dev)))
+        info = _Info(self, {"action_mask": self.mask, "status": self.status})
+        return out, self.reward, self.done, self._never, info
 
     def _check_choices(self, choices):
         if choices is None:

@@ -47,10 +47,10 @@ class VectorEnv:
 
     def step(self, actions):
         """actions: uint8[N] action indices 0..35 or int8[N,2] (a, b) pairs (any order)."""
-        _, reward, terminated, truncated, info = self.env.step(actions, autoreset="next")
+        self._obs, reward, terminated, truncated, info = self.env.step_obs(actions, autoreset="next", out=self._obs)
         if self.reward_kind == "p1":
             reward = info["reward_p1"]
-        return self._observation(), reward, terminated, truncated, info
+        return self._obs, reward, terminated, truncated, info
 
     def close(self):
         self.closed = True

@@ -181,6 +181,17 @@ class EmuGames:
         self.lib.emu_get_mask(_p(self.state), _p(out), C.c_int64(self.n))
         return out.astype(bool)
 
+    def step_obs(self, actions, coins=None, epoch=0, flags=0, pairs=False):
+        """host emulation: the step, then the plain observation of the new state"""
+        if pairs:
+            assert epoch == 0 and flags == 0
+            o = self.step(actions, coins)
+        else:
+            o = self.step_ex(actions, coins, epoch=epoch, flags=flags)
+        obs = self.observe()
+        o["obs"] = {k: obs[k] for k in ("classical", "q_p1", "q_p2", "turn")}
+        return o
+
     def step_features(self, actions, coins=None, epoch=0, flags=0):
         """host emulation: the step, then the two encoders on the new state"""
         o = self.step_ex(actions, coins, epoch=epoch, flags=flags)
@@ -361,6 +372,23 @@ class CudaGames:
 
     def get_mask(self):
         return self.Q.get_mask(self.env.state).cpu().numpy()
+
+    def step_obs(self, actions, coins=None, epoch=0, flags=0, pairs=False):
+        """the fused kernel: qttt_step_obs"""
+        t = self.torch
+        env = self.env
+        if pairs:
+            ac = t.from_numpy(np.ascontiguousarray(actions, dtype=np.int8).reshape(self.n, 2)).cuda()
+        else:
+            ac = t.from_numpy(np.ascontiguousarray(actions, np.uint8)).cuda()
+        co = None if coins is None else t.from_numpy(np.ascontiguousarray(coins, np.uint8)).cuda()
+        env.epoch = epoch - (1 if flags else 0)
+        res = env.step_obs(ac, co, autoreset=self._AUTORESET[flags])
+        o = self._outs(res)
+        obs = {k: v.cpu().numpy() for k, v in res[0].items()}
+        o["obs"] = {"classical": obs["classical"], "q_p1": obs["q_states_p1"], "q_p2": obs["q_states_p2"],
+                    "turn": obs["turn"]}
+        return o
 
     def step_features(self, actions, coins=None, epoch=0, flags=0):
         """the fused kernel: qttt_step_features"""

@@ -592,6 +592,58 @@ def check_step_features(backend, n_games=3000, seed=41):
         mask, over = r["mask"], r["done"].astype(bool)
 
 
+def check_step_obs(backend, n_games=3000, seed=43):
+    """qttt_step_obs: the step outputs and the observation that comes out of the same launch,
+    against the oracle after every step -- plain mode with (a, b) pairs played to the end and
+    beyond (post-terminal moves, illegal actions), then an auto-resetting batch in both modes
+    (every ply present in the batch at once), some illegal actions throughout."""
+    rng = np.random.default_rng(seed)
+    full_mask = np.uint64((1 << 36) - 1)
+    fresh = CO.Games(1).raw[0].copy()
+
+    def same(o, r, ref, where):
+        assert np.array_equal(o["reward"].view(np.uint32), r["reward"].view(np.uint32)), where
+        assert np.array_equal(o["done"], r["done"]) and np.array_equal(o["mask"], r["mask"]), where
+        want = ref.observe()
+        for k in ("classical", "q_p1", "q_p2", "turn"):
+            assert np.array_equal(o["obs"][k], want[k]), f"{where}: {k}"
+
+    ref, dut = CO.Games(n_games), backend.games(n_games)
+    mask = np.full(n_games, full_mask, np.uint64)
+    for t in range(11):
+        legal = expand_mask(mask)
+        k = (rng.random((n_games, 36)) * legal).argmax(1)
+        pairs = PAIRS[k].copy()
+        flip = rng.random(n_games) < 0.5
+        pairs[flip] = pairs[flip][:, ::-1]
+        bad = rng.random(n_games) < 0.05
+        pairs[bad] = rng.integers(-1, 10, (int(bad.sum()), 2)).astype(np.int8)
+        coins = rng.integers(0, 2, n_games).astype(np.uint8)
+        r = ref.step(pairs, coins)
+        o = dut.step_obs(pairs, coins, pairs=True)
+        same(o, r, ref, f"{backend.name} step_obs pairs step {t}")
+        assert_same_obs(dut.observe(), ref.observe(), f"{backend.name} step_obs pairs state {t}")
+        mask = r["mask"]
+    for flags in (2, 4):
+        ref, dut = CO.Games(n_games), backend.games(n_games)
+        mask = np.full(n_games, full_mask, np.uint64)
+        over = np.zeros(n_games, bool)
+        for t in range(20):
+            legal = expand_mask(np.where(over, full_mask, mask))
+            k = (rng.random((n_games, 36)) * legal).argmax(1).astype(np.uint8)
+            bad = rng.random(n_games) < 0.05
+            k[bad] = rng.integers(0, 64, int(bad.sum())).astype(np.uint8)
+            coins = rng.integers(0, 2, n_games).astype(np.uint8)
+            ref.raw[over] = fresh
+            pairs = np.full((n_games, 2), -1, np.int8)
+            play = (k < 36) & ~(over if flags == 4 else np.zeros(n_games, bool))   # "next": a reset env ignores its action
+            pairs[play] = PAIRS[k[play]]
+            r = ref.step(pairs, coins)
+            o = dut.step_obs(k, coins, epoch=t + 1, flags=flags)
+            same(o, r, ref, f"{backend.name} step_obs flags {flags} step {t}")
+            mask, over = r["mask"], r["done"].astype(bool)
+
+
 def _pack_oracle_games(backend, games):
     """oracle Game objects -> packed states via the backend's pack."""
     n = len(games)

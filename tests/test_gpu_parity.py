@@ -456,6 +456,36 @@ def test_fused_step_features(cuda, n):
     S.check_step_features(cuda, n)
 
 
+@pytest.mark.parametrize("n", [1, 255, 3000, 70_001])
+def test_fused_step_obs(cuda, n):
+    """qttt_step_obs: step + the env.py observation from one launch, ragged sizes, all modes"""
+    S.check_step_obs(cuda, n)
+
+
+def test_full_obs_mode_and_vector_env_use_the_fused_step(cuda):
+    """BatchedEnv(obs_mode='full').step and VectorEnv.step return the observation of the new state
+    (qttt_step_obs) -- the same tensors a separate observation() call decodes."""
+    import torch
+    import qtttgym_b200 as Q
+    env = Q.BatchedEnv(1000, seed=2, obs_mode="full")
+    env.reset()
+    for _ in range(7):
+        masks = env.action_mask().float()
+        masks[masks.sum(1) == 0, 0] = 1.0
+        act = torch.multinomial(masks, 1).squeeze(1).to(torch.uint8)
+        obs, _, _, _, _ = env.step(act)
+        want = env.observation()
+        for k in want:
+            assert torch.equal(obs[k], want[k]), k
+    venv = Q.VectorEnv(777, seed=3)
+    venv.reset()
+    for _ in range(15):
+        obs, _, _, _, _ = venv.step(venv.sample_actions())
+        want = venv.env.observation()
+        for k in want:
+            assert torch.equal(obs[k], want[k]), k
+
+
 def test_features_ragged_and_large(cuda):
     """to_vector on ragged sizes vs the host formula applied to observe() output."""
     import torch

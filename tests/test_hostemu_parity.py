@@ -110,5 +110,9 @@ def test_step_features(emu):
     S.check_step_features(emu, 1000)
 
 
+def test_step_obs(emu):
+    S.check_step_obs(emu, 700)
+
+
 def test_exhaustive_openings(emu):
     assert S.check_exhaustive_openings(emu, depth=3, stride=7) > 50000
