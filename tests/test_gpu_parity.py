@@ -477,6 +477,19 @@ def test_full_obs_mode_and_vector_env_use_the_fused_step(cuda):
         want = env.observation()
         for k in want:
             assert torch.equal(obs[k], want[k]), k
+    # fresh=True: reset + first step + observation in one launch == reset_step, then observation()
+    a, b = Q.BatchedEnv(1000, seed=5), Q.BatchedEnv(1000, seed=5)
+    for e in (a, b):
+        for _ in range(5):
+            e.step_random()
+    act = torch.randint(0, 36, (1000,), dtype=torch.uint8, device="cuda")
+    obs, r1, d1, _, i1 = a.step_obs(act, fresh=True)
+    _, r2, d2, _, i2 = b.reset_step(act)
+    assert torch.equal(a.state, b.state) and torch.equal(r1, r2) and torch.equal(d1, d2)
+    assert torch.equal(i1["action_mask"], i2["action_mask"]) and a.epoch == b.epoch
+    want = b.observation()
+    for k in want:
+        assert torch.equal(obs[k], want[k]), k
     venv = Q.VectorEnv(777, seed=3)
     venv.reset()
     for _ in range(15):
