@@ -518,7 +518,7 @@ struct StepObsArgs {
     bool aligned16;        // classical and q1 start on 16-byte boundaries
 };
 template <int kFmt, int kMode>
-__global__ void __launch_bounds__(kThreads, 6) k_step_obs(const StepObsArgs fa) {
+__global__ void __launch_bounds__(kThreads, 8) k_step_obs(const StepObsArgs fa) {
     __shared__ __align__(16) uint8_t smem[kLutStepBytes];
     __shared__ __align__(16) uint8_t smem_obs[kObsLutBytes];
     __shared__ __align__(16) uint8_t st_classical[kThreads * 9];
