@@ -21,6 +21,7 @@ gzip -f $OUT/src_step_${TAG}.csv
 cap desync '^k_step$' 45 2 "" "--only desync"
 cap packed '^k_step_packed' 0 4 "" "--only packed"
 cap io '^k_(observe|features|get_mask)' 0 8 "" "--only observe,features"
+cap stepobs '^k_step_obs' 0 2 "" "--only stepobs"
 cap qeval '^k_qeval' 0 4 "" "--only qeval"
 cap play '^k_(rollout|sweep)' 0 6 "--import-source on" "--only rollout,sweep"
 ncu -i $OUT/prof_play_${TAG}.ncu-rep --page source --csv --print-source sass > $OUT/src_play_${TAG}.csv 2>/dev/null

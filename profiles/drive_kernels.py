@@ -98,6 +98,13 @@ def main():
         buf2 = Q.observe_states(mid)
         timed("k_observe env.py outputs", lambda: Q.observe_states(mid, out=buf2))
         del buf, buf2
+    if want("stepobs"):
+        oenv = Q.BatchedEnv(E, device=dev, seed=seed)
+        obuf = oenv.observation()
+        for rep in range(2):
+            oenv.state.copy_(mid)
+            timed(f"k_step_obs ply 4 (rep {rep})", lambda: oenv.step_obs(actions[4], coins[4], out=obuf))
+        del oenv, obuf
     if want("features"):
         timed("k_features 2^20", lambda: Q.to_vector(mid[:1 << 20]))
         timed("k_features 2^20 (again)", lambda: Q.to_vector(mid[:1 << 20]))

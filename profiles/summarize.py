@@ -73,7 +73,7 @@ def kernels(tag):
     E, acc = labels_from_drive(tag)
     lines = []
     traffic = []
-    for part in ("step", "desync", "packed", "io", "qeval", "play", "mcts"):
+    for part in ("step", "desync", "packed", "io", "stepobs", "qeval", "play", "mcts"):
         path = os.path.join(GP, f"raw_{part}_{tag}.csv")
         if not os.path.exists(path):
             continue
@@ -117,6 +117,8 @@ def kernels(tag):
                     what, alg = "k_step DESYNC batch (autoreset, forced actions)", 47 * E
                 elif "k_step<0, 1, 0, 2" in name:
                     what, alg = "k_step desync batch, random policy (Philox inside)", 47 * E
+            elif name.startswith("k_step_obs"):
+                what, alg = "k_step_obs ply 4 (step + env.py observation)", 47 * (acc[4] if acc else E) + 28 * E
             elif name.startswith("k_step_packed_zc"):
                 what, alg = "k_step_packed_zc ply 4 (host-mapped I/O)", None
             elif name.startswith("k_step_packed"):
