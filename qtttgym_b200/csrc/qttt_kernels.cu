@@ -113,6 +113,7 @@ __device__ __forceinline__ void store_state(qttt_state* p, int64_t i, const Stat
 // running out of warps long before the kernel ended -- 46 of 64 warps resident on average at
 // ply 8 -- because the warp arbiter is not fair and nothing replaces a warp that finishes early.)
 constexpr int kStepIters = 8;       // chunks per block of the step kernels (tables restaged per block)
+constexpr int kZcMaxIters = 8;      // chunks per block of the mapped-memory step kernel (its staging is sized for it)
 constexpr int kSweepIters = 32;     // 8192 self-play games per block of the sweep (19 KB of tables per block)
 
 static int chunk_grid(int64_t n, int iters) {
@@ -266,47 +267,50 @@ k_step_packed(qttt_state* __restrict__ state, const uint8_t* __restrict__ action
 __global__ void __launch_bounds__(kThreads)
 k_step_packed_zc(qttt_state* __restrict__ state, const uint8_t* __restrict__ action_coin_host,
                  uint16_t* __restrict__ result_host, qttt_state* __restrict__ obs_host, uint32_t n, int iters) {
+    // A block owns `iters` (<= kZcMaxIters) consecutive chunks: their input bytes are one contiguous
+    // run in host memory and their result words another.  The run is fetched across PCIe with ONE
+    // round of 16-byte loads before any game is stepped, and the results leave in one burst of
+    // 16-byte stores at the end -- two link round trips per block instead of two per chunk.
     __shared__ __align__(16) uint8_t smem[kLutStepBytes];
-    __shared__ __align__(16) uint8_t sh_in[kThreads];
-    __shared__ __align__(16) uint16_t sh_out[kThreads];
-    stage_luts(smem, kLutStepBytes);
-    const Luts L = luts_from_image(smem);
+    __shared__ __align__(16) uint8_t sh_in[kThreads * kZcMaxIters];
+    __shared__ __align__(16) uint16_t sh_out[kThreads * kZcMaxIters];
     const uint32_t t = threadIdx.x;
+    const uint32_t base0 = blockIdx.x * (uint32_t)iters * kThreads;
+    if (base0 >= n) return;
+    const uint32_t span = n - base0 < (uint32_t)iters * kThreads ? n - base0 : (uint32_t)iters * kThreads;
+    const bool wide = span == (uint32_t)iters * kThreads &&
+                      ((reinterpret_cast<uintptr_t>(action_coin_host + base0) |
+                        reinterpret_cast<uintptr_t>(result_host + base0)) & 15u) == 0u;
+    if (wide) {
+        for (uint32_t v = t; v < span / 16u; v += kThreads)
+            reinterpret_cast<uint4*>(sh_in)[v] = reinterpret_cast<const uint4*>(action_coin_host + base0)[v];
+    } else {
+        for (uint32_t v = t; v < span; v += kThreads) sh_in[v] = action_coin_host[base0 + v];
+    }
+    stage_luts(smem, kLutStepBytes);          // (has the block-wide barrier that also covers sh_in)
+    const Luts L = luts_from_image(smem);
     for (int it = 0; it < iters; ++it) {
-        const uint32_t base = (blockIdx.x * (uint32_t)iters + (uint32_t)it) * kThreads;
-        if (base >= n) break;
-        const uint32_t valid = n - base < (uint32_t)kThreads ? n - base : (uint32_t)kThreads;
-        const bool wide = valid == (uint32_t)kThreads &&
-                          ((reinterpret_cast<uintptr_t>(action_coin_host + base) |
-                            reinterpret_cast<uintptr_t>(result_host + base)) & 15u) == 0u;
-        if (wide) {
-            if (t < kThreads / 16)
-                reinterpret_cast<uint4*>(sh_in)[t] = reinterpret_cast<const uint4*>(action_coin_host + base)[t];
-        } else if (t < valid) {
-            sh_in[t] = action_coin_host[base + t];
-        }
-        __syncthreads();
-        if (t < valid) {
-            const uint32_t i = base + t;
-            uint4* sp = reinterpret_cast<uint4*>(state + i);
-            const uint4 sv = *sp;
-            State s{sv.x, sv.y, sv.z, sv.w};
-            const uint32_t ac = sh_in[t];
-            const StepResult r = step_core(s, (uint32_t)L.pair[ac & 63u], ac >> 7, L);
-            const uint4 out = make_uint4(s.x, s.y, s.z, s.w);
-            if (!r.illegal) *sp = out;
-            if (obs_host) *reinterpret_cast<uint4*>(obs_host + i) = out;
-            const uint32_t win = any_line(s, r.classical, L) != 0u;
-            const uint32_t term = win | (uint32_t)(r.n > 8u);
-            sh_out[t] = (uint16_t)((~r.classical & M9) | (term << 9) | (win << 10) | (r.illegal << 11));
-        }
-        __syncthreads();
-        if (wide) {
-            if (t < kThreads / 8)
-                reinterpret_cast<uint4*>(result_host + base)[t] = reinterpret_cast<const uint4*>(sh_out)[t];
-        } else if (t < valid) {
-            result_host[base + t] = sh_out[t];
-        }
+        const uint32_t off = (uint32_t)it * kThreads + t;
+        if (off >= span) break;
+        const uint32_t i = base0 + off;
+        uint4* sp = reinterpret_cast<uint4*>(state + i);
+        const uint4 sv = *sp;
+        State s{sv.x, sv.y, sv.z, sv.w};
+        const uint32_t ac = sh_in[off];
+        const StepResult r = step_core(s, (uint32_t)L.pair[ac & 63u], ac >> 7, L);
+        const uint4 out = make_uint4(s.x, s.y, s.z, s.w);
+        if (!r.illegal) *sp = out;
+        if (obs_host) *reinterpret_cast<uint4*>(obs_host + i) = out;
+        const uint32_t win = any_line(s, r.classical, L) != 0u;
+        const uint32_t term = win | (uint32_t)(r.n > 8u);
+        sh_out[off] = (uint16_t)((~r.classical & M9) | (term << 9) | (win << 10) | (r.illegal << 11));
+    }
+    __syncthreads();
+    if (wide) {
+        for (uint32_t v = t; v < span / 8u; v += kThreads)
+            reinterpret_cast<uint4*>(result_host + base0)[v] = reinterpret_cast<const uint4*>(sh_out)[v];
+    } else {
+        for (uint32_t v = t; v < span; v += kThreads) result_host[base0 + v] = sh_out[v];
     }
 }
 
@@ -1338,9 +1342,10 @@ static int packed_entry(qttt_state* state, const uint8_t* action_coin, uint16_t*
         const int64_t m = n - lo < kSlice ? n - lo : kSlice;
         const int iters = iters_for(m, step_iters());
         qttt_state* o = obs ? obs + lo : nullptr;
+        const int zc_iters = iters < kZcMaxIters ? iters : kZcMaxIters;
         if (zero_copy)
-            k_step_packed_zc<<<chunk_grid(m, iters), kThreads, 0, st>>>(state + lo, action_coin + lo, result + lo, o,
-                                                                         (uint32_t)m, iters);
+            k_step_packed_zc<<<chunk_grid(m, zc_iters), kThreads, 0, st>>>(state + lo, action_coin + lo, result + lo, o,
+                                                                            (uint32_t)m, zc_iters);
         else
             k_step_packed<<<chunk_grid(m, iters), kThreads, 0, st>>>(state + lo, action_coin + lo, result + lo, o,
                                                                       (uint32_t)m, iters);
