@@ -215,7 +215,7 @@ def sass():
     os.makedirs(os.path.join(OUT, "sass"), exist_ok=True)
     text = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
     funcs = re.split(r"(?m)^\s*Function : ", text)[1:]
-    for want, fname in (("_ZN4qttt6k_stepILi0ELb0ELb1ELi0ELb0EEEvNS_8StepArgsE", "k_step_index_forced_full.sass"),
+    for want, fname in (("_ZN4qttt6k_stepILi0ELb0ELb1ELi0EEEvNS_8StepArgsE", "k_step_index_forced_full.sass"),
                         ("_ZN4qttt7k_sweepEllmPy", "k_sweep.sass")):
         for fn in funcs:
             if fn.startswith(want):
