@@ -11,7 +11,7 @@ importing this package without that library works, using it does not.
 from .arena import (BatchedStrategy, MCTSStrategy, RandomStrategy, RolloutStrategy, eval_strats,
                     play_games)
 from .actions import NUM_ACTIONS, PAIRS, ind2move, move2ind
-from .env import (BatchedEnv, Env, get_mask, observe_states, pack_actions, pack_states, render_text,
+from .env import (BatchedEnv, Env, get_mask, observe_states, pack_actions, pack_states, render_states, render_text,
                   to_vector, unpack_result)
 from .mcts import BatchedMCTS
 from .qeval import QEvalB200, qeval_both, square_probabilities
@@ -21,7 +21,7 @@ from .rollout import STAT_NAMES, rollout_eval, selfplay_sweep, shard_range, shar
 __all__ = [
     "NUM_ACTIONS", "PAIRS", "ind2move", "move2ind",
     "BatchedEnv", "Env", "observe_states", "pack_states", "pack_actions", "unpack_result",
-    "to_vector", "get_mask", "render_text",
+    "to_vector", "get_mask", "render_text", "render_states",
     "VectorEnv", "BatchedMCTS", "QEvalB200", "qeval_both", "square_probabilities",
     "BatchedStrategy", "MCTSStrategy", "RandomStrategy", "RolloutStrategy", "eval_strats", "play_games",
     "STAT_NAMES", "rollout_eval", "selfplay_sweep", "shard_range", "sharded_sweep",

@@ -458,6 +458,10 @@ class BatchedEnv:
             raise ValueError(f"expected {self.num_envs} actions, got {actions.shape[0]}")
         return actions.contiguous(), fmt
 
+    def render(self, index: int = 0) -> str:
+        """``displayBoard`` text (display.py:4-32) of env ``index`` (env.py:59-60 for one env of the batch)."""
+        return render_states(self.state, [int(index)])[0]
+
     def _obs(self):
         if self.obs_mode == "packed":
             return {"packed": self.state}
@@ -642,6 +646,23 @@ def render_text(classical, moves, n_moves) -> str:
                 out += "|" + "".join(cells[3 * i + j][3 * k:3 * k + 3])
             out += "|\n"
     return out + "+---+---+---+\n"
+
+
+def render_states(state, indices=None):
+    """ASCII dumps (``displayBoard`` layout, display.py:4-32) of packed states int32[N,4]: a list
+    with one string per requested game (all of them when ``indices`` is None) -- the debugging aid
+    for parity failures (SURVEY 8(f) #4).  One ``qttt_observe`` launch for the selection."""
+    if indices is not None:
+        state = state[torch.as_tensor(indices, dtype=torch.long, device=state.device)].contiguous()
+    if state.shape[0] == 0:
+        return []
+    obs = observe_states(state, extras=True)
+    classical, moves, n_moves = (obs[k].cpu().tolist() for k in ("classical", "moves", "n_moves"))
+    out = []
+    for cl, mv, nm in zip(classical, moves, n_moves):
+        # the autofill entry is stored as (s, s) like the reference's (s, s, 8) (board.py:25)
+        out.append(render_text(cl, mv, nm))
+    return out
 
 
 def pack_states(classical, moves, n_moves, device="cuda"):

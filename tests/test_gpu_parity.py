@@ -499,6 +499,32 @@ def test_full_obs_mode_and_vector_env_use_the_fused_step(cuda):
             assert torch.equal(obs[k], want[k]), k
 
 
+def test_render_states_matches_the_recorded_reference_display(cuda):
+    """render_states / BatchedEnv.render on packed states == the displayBoard text recorded from
+    the live reference (golden feature records: mid-game, collapsed and autofilled positions)."""
+    import numpy as np
+    import qtttgym_b200 as Q
+    from helpers import load_golden
+    recs = load_golden("features_v1.json.gz")
+    n = len(recs)
+    classical = np.array([r["board"] for r in recs], np.int8)
+    moves = np.full((n, 9, 2), -1, np.int8)
+    nm = np.array([len(r["moves"]) for r in recs], np.uint8)
+    for g, r in enumerate(recs):
+        for a, b, idx in r["moves"]:
+            moves[g, idx] = (a, b)
+    state = Q.pack_states(classical, moves, nm)
+    texts = Q.render_states(state)
+    assert len(texts) == n
+    for g, r in enumerate(recs):
+        # displayBoard prints the string followed by print()'s own newline
+        assert texts[g] + "\n" == r["display"], g
+    env = Q.BatchedEnv(n, seed=0)
+    env.state.copy_(state)
+    assert env.render(n - 1) + "\n" == recs[-1]["display"]
+    assert Q.render_states(state, [3, 1]) == [texts[3], texts[1]]
+
+
 def test_features_ragged_and_large(cuda):
     """to_vector on ragged sizes vs the host formula applied to observe() output."""
     import torch
