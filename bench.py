@@ -641,19 +641,26 @@ def run_b200(args):
 
     # MCTS search around the leaf evaluator (next row #1): 1024 mid-game roots, the reference's
     # default num_simulations=10, 500 rollouts per root; and the config-4 shape (256 playouts per leaf)
-    for name, n_roll, n_sim in (("mcts_1024_roots_500x10", 500, 10), ("mcts_1024_roots_100x256", 100, 256)):
-        mc = Q.BatchedMCTS(rollouts=n_roll, num_simulations=n_sim, seed=seed, root_base=rank * 1024, device=dev)
+    # (a search is one warp per tree, so it is latency-bound until the machine is full of trees:
+    # the third line is the same search over 32,768 roots)
+    many_roots = qenv.state[:32768].clone()
+    for name, n_roll, n_sim, rts in (("mcts_1024_roots_500x10", 500, 10, roots),
+                                     ("mcts_1024_roots_100x256", 100, 256, roots),
+                                     ("mcts_32768_roots_100x10", 100, 10, many_roots)):
+        n_rts = rts.shape[0]
+        mc = Q.BatchedMCTS(rollouts=n_roll, num_simulations=n_sim, seed=seed, root_base=rank * n_rts, device=dev)
 
         def search():
-            mc.reset(roots, total_rollouts=n_roll)
+            mc.reset(rts, total_rollouts=n_roll)
             mc.contemplate(n_roll)
         ms = timed(search, 3)
 
         assert int(mc.errors().max().item()) == 0
-        extra[name] = {"ms": ms, "rollouts_per_s": 1024 * n_roll / (ms * 1e-3) * world,
-                       "playouts_per_s": 1024 * n_roll * n_sim / (ms * 1e-3) * world,
+        extra[name] = {"ms": ms, "rollouts_per_s": n_rts * n_roll / (ms * 1e-3) * world,
+                       "playouts_per_s": n_rts * n_roll * n_sim / (ms * 1e-3) * world,
                        "nodes_per_tree_mean": float(mc.node_counts().float().mean().item())}
         del mc
+    del many_roots
 
     # a9 observation decode (env.py:68-85 + extras) and the to_vector feature encoder
     obs_buf = env.observation(extras=True)

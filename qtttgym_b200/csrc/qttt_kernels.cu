@@ -1066,26 +1066,42 @@ __device__ __forceinline__ bool warp_expand(MctsNode* tree, int32_t* meta, int64
     return true;
 }
 
-// One block per root.  A rollout is: warp 0 walks the tree (PUCT select, expanding one
-// (node, action) when needed), all threads play the leaf's num_simulations playouts in
-// parallel, a block reduction gives r_tot, thread 0 backs the value up.  Trees of different
-// roots advance independently in different blocks.
+// A rollout is: one warp walks the tree (PUCT select, expanding one (node, action) when needed),
+// the leaf's num_simulations playouts run in parallel on the lanes, a reduction gives r_tot, one
+// thread backs the value up.  Trees of different roots advance independently.
+//   kWarpPerRoot = false: one block per root, its threads share the playouts (num_simulations > 32).
+//   kWarpPerRoot = true:  num_simulations <= 32 -- a root needs one warp only, and a block carries
+//       kMctsWarps of them on one staged copy of the tables.  (As one-warp blocks the 19 KB of tables
+//       per block capped an SM at 11 trees; searching 32,768 roots ran at 116 M rollouts/s.)
+constexpr int kMctsWarps = 8;
+template <bool kWarpPerRoot>
 __global__ void __launch_bounds__(kThreads)
-k_mcts_run(MctsNode* __restrict__ pool, int64_t capacity, int32_t* __restrict__ meta,
+k_mcts_run(MctsNode* __restrict__ pool, int64_t capacity, int32_t* __restrict__ meta, int64_t n_roots,
            int32_t n_rollouts, int32_t num_sims, double c_puct, uint64_t seed, uint64_t root_base) {
     __shared__ __align__(16) uint8_t smem[kLutPolicyBytes];
-    __shared__ int sh_path_node[12], sh_path_act[12], sh_depth, sh_leaf, sh_rtot;
+    __shared__ int sh_path_node_all[kWarpPerRoot ? kMctsWarps : 1][12], sh_path_act_all[kWarpPerRoot ? kMctsWarps : 1][12];
+    __shared__ int sh_depth_all[kWarpPerRoot ? kMctsWarps : 1], sh_leaf_all[kWarpPerRoot ? kMctsWarps : 1];
+    __shared__ int sh_rtot_all[kWarpPerRoot ? kMctsWarps : 1];
     stage_luts(smem, kLutPolicyBytes);
     const Luts L = luts_from_image(smem);
-    const int64_t root = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = kWarpPerRoot ? (int)(threadIdx.x >> 5) : 0;
+    const int64_t root = kWarpPerRoot ? (int64_t)blockIdx.x * (blockDim.x >> 5) + warp : (int64_t)blockIdx.x;
+    if (root >= n_roots) return;                       // whole warps only (kWarpPerRoot); no block barrier below then
+    int* sh_path_node = sh_path_node_all[warp];
+    int* sh_path_act = sh_path_act_all[warp];
+    int& sh_depth = sh_depth_all[warp];
+    int& sh_leaf = sh_leaf_all[warp];
+    int& sh_rtot = sh_rtot_all[warp];
     MctsNode* tree = pool + root * capacity;
     int32_t* m = meta + root * kMetaStride;
     const uint64_t root_id = (root_base + (uint64_t)root) << 32;
     const int first = m[kMetaRollouts];
-    const int lane = threadIdx.x & 31;
+    const int tid = kWarpPerRoot ? lane : (int)threadIdx.x;          // index within the root's thread group
+    const int group = kWarpPerRoot ? 32 : (int)blockDim.x;
+    auto group_sync = [&]() { if (kWarpPerRoot) __syncwarp(); else __syncthreads(); };
     for (int it = 0; it < n_rollouts; ++it) {
         const uint64_t base = root_id + (uint64_t)(uint32_t)(first + it);
-        if (threadIdx.x < 32) {                                            // mcts.py:269-277
+        if (tid < 32) {                                                    // mcts.py:269-277
             int node = m[kMetaRoot], depth = 0;
             while (tree[node].has_p && !tree[node].terminal) {
                 const int a = warp_uct_select(tree[node], c_puct, lane);
@@ -1099,21 +1115,21 @@ k_mcts_run(MctsNode* __restrict__ pool, int64_t capacity, int32_t* __restrict__ 
             }
             if (lane == 0) { sh_leaf = node; sh_depth = depth; sh_rtot = 0; }
         }
-        __syncthreads();
+        group_sync();
         const MctsNode& leaf = tree[sh_leaf];
         int r = 0;
-        for (int sim = threadIdx.x; sim < num_sims; sim += blockDim.x)
+        for (int sim = tid; sim < num_sims; sim += group)
             r += mcts_sim_reward(leaf, seed, base, (uint32_t)sim, L);
         r = __reduce_add_sync(0xFFFFFFFFu, r);
         if (lane == 0 && r) atomicAdd(&sh_rtot, r);
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        group_sync();
+        if (tid == 0) {
             if (!tree[sh_leaf].terminal) tree[sh_leaf].has_p = 1;             // mcts.py:189-191
             mcts_backprop(tree, sh_path_node, sh_path_act, sh_depth, sh_rtot, num_sims);
         }
-        __syncthreads();
+        group_sync();
     }
-    if (threadIdx.x == 0) m[kMetaRollouts] = first + n_rollouts;
+    if (tid == 0) m[kMetaRollouts] = first + n_rollouts;
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -1742,8 +1758,21 @@ int qttt_mcts_run(void* pool, int64_t capacity, int32_t* meta, int32_t n_rollout
     if (misaligned(pool, 16) || misaligned(meta, 4)) return QTTT_ERR_ALIGN;
     int threads = ((num_simulations + 31) / 32) * 32;
     threads = threads > kThreads ? kThreads : threads;
-    k_mcts_run<<<(int)n_roots, threads, 0, (cudaStream_t)stream>>>(
-        static_cast<MctsNode*>(pool), capacity, meta, n_rollouts, num_simulations, c_puct, seed, root_base);
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // one warp per root: with more roots than one-warp blocks can keep resident (11 per SM: the
+    // tables), several roots share a block; fewer roots stay spread over all SMs, one per block
+    if (threads == 32 && n_roots > (int64_t)sms * 11) {
+        const int64_t blocks = (n_roots + kMctsWarps - 1) / kMctsWarps;
+        k_mcts_run<true><<<(int)blocks, 32 * kMctsWarps, 0, (cudaStream_t)stream>>>(
+            static_cast<MctsNode*>(pool), capacity, meta, n_roots, n_rollouts, num_simulations, c_puct, seed, root_base);
+    } else if (threads == 32) {
+        k_mcts_run<true><<<(int)n_roots, 32, 0, (cudaStream_t)stream>>>(
+            static_cast<MctsNode*>(pool), capacity, meta, n_roots, n_rollouts, num_simulations, c_puct, seed, root_base);
+    } else {
+        k_mcts_run<false><<<(int)n_roots, threads, 0, (cudaStream_t)stream>>>(
+            static_cast<MctsNode*>(pool), capacity, meta, n_roots, n_rollouts, num_simulations, c_puct, seed, root_base);
+    }
     return check_launch();
 }
 

@@ -499,6 +499,30 @@ def test_full_obs_mode_and_vector_env_use_the_fused_step(cuda):
             assert torch.equal(obs[k], want[k]), k
 
 
+def test_mcts_many_roots_per_block_equals_one_root_per_block(cuda):
+    """With more roots than one-warp blocks keep resident, qttt_mcts_run packs several roots into a
+    block: the same trees, visit for visit, as the same roots searched 1000 at a time (each shard
+    keyed by its root_base, one root per block)."""
+    import torch
+    import qtttgym_b200 as Q
+    n = 4000
+    env = Q.BatchedEnv(n, seed=11)
+    for _ in range(4):
+        env.step_random()
+    roots = env.state.clone()
+    big = Q.BatchedMCTS(rollouts=60, num_simulations=10, seed=5).reset(roots)
+    big.contemplate()
+    n_big, q_big, tot_big = big.root_stats()[:3]
+    pick_big = big.choose()
+    assert int(big.errors().max().item()) == 0
+    for lo in range(0, n, 1000):
+        part = Q.BatchedMCTS(rollouts=60, num_simulations=10, seed=5, root_base=lo).reset(roots[lo:lo + 1000])
+        part.contemplate()
+        n_p, q_p, tot_p = part.root_stats()[:3]
+        assert torch.equal(n_p, n_big[lo:lo + 1000]) and torch.equal(q_p, q_big[lo:lo + 1000])
+        assert torch.equal(tot_p, tot_big[lo:lo + 1000]) and torch.equal(part.choose(), pick_big[lo:lo + 1000])
+
+
 def test_render_states_matches_the_recorded_reference_display(cuda):
     """render_states / BatchedEnv.render on packed states == the displayBoard text recorded from
     the live reference (golden feature records: mid-game, collapsed and autofilled positions)."""
