@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 8) k_step(const StepArgs a) {   // 8
     };
 
     const uint32_t first = (blockIdx.x * (uint32_t)a.iters) * kThreads + threadIdx.x;
-    if (kMode == kStepFresh && !kRandom) {
+    if constexpr (kMode == kStepFresh && !kRandom) {
         // The fused reset + first step reads two bytes per game and writes 30: nothing to overlap
         // the load latency with inside one chunk, so the next chunk's bytes are fetched first.
         StepIn cur = load(first);
@@ -224,11 +224,11 @@ __global__ void __launch_bounds__(kThreads, 8) k_step(const StepArgs a) {   // 8
             run(i, cur);
             cur = nxt;
         }
-        return;
-    }
-    for (int it = 0; it < a.iters; ++it) {
-        const uint32_t i = first + (uint32_t)it * kThreads;
-        run(i, load(i));
+    } else {
+        for (int it = 0; it < a.iters; ++it) {
+            const uint32_t i = first + (uint32_t)it * kThreads;
+            run(i, load(i));
+        }
     }
 }
 
