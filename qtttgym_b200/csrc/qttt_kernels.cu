@@ -164,7 +164,14 @@ struct StepIn { uint4 sv; uint32_t act, coin; };
 template <int kFmt, bool kRandom, bool kFull, int kMode>
 __global__ void __launch_bounds__(kThreads, 8) k_step(const StepArgs a) {   // 8 blocks/SM: 32 registers
     __shared__ __align__(16) uint8_t smem[kLutStepBytes];
+    // Programmatic dependent launch (when the host launched with it, see launch_pdl): the NEXT
+    // kernel in the stream may start placing blocks as soon as every block of this one has got
+    // here, and this kernel stages its tables -- constants, independent of earlier kernels --
+    // before it waits for the previous kernel to finish and its writes to be visible.  Back-to-back
+    // steps overlap one kernel's tail with the next one's prologue.  (No-ops in a plain launch.)
+    asm volatile("griddepcontrol.launch_dependents;");
     stage_luts(smem, kLutStepBytes);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const Luts L = luts_from_image(smem);
 
     auto load = [&](uint32_t i) {
@@ -1257,6 +1264,32 @@ int qttt_reset_all(qttt_state* state, uint64_t* mask, float* reward, uint8_t* do
 
 }  // extern "C"
 
+// Kernel launch that allows programmatic dependent launch on the stream (the kernel must order
+// itself after its predecessor with griddepcontrol.wait before touching anything the predecessor
+// writes -- k_step does).  QTTT_PDL=0 in the environment turns it off.
+static bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("QTTT_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), int grid, int threads, cudaStream_t st, Args... args) {
+    if (!pdl_enabled()) {
+        kernel<<<grid, threads, 0, st>>>(args...);
+        return;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // Launches k_step over [0, n) in slices of at most 2^31 games (32-bit indices in the kernel).
 template <int kFmt, bool kRandom, int kMode>
 static int launch_step_mode(StepArgs a, int64_t n, cudaStream_t st) {
@@ -1283,11 +1316,11 @@ static int launch_step_mode(StepArgs a, int64_t n, cudaStream_t st) {
         bool launched = false;
         if constexpr (kFmt == QTTT_ACT_INDEX && !kRandom && kMode != kStepAutoNext) {
             if (full) {                           // the headline shape gets the specialised variants
-                k_step<kFmt, false, true, kMode><<<grid, kThreads, 0, st>>>(b);
+                launch_pdl(k_step<kFmt, false, true, kMode>, grid, kThreads, st, b);
                 launched = true;
             }
         }
-        if (!launched) k_step<kFmt, kRandom, false, kMode><<<grid, kThreads, 0, st>>>(b);
+        if (!launched) launch_pdl(k_step<kFmt, kRandom, false, kMode>, grid, kThreads, st, b);
         const int rc = check_launch();
         if (rc != QTTT_OK) return rc;
     }
