@@ -508,20 +508,33 @@ def run_b200(args):
         variants[name] = {"value": v, "ms_per_pass": ms, "h2d_bytes_per_pass": b_in * E * PLIES,
                           "d2h_bytes_per_pass": b_out * E * PLIES, "link_floor_ms_per_pass": floor,
                           "frac_of_link_ceiling": floor / ms}
-    best = "packed_copy" if variants["packed_copy"]["value"] >= variants["packed_mapped"]["value"] else "packed_mapped"
+    # the mapped path with the result words bit-packed: 12 bits per env, four envs in three words
+    h_res12 = torch.empty(3 * ((E + 3) // 4), dtype=torch.int16).pin_memory()      # 1.5 bytes per env per ply
+    v, ms = e2e_run(lambda ply: env.step_host_packed12(h_ac[ply], h_res12))
+    _, term_chk, _, _ = Q.unpack_result(Q.unpack_result12(h_res12, E))
+    assert int(term_chk.sum()) == E, "e2e pass did not finish every game"
+    floor = link_floor_ms(E * PLIES, 3 * ((E + 3) // 4) * 2 * PLIES)
+    variants["packed12_mapped"] = {"value": v, "ms_per_pass": ms, "h2d_bytes_per_pass": E * PLIES,
+                                   "d2h_bytes_per_pass": 3 * ((E + 3) // 4) * 2 * PLIES,
+                                   "link_floor_ms_per_pass": floor, "frac_of_link_ceiling": floor / ms}
+    del h_res12
+    best = max(("packed_copy", "packed_mapped", "packed12_mapped"), key=lambda k: variants[k]["value"])
     best_obs = ("packed_copy_obs" if variants["packed_copy_obs"]["value"] >= variants["packed_mapped_obs"]["value"]
                 else "packed_mapped_obs")
-    e2e = {"value": variants[best]["value"], "unit": UNIT, "h2d_bytes_per_step": 1 * E * PLIES * P,
-           "d2h_bytes_per_step": 2 * E * PLIES * P, "passes_timed": e2e_K, "ms_per_pass": variants[best]["ms_per_pass"],
+    e2e = {"value": variants[best]["value"], "unit": UNIT, "h2d_bytes_per_step": variants[best]["h2d_bytes_per_pass"] * P,
+           "d2h_bytes_per_step": variants[best]["d2h_bytes_per_pass"] * P, "passes_timed": e2e_K,
+           "ms_per_pass": variants[best]["ms_per_pass"],
            "variant": best,
-           "fields_returned": "per env per ply one 16-bit word: free-square set (= the 36-bit legal mask, re-expanded by "
-                              "unpack_result), terminated, line (= reward -1.0 / -0.0), status.  The observation stays "
+           "fields_returned": "per env per ply one result word: free-square set (= the 36-bit legal mask, re-expanded by "
+                              "unpack_result), terminated, line (= reward -1.0 / -0.0), status -- 16 bits per env, or "
+                              "(packed12_mapped) 12 bits per env with four envs in three words.  The observation stays "
                               "in HBM (the packed state tensor); `with_obs` is the same path with the observation "
                               "(packed 16-B state per env) copied to the host as well",
            "api": "BatchedEnv.reset + 9 x BatchedEnv.step_host_packed (pinned host buffers: 1 B action|coin in, 2 B out "
                   "per env per ply).  packed_copy = qttt_step_packed_host_obs: 8 slices pipelined over 4 side "
                   "streams, one cudaMemcpyAsync per array per slice; packed_mapped = qttt_step_packed_mapped: one "
-                  "launch whose threads read / write the pinned host buffers across PCIe themselves",
+                  "launch whose threads read / write the pinned host buffers across PCIe themselves; packed12_mapped = "
+                  "qttt_step_packed12_mapped (BatchedEnv.step_host_packed12): the same with 1.5 B out per env per ply",
            "with_obs": {"value": variants[best_obs]["value"], "variant": best_obs,
                         "ms_per_pass": variants[best_obs]["ms_per_pass"],
                         "h2d_bytes_per_pass": 1 * E * PLIES, "d2h_bytes_per_pass": 18 * E * PLIES},

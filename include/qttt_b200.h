@@ -147,6 +147,15 @@ QTTT_API int qttt_step_packed_obs(qttt_state* state, const uint8_t* action_coin,
 QTTT_API int qttt_step_packed_mapped(qttt_state* state, const uint8_t* action_coin_host,
                                      uint16_t* result_host, qttt_state* obs_host, int64_t n, void* stream);
 
+/* qttt_step_packed_mapped with the results bit-packed: a result word carries 12 bits (free-square
+ * set 0-8, terminated 9, line 10, illegal 11), so four consecutive games' results are written as
+ * THREE 16-bit words -- word k (k = 0..2) of group g = games 4g..4g+3 holds game 4g+k's result in
+ * bits 0-11 and bits 4k..4k+3 of game 4g+3's result in bits 12-15.  result12_host:
+ * uint16[3 * ceil(n / 4)] (games past n read as 0).  1.5 instead of 2 bytes per game cross the
+ * link, which is what bounds the host-resident caller. */
+QTTT_API int qttt_step_packed12_mapped(qttt_state* state, const uint8_t* action_coin_host,
+                                       uint16_t* result12_host, int64_t n, void* stream);
+
 /* The host-buffer form of qttt_step_packed: action_coin_host / result_host are PINNED HOST
  * arrays; in_dev (uint8[n]) / out_dev (uint16[n]) are caller-provided device staging buffers.
  * The batch is cut into slices of `slice` games; slice k is copied in, stepped and copied out

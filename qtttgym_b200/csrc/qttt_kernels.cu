@@ -271,6 +271,10 @@ k_step_packed(qttt_state* __restrict__ state, const uint8_t* __restrict__ action
 // 16-byte loads and its 256 result words out as thirty-two 16-byte stores, so every PCIe
 // transaction is a full 512-byte burst; the observation (16 B per game) is written by each
 // thread directly (512 contiguous bytes per warp).
+// kPack12: the result words carry 12 bits each (free-square set, terminated, line, illegal), so
+// four games' results leave as THREE 16-bit words -- word k of a group holds game k's result in
+// its low 12 bits and nibble k of game 3's result on top: 1.5 bytes per game cross the link.
+template <bool kPack12>
 __global__ void __launch_bounds__(kThreads)
 k_step_packed_zc(qttt_state* __restrict__ state, const uint8_t* __restrict__ action_coin_host,
                  uint16_t* __restrict__ result_host, qttt_state* __restrict__ obs_host, uint32_t n, int iters) {
@@ -281,13 +285,15 @@ k_step_packed_zc(qttt_state* __restrict__ state, const uint8_t* __restrict__ act
     __shared__ __align__(16) uint8_t smem[kLutStepBytes];
     __shared__ __align__(16) uint8_t sh_in[kThreads * kZcMaxIters];
     __shared__ __align__(16) uint16_t sh_out[kThreads * kZcMaxIters];
+    __shared__ __align__(16) uint16_t sh_pk[kPack12 ? kThreads * kZcMaxIters * 3 / 4 : 8];
     const uint32_t t = threadIdx.x;
     const uint32_t base0 = blockIdx.x * (uint32_t)iters * kThreads;
     if (base0 >= n) return;
     const uint32_t span = n - base0 < (uint32_t)iters * kThreads ? n - base0 : (uint32_t)iters * kThreads;
+    uint16_t* out_host = kPack12 ? result_host + (base0 / 4u) * 3u : result_host + base0;
     const bool wide = span == (uint32_t)iters * kThreads &&
                       ((reinterpret_cast<uintptr_t>(action_coin_host + base0) |
-                        reinterpret_cast<uintptr_t>(result_host + base0)) & 15u) == 0u;
+                        reinterpret_cast<uintptr_t>(out_host)) & 15u) == 0u;
     if (wide) {
         for (uint32_t v = t; v < span / 16u; v += kThreads)
             reinterpret_cast<uint4*>(sh_in)[v] = reinterpret_cast<const uint4*>(action_coin_host + base0)[v];
@@ -313,11 +319,31 @@ k_step_packed_zc(qttt_state* __restrict__ state, const uint8_t* __restrict__ act
         sh_out[off] = (uint16_t)((~r.classical & M9) | (term << 9) | (win << 10) | (r.illegal << 11));
     }
     __syncthreads();
+    if (kPack12) {
+        const uint32_t groups = (span + 3u) / 4u;
+        for (uint32_t g = t; g < groups; g += kThreads) {
+            uint32_t r[4];
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; ++k) r[k] = 4u * g + k < span ? (uint32_t)sh_out[4u * g + k] : 0u;
+            sh_pk[3u * g + 0u] = (uint16_t)(r[0] | ((r[3] & 15u) << 12));
+            sh_pk[3u * g + 1u] = (uint16_t)(r[1] | (((r[3] >> 4) & 15u) << 12));
+            sh_pk[3u * g + 2u] = (uint16_t)(r[2] | (((r[3] >> 8) & 15u) << 12));
+        }
+        __syncthreads();
+        const uint32_t words = 3u * groups;
+        if (wide) {
+            for (uint32_t v = t; v < words / 8u; v += kThreads)
+                reinterpret_cast<uint4*>(out_host)[v] = reinterpret_cast<const uint4*>(sh_pk)[v];
+        } else {
+            for (uint32_t v = t; v < words; v += kThreads) out_host[v] = sh_pk[v];
+        }
+        return;
+    }
     if (wide) {
         for (uint32_t v = t; v < span / 8u; v += kThreads)
-            reinterpret_cast<uint4*>(result_host + base0)[v] = reinterpret_cast<const uint4*>(sh_out)[v];
+            reinterpret_cast<uint4*>(out_host)[v] = reinterpret_cast<const uint4*>(sh_out)[v];
     } else {
-        for (uint32_t v = t; v < span; v += kThreads) result_host[base0 + v] = sh_out[v];
+        for (uint32_t v = t; v < span; v += kThreads) out_host[v] = sh_out[v];
     }
 }
 
@@ -1393,8 +1419,8 @@ static int packed_entry(qttt_state* state, const uint8_t* action_coin, uint16_t*
         qttt_state* o = obs ? obs + lo : nullptr;
         const int zc_iters = iters < kZcMaxIters ? iters : kZcMaxIters;
         if (zero_copy)
-            k_step_packed_zc<<<chunk_grid(m, zc_iters), kThreads, 0, st>>>(state + lo, action_coin + lo, result + lo, o,
-                                                                            (uint32_t)m, zc_iters);
+            k_step_packed_zc<false><<<chunk_grid(m, zc_iters), kThreads, 0, st>>>(state + lo, action_coin + lo, result + lo,
+                                                                                   o, (uint32_t)m, zc_iters);
         else
             k_step_packed<<<chunk_grid(m, iters), kThreads, 0, st>>>(state + lo, action_coin + lo, result + lo, o,
                                                                       (uint32_t)m, iters);
@@ -1425,6 +1451,25 @@ int qttt_step_packed_mapped(qttt_state* state, const uint8_t* action_coin_host, 
     if (misaligned(state, 16) || misaligned(result_host, 2) || misaligned(obs_host, 16)) return QTTT_ERR_ALIGN;
     if (const int rc = device_ok()) return rc;
     return packed_entry(state, action_coin_host, result_host, obs_host, n, true, (cudaStream_t)stream);
+}
+
+int qttt_step_packed12_mapped(qttt_state* state, const uint8_t* action_coin_host, uint16_t* result12_host,
+                              int64_t n, void* stream) {
+    if (n == 0) return QTTT_OK;
+    if (!state || !action_coin_host || !result12_host || n < 0) return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(result12_host, 2)) return QTTT_ERR_ALIGN;
+    if (const int rc = device_ok()) return rc;
+    const int64_t kSlice = 1ll << 31;          // a multiple of 4: every slice starts on a group boundary
+    for (int64_t lo = 0; lo < n; lo += kSlice) {
+        const int64_t m = n - lo < kSlice ? n - lo : kSlice;
+        int iters = iters_for(m, step_iters());
+        iters = iters < kZcMaxIters ? iters : kZcMaxIters;
+        k_step_packed_zc<true><<<chunk_grid(m, iters), kThreads, 0, (cudaStream_t)stream>>>(
+            state + lo, action_coin_host + lo, result12_host + (lo / 4) * 3, nullptr, (uint32_t)m, iters);
+        const int rc = check_launch();
+        if (rc != QTTT_OK) return rc;
+    }
+    return QTTT_OK;
 }
 
 int qttt_step_packed_host(qttt_state* state, const uint8_t* action_coin_host, uint16_t* result_host,

@@ -298,6 +298,22 @@ class BatchedEnv:
                 cur.wait_event(fin)
         return reward_host, done_host, mask_host
 
+    def step_host_packed12(self, action_coin_host, result12_host):
+        """``step_host_packed(..., mapped=True)`` with the result words bit-packed
+        (``qttt_step_packed12_mapped``): 12 bits per env, four envs in three 16-bit words, so 1.5
+        instead of 2 bytes per env come back across PCIe -- the direction that bounds the
+        host-resident caller.  ``result12_host``: pinned int16[3 * ceil(N / 4)]; decode with
+        ``unpack_result12(result12_host, N)``.  Same transition, bit for bit."""
+        n, dev = self.num_envs, self.device
+        words = 3 * ((n + 3) // 4)
+        for t, dt, numel in ((action_coin_host, torch.uint8, n), (result12_host, torch.int16, words)):
+            if t.dtype != dt or t.numel() != numel or t.device.type != "cpu" or not t.is_contiguous() or not t.is_pinned():
+                raise ValueError("step_host_packed12 expects pinned contiguous CPU uint8[N] / int16[3*ceil(N/4)] tensors")
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.qttt_step_packed12_mapped(
+                self.state.data_ptr(), action_coin_host.data_ptr(), result12_host.data_ptr(), n, _stream_ptr(dev)))
+        return result12_host
+
     def step_host_packed(self, action_coin_host, result_host, obs_host=None, chunks: int = 8,
                          n_streams: int = 4, mapped: bool = False):
         """``step_host`` with compact I/O: 1 byte in and 2 bytes out per env cross PCIe instead of
@@ -560,6 +576,17 @@ def unpack_result(result):
     reward = torch.where(win, neg_one, neg_zero)
     status = ((r >> 11) & 3).to(torch.uint8)
     return reward, terminated, mask, status
+
+
+def unpack_result12(result12, n: int):
+    """The bit-packed result words of ``step_host_packed12`` (int16[3 * ceil(n / 4)]) -> the int16[n]
+    words ``unpack_result`` takes: word k of a group holds env 4g+k's 12 bits, the three top nibbles
+    together env 4g+3's."""
+    w = (result12.to(torch.int32) & 0xFFFF).view(-1, 3)
+    low = w & 0xFFF
+    last = (w[:, 0] >> 12) | ((w[:, 1] >> 12) << 4) | ((w[:, 2] >> 12) << 8)
+    out = torch.cat([low, last[:, None]], dim=1).reshape(-1)[:n]
+    return out.to(torch.int16)
 
 
 def observe_states(state, extras: bool = False, out=None):

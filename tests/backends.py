@@ -341,9 +341,14 @@ class CudaGames:
 
     def step_packed(self, action_coin, variant="copy"):
         """variant: "copy" (cudaMemcpyAsync pipeline), "copy_obs" (+ observation), "mapped"
-        (the kernel reads/writes the pinned host buffers itself), "mapped_obs"."""
+        (the kernel reads/writes the pinned host buffers itself), "mapped_obs", "mapped12" (bit-packed results)."""
         t = self.torch
         ac = t.from_numpy(np.ascontiguousarray(action_coin, np.uint8)).pin_memory()
+        if variant == "mapped12":        # 12-bit results, four envs in three words
+            res12 = t.full((3 * ((self.n + 3) // 4),), -1, dtype=t.int16).pin_memory()
+            self.env.step_host_packed12(ac, res12)
+            t.cuda.synchronize()
+            return self.Q.unpack_result12(res12, self.n).numpy().view(np.uint16).copy()
         res = t.empty(self.n, dtype=t.int16).pin_memory()
         obs = t.empty((self.n, 4), dtype=t.int32).pin_memory() if variant.endswith("obs") else None
         self.env.step_host_packed(ac, res, obs_host=obs, chunks=3, n_streams=2, mapped=variant.startswith("mapped"))

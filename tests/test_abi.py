@@ -26,7 +26,7 @@ def built_lib():
 def test_header_declares_the_expected_surface():
     assert _declared_symbols() == {
         "qttt_abi_version", "qttt_strerror", "qttt_reset", "qttt_reset_all", "qttt_reset_step", "qttt_step", "qttt_step_ex",
-        "qttt_step_packed", "qttt_step_packed_obs", "qttt_step_packed_mapped", "qttt_step_packed_host",
+        "qttt_step_packed", "qttt_step_packed_obs", "qttt_step_packed_mapped", "qttt_step_packed12_mapped", "qttt_step_packed_host",
         "qttt_step_packed_host_obs", "qttt_step_random", "qttt_step_random_ex",
         "qttt_observe", "qttt_features", "qttt_env1", "qttt_qeval1", "qttt_get_mask", "qttt_step_features", "qttt_step_obs", "qttt_pack", "qttt_qeval_both", "qttt_rollout", "qttt_sweep",
         "qttt_mcts_node_bytes", "qttt_mcts_init", "qttt_mcts_run", "qttt_mcts_stats", "qttt_mcts_sync"}
@@ -118,3 +118,18 @@ def test_spaces_mirror_the_reference_env():
         assert o.contains(obs)
         assert o["q_states_p1"].max_len == 5 and o["q_states_p2"].max_len == 4
         assert not o["classical"].contains(np.full(9, 9, np.int32))
+
+
+def test_unpack_result12_is_the_inverse_of_the_kernel_packing():
+    """host-side decode of the 12-bit result words (pure torch, no GPU)"""
+    import numpy as np
+    import torch
+    from qtttgym_b200.env import unpack_result12
+    rng = np.random.default_rng(0)
+    for n in (1, 3, 4, 5, 1023, 4096):
+        r = rng.integers(0, 1 << 12, n).astype(np.uint32)
+        pad = np.concatenate([r, np.zeros((-n) % 4, np.uint32)]).reshape(-1, 4)
+        w = np.stack([pad[:, 0] | ((pad[:, 3] & 15) << 12), pad[:, 1] | (((pad[:, 3] >> 4) & 15) << 12),
+                      pad[:, 2] | (((pad[:, 3] >> 8) & 15) << 12)], 1).astype(np.uint16).reshape(-1)
+        got = unpack_result12(torch.from_numpy(w.view(np.int16).copy()), n).numpy().view(np.uint16)
+        assert np.array_equal(got.astype(np.uint32), r)

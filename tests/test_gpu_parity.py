@@ -346,6 +346,13 @@ def test_packed_step_host(cuda):
     S.check_packed_step(cuda, 40_001)
 
 
+@pytest.mark.parametrize("n", [1, 6, 255, 20_003, 70_000])
+def test_packed12_step_host(cuda, n):
+    """bit-packed results (12 bits per env, four envs in three words): sizes that are not
+    multiples of 4 / 256 / the block span, and one that is"""
+    S.check_packed_step(cuda, n, variant="mapped12")
+
+
 @pytest.mark.parametrize("variant", ["copy_obs", "mapped", "mapped_obs"])
 def test_packed_step_host_variants(cuda, variant):
     """the observation coming back with the result words, and the zero-copy path (the kernel
