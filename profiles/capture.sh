@@ -19,7 +19,7 @@ ncu -i $OUT/prof_step_${TAG}.ncu-rep --page source --csv --print-source sass > $
 gzip -f $OUT/src_step_${TAG}.csv
 # the desynchronised batch: 9 trace + 4 mid-game + 31 mixing + 1 recording launches of k_step come first
 cap desync '^k_step$' 45 2 "" "--only desync"
-cap packed '^k_step_packed' 0 4 "" "--only packed"
+cap packed '^k_step_packed' 0 6 "" "--only packed"
 cap io '^k_(observe|features|get_mask)' 0 8 "" "--only observe,features"
 cap stepobs '^k_step_obs' 0 2 "" "--only stepobs"
 cap qeval '^k_qeval' 0 4 "" "--only qeval"

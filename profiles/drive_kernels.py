@@ -92,6 +92,13 @@ def main():
                                                          torch.cuda.current_stream().cuda_stream))
         timed("k_step_packed_zc ply 4 (mapped pinned host buffers)", mapped)
         timed("k_step_packed_zc ply 4 (again)", mapped)
+        h_res12 = torch.empty(3 * ((E + 3) // 4), dtype=torch.int16).pin_memory()
+
+        def mapped12():
+            Q._lib.check(env.lib.qttt_step_packed12_mapped(st.data_ptr(), h_ac.data_ptr(), h_res12.data_ptr(), E,
+                                                           torch.cuda.current_stream().cuda_stream))
+        timed("k_step_packed_zc<12-bit results> ply 4", mapped12)
+        timed("k_step_packed_zc<12-bit results> ply 4 (again)", mapped12)
     if want("observe"):
         buf = Q.observe_states(mid, extras=True)
         timed("k_observe all outputs", lambda: Q.observe_states(mid, extras=True, out=buf))

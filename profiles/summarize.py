@@ -102,7 +102,9 @@ def kernels(tag):
                 what, alg = "k_step DESYNC batch (autoreset, forced actions, plies 1-9 mixed in every warp)", 47 * E
             elif part == "packed":
                 what, alg = (("k_step_packed ply 4", 35 * (acc[4] if acc else E)) if "zc" not in name else
-                             ("k_step_packed_zc ply 4 (kernel reads/writes mapped pinned host memory)", None))
+                             (("k_step_packed_zc<12-bit results> ply 4 (1 B in, 1.5 B out per env over PCIe)"
+                               if "<1>" in name.replace(" ", "") else
+                               "k_step_packed_zc ply 4 (kernel reads/writes mapped pinned host memory)"), None))
             elif part == "step" and name.startswith("k_step<"):
                 if "k_step<0, 0, 1, 1" in name:
                     what, alg = "k_step ply 0 (reset fused in)", (31 * acc[0] if acc else None)
