@@ -530,6 +530,79 @@ def test_mcts_many_roots_per_block_equals_one_root_per_block(cuda):
         assert torch.equal(tot_p, tot_big[lo:lo + 1000]) and torch.equal(part.choose(), pick_big[lo:lo + 1000])
 
 
+def test_batches_beyond_2_31_games_are_sliced_correctly(cuda):
+    """The kernels index games with 32 bits; the entry points cut larger batches into slices of
+    2^31 (2^30 for the boards-only qeval).  2^31 + 70,001 games (34 GB of states) stepped three plies
+    through qttt_step_ex, then qttt_qeval_both and qttt_step_packed: the games on both sides of the
+    slice boundaries and at the very end equal the same games processed as a small batch."""
+    import torch
+    import qtttgym_b200 as Q
+    import qtttgym_b200._lib as L
+    n = (1 << 31) + 70_001
+    free, _ = torch.cuda.mem_get_info()
+    if free < 70 * (1 << 30):
+        pytest.skip("needs 70 GB of free device memory")
+    lib = L.lib()
+    dev = torch.device("cuda")
+    state = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    mask = torch.empty(n, dtype=torch.int64, device=dev)
+    done = torch.empty(n, dtype=torch.uint8, device=dev)
+    plies = [(torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev))
+             for _ in range(3)]
+    step = 1 << 27                                                   # generated in pieces: small temporaries
+    for lo in range(0, n, step):
+        idx = torch.arange(lo, min(n, lo + step), device=dev, dtype=torch.int64)
+        for ply, (act, coin) in enumerate(plies):
+            act[lo:lo + step] = ((idx * 7 + ply * 11) % 36).to(torch.uint8)   # some legal, some not; pairs repeat
+            coin[lo:lo + step] = ((idx >> 3) & 1).to(torch.uint8)
+        del idx
+    stream = torch.cuda.current_stream().cuda_stream
+    for ply, (act, coin) in enumerate(plies):
+        L.check(lib.qttt_step_ex(state.data_ptr(), act.data_ptr(), 0, coin.data_ptr(), 5, 0, 1,
+                                 L.STEP_FRESH if ply == 0 else 0, None, done.data_ptr(), mask.data_ptr(), None,
+                                 n, stream))
+    torch.cuda.synchronize()
+    windows = [(0, 1000), ((1 << 31) - 600, (1 << 31) + 600), (n - 1000, n)]
+    for lo, hi in windows:
+        m = hi - lo
+        small = Q.BatchedEnv(m, seed=5, game_base=lo)
+        for ply, (act, coin) in enumerate(plies):
+            (small.reset_step if ply == 0 else small.step)(act[lo:hi].clone(), coin[lo:hi].clone())
+        assert torch.equal(small.state, state[lo:hi]), (lo, hi)
+        assert torch.equal(small.mask, mask[lo:hi]) and torch.equal(small.done.to(torch.uint8), done[lo:hi]), (lo, hi)
+    # every game of the big batch made progress or was refused: no slice was skipped
+    for lo in range(0, n, step):
+        nm = (state[lo:lo + step, 0] >> 27) & 15
+        assert int(nm.min()) >= 1 and int(nm.max()) <= 3, lo
+    del mask, done, nm
+    # the boards-only qeval kernel (slices of 2^30) on the same states
+    act3 = plies[0][0]
+    b0 = torch.empty(n, dtype=torch.int64, device=dev)
+    b1 = torch.empty(n, dtype=torch.int64, device=dev)
+    closes = torch.empty(n, dtype=torch.uint8, device=dev)
+    L.check(lib.qttt_qeval_both(state.data_ptr(), act3.data_ptr(), None, None, b0.data_ptr(), b1.data_ptr(),
+                                None, None, closes.data_ptr(), None, n, stream))
+    torch.cuda.synchronize()
+    for lo, hi in windows + [((1 << 30) - 300, (1 << 30) + 300)]:
+        want = Q.qeval_both(state[lo:hi].clone(), act3[lo:hi].clone(), want_states=False, want_probs=False)
+        assert torch.equal(want["board0"].view(torch.int64), b0[lo:hi]), (lo, hi)
+        assert torch.equal(want["board1"].view(torch.int64), b1[lo:hi]) and torch.equal(want["closes"], closes[lo:hi])
+    del b0, b1, closes
+    # the packed step (1 byte in, one word out) over the slice boundary
+    ac = (plies[1][0] % 36) | (plies[1][1] << 7)
+    res = torch.empty(n, dtype=torch.int16, device=dev)
+    before = {w: state[w[0]:w[1]].clone() for w in windows}
+    L.check(lib.qttt_step_packed(state.data_ptr(), ac.data_ptr(), res.data_ptr(), n, stream))
+    torch.cuda.synchronize()
+    for (lo, hi), st in before.items():
+        r2 = torch.empty(hi - lo, dtype=torch.int16, device=dev)
+        L.check(lib.qttt_step_packed(st.data_ptr(), ac[lo:hi].clone().data_ptr(), r2.data_ptr(), hi - lo, stream))
+        torch.cuda.synchronize()
+        assert torch.equal(st, state[lo:hi]) and torch.equal(r2, res[lo:hi]), (lo, hi)
+    del state, plies, res, ac, before
+    torch.cuda.empty_cache()
+
+
 def test_render_states_matches_the_recorded_reference_display(cuda):
     """render_states / BatchedEnv.render on packed states == the displayBoard text recorded from
     the live reference (golden feature records: mid-game, collapsed and autofilled positions)."""
