@@ -533,15 +533,15 @@ def test_mcts_many_roots_per_block_equals_one_root_per_block(cuda):
 def test_batches_beyond_2_31_games_are_sliced_correctly(cuda):
     """The kernels index games with 32 bits; the entry points cut larger batches into slices of
     2^31 (2^30 for the boards-only qeval).  2^31 + 70,001 games (34 GB of states) stepped three plies
-    through qttt_step_ex, then qttt_qeval_both and qttt_step_packed: the games on both sides of the
+    through qttt_step_ex, then qttt_qeval_both, qttt_step_packed and qttt_step_obs: the games on both sides of the
     slice boundaries and at the very end equal the same games processed as a small batch."""
     import torch
     import qtttgym_b200 as Q
     import qtttgym_b200._lib as L
     n = (1 << 31) + 70_001
     free, _ = torch.cuda.mem_get_info()
-    if free < 70 * (1 << 30):
-        pytest.skip("needs 70 GB of free device memory")
+    if free < 120 * (1 << 30):
+        pytest.skip("needs 120 GB of free device memory")
     lib = L.lib()
     dev = torch.device("cuda")
     state = torch.empty((n, 4), dtype=torch.int32, device=dev)
@@ -599,7 +599,25 @@ def test_batches_beyond_2_31_games_are_sliced_correctly(cuda):
         L.check(lib.qttt_step_packed(st.data_ptr(), ac[lo:hi].clone().data_ptr(), r2.data_ptr(), hi - lo, stream))
         torch.cuda.synchronize()
         assert torch.equal(st, state[lo:hi]) and torch.equal(r2, res[lo:hi]), (lo, hi)
-    del state, plies, res, ac, before
+    del res, ac
+    # the fused step + observation launch over the slice boundary
+    act, coin = plies[2]
+    before = {w: state[w[0]:w[1]].clone() for w in windows}
+    cl = torch.empty((n, 9), dtype=torch.int8, device=dev)
+    q1 = torch.empty((n, 5, 2), dtype=torch.int8, device=dev)
+    q2 = torch.empty((n, 4, 2), dtype=torch.int8, device=dev)
+    turn = torch.empty(n, dtype=torch.uint8, device=dev)
+    L.check(lib.qttt_step_obs(state.data_ptr(), act.data_ptr(), 0, coin.data_ptr(), 5, 0, 1, 0, None, None, None,
+                              None, cl.data_ptr(), q1.data_ptr(), q2.data_ptr(), turn.data_ptr(), n, stream))
+    torch.cuda.synchronize()
+    for (lo, hi), st in before.items():
+        small = Q.BatchedEnv(hi - lo, seed=5, game_base=lo)
+        small.state.copy_(st)
+        obs = small.step_obs(act[lo:hi].clone(), coin[lo:hi].clone())[0]
+        assert torch.equal(small.state, state[lo:hi]), (lo, hi)
+        assert torch.equal(obs["classical"], cl[lo:hi]) and torch.equal(obs["q_states_p1"], q1[lo:hi]), (lo, hi)
+        assert torch.equal(obs["q_states_p2"], q2[lo:hi]) and torch.equal(obs["turn"], turn[lo:hi]), (lo, hi)
+    del state, plies, before, cl, q1, q2, turn
     torch.cuda.empty_cache()
 
 
