@@ -156,6 +156,14 @@ QTTT_API int qttt_step_packed_mapped(qttt_state* state, const uint8_t* action_co
 QTTT_API int qttt_step_packed12_mapped(qttt_state* state, const uint8_t* action_coin_host,
                                        uint16_t* result12_host, int64_t n, void* stream);
 
+/* The bit-packed results through explicit copies: qttt_step_packed_host with 12-bit results.  Slices
+ * of `slice` games (a multiple of 4) are pipelined over `streams`: cudaMemcpyAsync of the slice's
+ * action bytes into in_dev[n], the step kernel writing packed words into out12_dev
+ * (uint16[3 * ceil(n / 4)]), cudaMemcpyAsync of those words into result12_host. */
+QTTT_API int qttt_step_packed12_host(qttt_state* state, const uint8_t* action_coin_host,
+                                     uint16_t* result12_host, uint8_t* in_dev, uint16_t* out12_dev,
+                                     int64_t n, int64_t slice, void* const* streams, int n_streams);
+
 /* The host-buffer form of qttt_step_packed: action_coin_host / result_host are PINNED HOST
  * arrays; in_dev (uint8[n]) / out_dev (uint16[n]) are caller-provided device staging buffers.
  * The batch is cut into slices of `slice` games; slice k is copied in, stepped and copied out

@@ -242,6 +242,9 @@ __global__ void __launch_bounds__(kThreads, 8) k_step(const StepArgs a) {   // 8
 // K1 with compact I/O (one byte in, one 16-bit word out per game): see qttt_step_packed.
 // obs (optional): the post-step packed state is ALSO written there (the observation of a caller
 // whose buffers are not the state array itself, e.g. mapped host memory).
+// kPack12: results leave bit-packed, four games in three 16-bit words (see qttt_step_packed12_mapped):
+// lane 4g+k (k < 3) writes word k of its group, with nibble k of lane 4g+3's result on top.
+template <bool kPack12>
 __global__ void __launch_bounds__(kThreads)
 k_step_packed(qttt_state* __restrict__ state, const uint8_t* __restrict__ action_coin,
               uint16_t* __restrict__ result, qttt_state* __restrict__ obs, uint32_t n, int iters) {
@@ -251,18 +254,31 @@ k_step_packed(qttt_state* __restrict__ state, const uint8_t* __restrict__ action
     const uint32_t first = (blockIdx.x * (uint32_t)iters) * kThreads + threadIdx.x;
     for (int it = 0; it < iters; ++it) {
         const uint32_t i = first + (uint32_t)it * kThreads;
-        if (i >= n) break;
-        uint4* sp = reinterpret_cast<uint4*>(state + i);
-        const uint4 sv = *sp;
-        State s{sv.x, sv.y, sv.z, sv.w};
-        const uint32_t ac = action_coin[i];
-        const StepResult r = step_core(s, (uint32_t)L.pair[ac & 63u], ac >> 7, L);
-        const uint4 out = make_uint4(s.x, s.y, s.z, s.w);
-        if (!r.illegal) *sp = out;
-        if (obs) *reinterpret_cast<uint4*>(obs + i) = out;
-        const uint32_t win = any_line(s, r.classical, L) != 0u;
-        const uint32_t term = win | (uint32_t)(r.n > 8u);
-        result[i] = (uint16_t)((~r.classical & M9) | (term << 9) | (win << 10) | (r.illegal << 11));
+        if (!kPack12 && i >= n) break;
+        uint32_t word = 0u;
+        if (i < n) {
+            uint4* sp = reinterpret_cast<uint4*>(state + i);
+            const uint4 sv = *sp;
+            State s{sv.x, sv.y, sv.z, sv.w};
+            const uint32_t ac = action_coin[i];
+            const StepResult r = step_core(s, (uint32_t)L.pair[ac & 63u], ac >> 7, L);
+            const uint4 out = make_uint4(s.x, s.y, s.z, s.w);
+            if (!r.illegal) *sp = out;
+            if (obs) *reinterpret_cast<uint4*>(obs + i) = out;
+            const uint32_t win = any_line(s, r.classical, L) != 0u;
+            const uint32_t term = win | (uint32_t)(r.n > 8u);
+            word = (~r.classical & M9) | (term << 9) | (win << 10) | (r.illegal << 11);
+        }
+        if (kPack12) {
+            // (a warp's lanes are in or out of step_core together only by accident, but nothing in it
+            // votes: step_core queries the active mask)
+            const uint32_t k = threadIdx.x & 3u;
+            const uint32_t last = __shfl_sync(0xFFFFFFFFu, word, (threadIdx.x & 31u) | 3u);
+            if (k < 3u && (i & ~3u) < n)
+                result[(i >> 2) * 3u + k] = (uint16_t)(word | (((last >> (4u * k)) & 15u) << 12));
+        } else {
+            result[i] = (uint16_t)word;
+        }
     }
 }
 
@@ -1422,8 +1438,8 @@ static int packed_entry(qttt_state* state, const uint8_t* action_coin, uint16_t*
             k_step_packed_zc<false><<<chunk_grid(m, zc_iters), kThreads, 0, st>>>(state + lo, action_coin + lo, result + lo,
                                                                                    o, (uint32_t)m, zc_iters);
         else
-            k_step_packed<<<chunk_grid(m, iters), kThreads, 0, st>>>(state + lo, action_coin + lo, result + lo, o,
-                                                                      (uint32_t)m, iters);
+            k_step_packed<false><<<chunk_grid(m, iters), kThreads, 0, st>>>(state + lo, action_coin + lo, result + lo, o,
+                                                                             (uint32_t)m, iters);
         const int rc = check_launch();
         if (rc != QTTT_OK) return rc;
     }
@@ -1503,6 +1519,33 @@ int qttt_step_packed_host_obs(qttt_state* state, const uint8_t* action_coin_host
             e = cudaMemcpyAsync(obs_host + lo, state + lo, (size_t)m * sizeof(qttt_state), cudaMemcpyDeviceToHost, st);
             if (e != cudaSuccess) return -(1000 + (int)e);
         }
+    }
+    return QTTT_OK;
+}
+
+int qttt_step_packed12_host(qttt_state* state, const uint8_t* action_coin_host, uint16_t* result12_host,
+                            uint8_t* in_dev, uint16_t* out12_dev, int64_t n, int64_t slice,
+                            void* const* streams, int n_streams) {
+    if (n == 0) return QTTT_OK;
+    if (!state || !action_coin_host || !result12_host || !in_dev || !out12_dev || !streams || n < 0 ||
+        slice < 4 || (slice & 3) || slice > (1ll << 31) || n_streams < 1)
+        return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(out12_dev, 2) || misaligned(result12_host, 2)) return QTTT_ERR_ALIGN;
+    if (const int rc = device_ok()) return rc;
+    int k = 0;
+    for (int64_t lo = 0; lo < n; lo += slice, ++k) {
+        const int64_t m = n - lo < slice ? n - lo : slice;
+        const int64_t w0 = (lo / 4) * 3, words = ((m + 3) / 4) * 3;       // slices start on group boundaries
+        cudaStream_t st = (cudaStream_t)streams[k % n_streams];
+        cudaError_t e = cudaMemcpyAsync(in_dev + lo, action_coin_host + lo, (size_t)m, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return -(1000 + (int)e);
+        const int iters = iters_for(m, step_iters());
+        k_step_packed<true><<<chunk_grid(m, iters), kThreads, 0, st>>>(state + lo, in_dev + lo, out12_dev + w0, nullptr,
+                                                                       (uint32_t)m, iters);
+        const int rc = check_launch();
+        if (rc != QTTT_OK) return rc;
+        e = cudaMemcpyAsync(result12_host + w0, out12_dev + w0, (size_t)words * 2, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return -(1000 + (int)e);
     }
     return QTTT_OK;
 }

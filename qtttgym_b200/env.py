@@ -298,20 +298,43 @@ class BatchedEnv:
                 cur.wait_event(fin)
         return reward_host, done_host, mask_host
 
-    def step_host_packed12(self, action_coin_host, result12_host):
-        """``step_host_packed(..., mapped=True)`` with the result words bit-packed
-        (``qttt_step_packed12_mapped``): 12 bits per env, four envs in three 16-bit words, so 1.5
-        instead of 2 bytes per env come back across PCIe -- the direction that bounds the
-        host-resident caller.  ``result12_host``: pinned int16[3 * ceil(N / 4)]; decode with
-        ``unpack_result12(result12_host, N)``.  Same transition, bit for bit."""
+    def step_host_packed12(self, action_coin_host, result12_host, mapped: bool = True, chunks: int = 8,
+                           n_streams: int = 4):
+        """``step_host_packed`` with the result words bit-packed: 12 bits per env, four envs in
+        three 16-bit words, so 1.5 instead of 2 bytes per env come back across PCIe -- the direction
+        that bounds the host-resident caller.  ``result12_host``: pinned int16[3 * ceil(N / 4)];
+        decode with ``unpack_result12(result12_host, N)``.  ``mapped=True``
+        (``qttt_step_packed12_mapped``): one launch reads / writes the pinned buffers itself;
+        ``mapped=False`` (``qttt_step_packed12_host``): slices pipelined over side streams with
+        explicit ``cudaMemcpyAsync`` copies.  Same transition, bit for bit."""
         n, dev = self.num_envs, self.device
         words = 3 * ((n + 3) // 4)
         for t, dt, numel in ((action_coin_host, torch.uint8, n), (result12_host, torch.int16, words)):
             if t.dtype != dt or t.numel() != numel or t.device.type != "cpu" or not t.is_contiguous() or not t.is_pinned():
                 raise ValueError("step_host_packed12 expects pinned contiguous CPU uint8[N] / int16[3*ceil(N/4)] tensors")
+        if mapped:
+            with torch.cuda.device(dev):
+                _lib.check(self.lib.qttt_step_packed12_mapped(
+                    self.state.data_ptr(), action_coin_host.data_ptr(), result12_host.data_ptr(), n, _stream_ptr(dev)))
+            return result12_host
+        streams = self._host_pipeline(n_streams)
+        cur = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        per = self._slices(chunks)                    # a multiple of 256, hence of 4
+        if getattr(self, "_d_res12", None) is None:
+            self._d_res12 = torch.empty(words, dtype=torch.int16, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(self.lib.qttt_step_packed12_mapped(
-                self.state.data_ptr(), action_coin_host.data_ptr(), result12_host.data_ptr(), n, _stream_ptr(dev)))
+            for st in streams:
+                st.wait_event(ready)
+            _lib.check(self.lib.qttt_step_packed12_host(
+                self.state.data_ptr(), action_coin_host.data_ptr(), result12_host.data_ptr(),
+                self._d_act.data_ptr(), self._d_res12.data_ptr(), n, per, self._stream_array, n_streams),
+                launches=-(-n // per))
+            for st in streams:
+                fin = torch.cuda.Event()
+                fin.record(st)
+                cur.wait_event(fin)
         return result12_host
 
     def step_host_packed(self, action_coin_host, result_host, obs_host=None, chunks: int = 8,

@@ -344,9 +344,9 @@ class CudaGames:
         (the kernel reads/writes the pinned host buffers itself), "mapped_obs", "mapped12" (bit-packed results)."""
         t = self.torch
         ac = t.from_numpy(np.ascontiguousarray(action_coin, np.uint8)).pin_memory()
-        if variant == "mapped12":        # 12-bit results, four envs in three words
+        if variant in ("mapped12", "copy12"):        # 12-bit results, four envs in three words
             res12 = t.full((3 * ((self.n + 3) // 4),), -1, dtype=t.int16).pin_memory()
-            self.env.step_host_packed12(ac, res12)
+            self.env.step_host_packed12(ac, res12, mapped=(variant == "mapped12"), chunks=3, n_streams=2)
             t.cuda.synchronize()
             return self.Q.unpack_result12(res12, self.n).numpy().view(np.uint16).copy()
         res = t.empty(self.n, dtype=t.int16).pin_memory()

@@ -351,6 +351,7 @@ def test_packed12_step_host(cuda, n):
     """bit-packed results (12 bits per env, four envs in three words): sizes that are not
     multiples of 4 / 256 / the block span, and one that is"""
     S.check_packed_step(cuda, n, variant="mapped12")
+    S.check_packed_step(cuda, n, variant="copy12")
 
 
 @pytest.mark.parametrize("variant", ["copy_obs", "mapped", "mapped_obs"])
