@@ -164,6 +164,23 @@ QTTT_API int qttt_step_packed12_host(qttt_state* state, const uint8_t* action_co
                                      uint16_t* result12_host, uint8_t* in_dev, uint16_t* out12_dev,
                                      int64_t n, int64_t slice, void* const* streams, int n_streams);
 
+/* Env.step for a host-resident caller that wants the OBSERVATION back (env.py:34-53,68-85) at 12
+ * bytes per game instead of 18 (16-byte packed state + result word): after the step the kernel
+ * writes one record of three 32-bit words per game into obs12_dev (uint32[n][3], device staging),
+ * and each slice is copied to obs12_host (pinned) -- pipelined over `streams` like
+ * qttt_step_packed_host.
+ *   word 0  classical squares 0..7, 4 bits each: owning move index + 1, 0 = not classical
+ *   word 1  square 8 (bits 0-3) | move slots 0..3, 6 bits each from bit 4 |
+ *           terminated (28) | line, i.e. reward -1.0 (29) | illegal no-op (30)
+ *   word 2  move slots 4..8, 6 bits each
+ * A slot holds the action index (0..35, mcts.py:339-349) of an UNCOLLAPSED move and 63 otherwise:
+ * the even slots in order are obs["q_states_p1"], the odd ones obs["q_states_p2"];
+ * obs["turn"] = (classical squares + uncollapsed moves) % 2; the legal mask follows from the free
+ * squares. */
+QTTT_API int qttt_step_packed_host_obs12(qttt_state* state, const uint8_t* action_coin_host,
+                                         uint32_t* obs12_host, uint8_t* in_dev, uint32_t* obs12_dev,
+                                         int64_t n, int64_t slice, void* const* streams, int n_streams);
+
 /* The host-buffer form of qttt_step_packed: action_coin_host / result_host are PINNED HOST
  * arrays; in_dev (uint8[n]) / out_dev (uint16[n]) are caller-provided device staging buffers.
  * The batch is cut into slices of `slice` games; slice k is copied in, stepped and copied out

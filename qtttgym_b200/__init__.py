@@ -12,7 +12,7 @@ from .arena import (BatchedStrategy, MCTSStrategy, RandomStrategy, RolloutStrate
                     play_games)
 from .actions import NUM_ACTIONS, PAIRS, ind2move, move2ind
 from .env import (BatchedEnv, Env, get_mask, observe_states, pack_actions, pack_states, render_states, render_text,
-                  to_vector, unpack_result, unpack_result12)
+                  to_vector, unpack_obs12, unpack_result, unpack_result12)
 from .mcts import BatchedMCTS
 from .qeval import QEvalB200, qeval_both, square_probabilities
 from .vector import VectorEnv
@@ -20,7 +20,7 @@ from .rollout import STAT_NAMES, rollout_eval, selfplay_sweep, shard_range, shar
 
 __all__ = [
     "NUM_ACTIONS", "PAIRS", "ind2move", "move2ind",
-    "BatchedEnv", "Env", "observe_states", "pack_states", "pack_actions", "unpack_result", "unpack_result12",
+    "BatchedEnv", "Env", "observe_states", "pack_states", "pack_actions", "unpack_result", "unpack_result12", "unpack_obs12",
     "to_vector", "get_mask", "render_text", "render_states",
     "VectorEnv", "BatchedMCTS", "QEvalB200", "qeval_both", "square_probabilities",
     "BatchedStrategy", "MCTSStrategy", "RandomStrategy", "RolloutStrategy", "eval_strats", "play_games",

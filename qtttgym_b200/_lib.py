@@ -28,6 +28,7 @@ _SIGNATURES = {
     "qttt_step_packed_obs": ([_vp, _vp, _vp, _vp, _i64, _vp], _int),
     "qttt_step_packed_mapped": ([_vp, _vp, _vp, _vp, _i64, _vp], _int),
     "qttt_step_packed12_mapped": ([_vp, _vp, _vp, _i64, _vp], _int),
+    "qttt_step_packed_host_obs12": ([_vp, _vp, _vp, _vp, _vp, _i64, _i64, C.POINTER(C.c_void_p), _int], _int),
     "qttt_step_packed12_host": ([_vp, _vp, _vp, _vp, _vp, _i64, _i64, C.POINTER(C.c_void_p), _int], _int),
     "qttt_step_packed_host": ([_vp, _vp, _vp, _vp, _vp, _i64, _i64, C.POINTER(C.c_void_p), _int], _int),
     "qttt_step_packed_host_obs": ([_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, C.POINTER(C.c_void_p), _int], _int),

@@ -287,6 +287,58 @@ k_step_packed(qttt_state* __restrict__ state, const uint8_t* __restrict__ action
 // 16-byte loads and its 256 result words out as thirty-two 16-byte stores, so every PCIe
 // transaction is a full 512-byte burst; the observation (16 B per game) is written by each
 // thread directly (512 contiguous bytes per warp).
+// Env.step for a host-resident caller that wants the OBSERVATION back: the step, then the env.py
+// observation (env.py:68-85) and the step's flags as one 12-byte record per game instead of the
+// 16-byte packed state plus a result word -- what crosses PCIe is what bounds that caller.
+//   word 0: classical squares 0..7, 4 bits each: owning move index + 1, 0 = free
+//   word 1: square 8 (bits 0-3) | slots 0..3, 6 bits each from bit 4 | terminated 28 | line 29 | illegal 30
+//   word 2: slots 4..8, 6 bits each
+// A slot holds the action index (mcts.py:339-349) of an UNCOLLAPSED move, 63 otherwise: exactly the
+// moves env.py lists in q_states_p1 (even slots) / q_states_p2 (odd slots); turn = len(moves) % 2
+// with len(moves) = classical squares + uncollapsed moves.
+__device__ __forceinline__ uint32_t live_move_code(uint32_t E, uint32_t free_sq) {
+    if ((E & free_sq) == 0u) return 63u;
+    const uint32_t a = (uint32_t)ctz32(E), b = (uint32_t)flo32(E);
+    return (15u * a - a * a + 2u * b - 2u) >> 1;                          // move2ind, mcts.py:345-349
+}
+__global__ void __launch_bounds__(kThreads)
+k_step_packed_obs12(qttt_state* __restrict__ state, const uint8_t* __restrict__ action_coin,
+                    uint32_t* __restrict__ obs12, uint32_t n, int iters) {
+    __shared__ __align__(16) uint8_t smem[kLutQevalBytes];
+    stage_luts(smem, kLutQevalBytes);
+    const Luts L = luts_from_image(smem);
+    const uint32_t first = (blockIdx.x * (uint32_t)iters) * kThreads + threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+        const uint32_t i = first + (uint32_t)it * kThreads;
+        if (i >= n) break;
+        uint4* sp = reinterpret_cast<uint4*>(state + i);
+        const uint4 sv = *sp;
+        State s{sv.x, sv.y, sv.z, sv.w};
+        const uint32_t ac = action_coin[i];
+        const StepResult r = step_core(s, (uint32_t)L.pair[ac & 63u], ac >> 7, L);
+        if (!r.illegal) *sp = make_uint4(s.x, s.y, s.z, s.w);
+        const uint32_t win = any_line(s, r.classical, L) != 0u;
+        const uint32_t term = win | (uint32_t)(r.n > 8u);
+        const uint64_t nib = board_nibbles(s, L);
+        const uint32_t free_sq = ~r.classical & M9;
+        uint32_t w1 = (uint32_t)(nib >> 32) & 15u, w2 = 0u;
+        w1 |= live_move_code(edge<0>(s), free_sq) << 4;
+        w1 |= live_move_code(edge<1>(s), free_sq) << 10;
+        w1 |= live_move_code(edge<2>(s), free_sq) << 16;
+        w1 |= live_move_code(edge<3>(s), free_sq) << 22;
+        w1 |= (term << 28) | (win << 29) | (r.illegal << 30);
+        w2 |= live_move_code(edge<4>(s), free_sq);
+        w2 |= live_move_code(edge<5>(s), free_sq) << 6;
+        w2 |= live_move_code(edge<6>(s), free_sq) << 12;
+        w2 |= live_move_code(edge<7>(s), free_sq) << 18;
+        w2 |= live_move_code(edge<8>(s), free_sq) << 24;
+        uint32_t* o = obs12 + 3ull * i;
+        o[0] = (uint32_t)nib;
+        o[1] = w1;
+        o[2] = w2;
+    }
+}
+
 // kPack12: the result words carry 12 bits each (free-square set, terminated, line, illegal), so
 // four games' results leave as THREE 16-bit words -- word k of a group holds game k's result in
 // its low 12 bits and nibble k of game 3's result on top: 1.5 bytes per game cross the link.
@@ -1545,6 +1597,32 @@ int qttt_step_packed12_host(qttt_state* state, const uint8_t* action_coin_host, 
         const int rc = check_launch();
         if (rc != QTTT_OK) return rc;
         e = cudaMemcpyAsync(result12_host + w0, out12_dev + w0, (size_t)words * 2, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return -(1000 + (int)e);
+    }
+    return QTTT_OK;
+}
+
+int qttt_step_packed_host_obs12(qttt_state* state, const uint8_t* action_coin_host, uint32_t* obs12_host,
+                                uint8_t* in_dev, uint32_t* obs12_dev, int64_t n, int64_t slice,
+                                void* const* streams, int n_streams) {
+    if (n == 0) return QTTT_OK;
+    if (!state || !action_coin_host || !obs12_host || !in_dev || !obs12_dev || !streams || n < 0 ||
+        slice < 1 || slice > (1ll << 31) || n_streams < 1)
+        return QTTT_ERR_ARG;
+    if (misaligned(state, 16) || misaligned(obs12_dev, 4) || misaligned(obs12_host, 4)) return QTTT_ERR_ALIGN;
+    if (const int rc = device_ok()) return rc;
+    int k = 0;
+    for (int64_t lo = 0; lo < n; lo += slice, ++k) {
+        const int64_t m = n - lo < slice ? n - lo : slice;
+        cudaStream_t st = (cudaStream_t)streams[k % n_streams];
+        cudaError_t e = cudaMemcpyAsync(in_dev + lo, action_coin_host + lo, (size_t)m, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return -(1000 + (int)e);
+        const int iters = iters_for(m, step_iters());
+        k_step_packed_obs12<<<chunk_grid(m, iters), kThreads, 0, st>>>(state + lo, in_dev + lo, obs12_dev + 3 * lo,
+                                                                       (uint32_t)m, iters);
+        const int rc = check_launch();
+        if (rc != QTTT_OK) return rc;
+        e = cudaMemcpyAsync(obs12_host + 3 * lo, obs12_dev + 3 * lo, (size_t)m * 12, cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return -(1000 + (int)e);
     }
     return QTTT_OK;

@@ -337,6 +337,37 @@ class BatchedEnv:
                 cur.wait_event(fin)
         return result12_host
 
+    def step_host_obs12(self, action_coin_host, obs12_host, chunks: int = 8, n_streams: int = 4):
+        """``step_host_packed`` returning the OBSERVATION in compact form
+        (``qttt_step_packed_host_obs12``): one 12-byte record per env -- the env.py observation
+        (classical squares, the uncollapsed moves of both players, hence ``turn``) plus the
+        terminated / line / illegal flags -- instead of the 16-byte packed state and a result word.
+        ``obs12_host``: pinned int32[N,3]; ``unpack_obs12`` decodes it into what ``step`` and
+        ``observation()`` return.  Same transition, bit for bit."""
+        n, dev = self.num_envs, self.device
+        for t, dt, numel in ((action_coin_host, torch.uint8, n), (obs12_host, torch.int32, 3 * n)):
+            if t.dtype != dt or t.numel() != numel or t.device.type != "cpu" or not t.is_contiguous():
+                raise ValueError("step_host_obs12 expects contiguous CPU uint8[N] / int32[N,3] tensors")
+        streams = self._host_pipeline(n_streams)
+        cur = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        per = self._slices(chunks)
+        if getattr(self, "_d_obs12", None) is None:
+            self._d_obs12 = torch.empty((n, 3), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            for st in streams:
+                st.wait_event(ready)
+            _lib.check(self.lib.qttt_step_packed_host_obs12(
+                self.state.data_ptr(), action_coin_host.data_ptr(), obs12_host.data_ptr(),
+                self._d_act.data_ptr(), self._d_obs12.data_ptr(), n, per, self._stream_array, n_streams),
+                launches=-(-n // per))
+            for st in streams:
+                fin = torch.cuda.Event()
+                fin.record(st)
+                cur.wait_event(fin)
+        return obs12_host
+
     def step_host_packed(self, action_coin_host, result_host, obs_host=None, chunks: int = 8,
                          n_streams: int = 4, mapped: bool = False):
         """``step_host`` with compact I/O: 1 byte in and 2 bytes out per env cross PCIe instead of
@@ -599,6 +630,40 @@ def unpack_result(result):
     reward = torch.where(win, neg_one, neg_zero)
     status = ((r >> 11) & 3).to(torch.uint8)
     return reward, terminated, mask, status
+
+
+def unpack_obs12(obs12):
+    """The 12-byte records of ``step_host_obs12`` (int32[N,3]) -> ``(obs, reward, terminated, mask,
+    status)``: ``obs`` = ``classical`` int8[N,9], ``q_states_p1`` int8[N,5,2], ``q_states_p2``
+    int8[N,4,2] (padded with -1), ``turn`` uint8[N] as ``observation()`` returns them; the rest as
+    ``unpack_result``.  Runs wherever ``obs12`` lives (the host, normally)."""
+    dev = obs12.device
+    w = obs12.to(torch.int64) & 0xFFFFFFFF
+    w0, w1, w2 = w[:, 0], w[:, 1], w[:, 2]
+    n = w.shape[0]
+    nib = torch.stack([(w0 >> (4 * k)) & 15 for k in range(8)] + [w1 & 15], dim=1)          # value = owner + 1
+    classical = (nib - 1).to(torch.int8)
+    codes = torch.stack([(w1 >> (4 + 6 * k)) & 63 for k in range(4)] + [(w2 >> (6 * k)) & 63 for k in range(5)], dim=1)
+    pairs = torch.full((64, 2), -1, dtype=torch.int8, device=dev)
+    pairs[:36] = torch.tensor(PAIRS, dtype=torch.int8, device=dev)
+
+    def qlist(slots, width):
+        c = codes[:, slots]
+        live = c < 36
+        order = torch.sort((~live).to(torch.int8), dim=1, stable=True).indices     # live entries first, in slot order
+        c = torch.where(live, c, torch.full_like(c, 63)).gather(1, order)
+        return pairs[c][:, :width]
+    q1, q2 = qlist([0, 2, 4, 6, 8], 5), qlist([1, 3, 5, 7], 4)
+    n_moves = (nib != 0).sum(1) + (codes < 36).sum(1)
+    obs = {"classical": classical, "q_states_p1": q1.contiguous(), "q_states_p2": q2.contiguous(),
+           "turn": (n_moves & 1).to(torch.uint8)}
+    free = ((nib == 0).to(torch.int64) << torch.arange(9, device=dev)).sum(1)
+    mask = _legal_table(dev)[free]
+    terminated = ((w1 >> 28) & 1).bool()
+    win = ((w1 >> 29) & 1).bool()
+    reward = torch.where(win, torch.tensor(-1.0, device=dev), torch.tensor(-0.0, device=dev))
+    status = ((w1 >> 30) & 1).to(torch.uint8)
+    return obs, reward, terminated, mask, status
 
 
 def unpack_result12(result12, n: int):

@@ -26,7 +26,7 @@ def built_lib():
 def test_header_declares_the_expected_surface():
     assert _declared_symbols() == {
         "qttt_abi_version", "qttt_strerror", "qttt_reset", "qttt_reset_all", "qttt_reset_step", "qttt_step", "qttt_step_ex",
-        "qttt_step_packed", "qttt_step_packed_obs", "qttt_step_packed_mapped", "qttt_step_packed12_mapped", "qttt_step_packed12_host", "qttt_step_packed_host",
+        "qttt_step_packed", "qttt_step_packed_obs", "qttt_step_packed_mapped", "qttt_step_packed12_mapped", "qttt_step_packed12_host", "qttt_step_packed_host_obs12", "qttt_step_packed_host",
         "qttt_step_packed_host_obs", "qttt_step_random", "qttt_step_random_ex",
         "qttt_observe", "qttt_features", "qttt_env1", "qttt_qeval1", "qttt_get_mask", "qttt_step_features", "qttt_step_obs", "qttt_pack", "qttt_qeval_both", "qttt_rollout", "qttt_sweep",
         "qttt_mcts_node_bytes", "qttt_mcts_init", "qttt_mcts_run", "qttt_mcts_stats", "qttt_mcts_sync"}

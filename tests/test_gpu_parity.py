@@ -354,6 +354,35 @@ def test_packed12_step_host(cuda, n):
     S.check_packed_step(cuda, n, variant="copy12")
 
 
+@pytest.mark.parametrize("n", [1, 777, 40_003])
+def test_step_host_obs12_equals_step_and_observation(cuda, n):
+    """The 12-byte observation records (qttt_step_packed_host_obs12 + unpack_obs12) carry exactly what
+    step() and observation() return: games played to the end and beyond, some illegal actions."""
+    import torch
+    import qtttgym_b200 as Q
+    a, b = Q.BatchedEnv(n, seed=4), Q.BatchedEnv(n, seed=4)
+    a.reset(), b.reset()
+    rec = torch.empty((n, 3), dtype=torch.int32).pin_memory()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for ply in range(11):
+        legal = b.action_mask().float()
+        legal[legal.sum(1) == 0, 0] = 1.0
+        act = torch.multinomial(legal, 1, generator=g).squeeze(1).to(torch.uint8)
+        bad = torch.rand(n, device="cuda", generator=g) < 0.06
+        act = torch.where(bad, torch.randint(0, 36, (n,), device="cuda", generator=g).to(torch.uint8), act)
+        coin = torch.randint(0, 2, (n,), device="cuda", generator=g).to(torch.uint8)
+        _, reward, term, _, info = b.step(act, coin)
+        want = b.observation()
+        a.step_host_obs12(Q.pack_actions(act, coin).cpu().pin_memory(), rec, chunks=3, n_streams=2)
+        torch.cuda.synchronize()
+        obs, r2, t2, m2, s2 = Q.unpack_obs12(rec)
+        assert torch.equal(a.state, b.state), ply
+        for k in want:
+            assert torch.equal(obs[k], want[k].cpu()), (ply, k)
+        assert torch.equal(r2.view(torch.int32), reward.cpu().view(torch.int32)) and torch.equal(t2, term.cpu()), ply
+        assert torch.equal(m2, info["action_mask"].cpu()) and torch.equal(s2, (info["status"] & 1).cpu()), ply
+
+
 @pytest.mark.parametrize("variant", ["copy_obs", "mapped", "mapped_obs"])
 def test_packed_step_host_variants(cuda, variant):
     """the observation coming back with the result words, and the zero-copy path (the kernel
