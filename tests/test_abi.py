@@ -133,3 +133,27 @@ def test_unpack_result12_is_the_inverse_of_the_kernel_packing():
                       pad[:, 2] | (((pad[:, 3] >> 8) & 15) << 12)], 1).astype(np.uint16).reshape(-1)
         got = unpack_result12(torch.from_numpy(w.view(np.int16).copy()), n).numpy().view(np.uint16)
         assert np.array_equal(got.astype(np.uint32), r)
+
+
+def test_unpack_obs12_decodes_a_hand_built_record():
+    """host-side decode of the 12-byte observation records (pure torch, no GPU)"""
+    import torch
+    from qtttgym_b200.env import unpack_obs12
+
+    def ind(a, b):
+        return (15 * a - a * a + 2 * b - 2) // 2
+    # squares 0, 1, 2 classical (owners 2, 0, 1); uncollapsed: move 3 = (3, 4) [O], move 4 = (5, 6) [X];
+    # flags: illegal no-op
+    codes = [63] * 9
+    codes[3], codes[4] = ind(3, 4), ind(5, 6)
+    w0 = 3 | (1 << 4) | (2 << 8)
+    w1 = sum(codes[k] << (4 + 6 * k) for k in range(4)) | (1 << 30)
+    w2 = sum(codes[4 + k] << (6 * k) for k in range(5))
+    rec = torch.tensor([[w0, w1, w2]], dtype=torch.int64).to(torch.int32)
+    obs, reward, term, mask, status = unpack_obs12(rec)
+    assert obs["classical"].tolist() == [[2, 0, 1, -1, -1, -1, -1, -1, -1]]
+    assert obs["q_states_p1"].tolist() == [[[5, 6]] + [[-1, -1]] * 4]
+    assert obs["q_states_p2"].tolist() == [[[3, 4]] + [[-1, -1]] * 3]
+    assert obs["turn"].tolist() == [1] and term.tolist() == [False] and status.tolist() == [1]
+    assert reward.view(torch.int32).tolist() == [-(1 << 31)]          # -0.0
+    assert bin(int(mask[0])).count("1") == 15                          # pairs of the 6 free squares
